@@ -1,0 +1,186 @@
+/*
+ * qexxc.h -- C ABI of libqexxc.so: the B200 (sm_100a) implementation of QEX's 3D Kohn-Sham
+ * exchange-correlation (XC) grid-integration hot path, forward and reverse mode.
+ *
+ * The reference (pasqal-io/qex, Python package `qedft`) has no native/FFI interface: its boundary
+ * for this path is four Python call signatures.  Each entry point below
+ * cites the reference function it stands in for (paths relative to the reference tree).  The
+ * Python host side (qex_b200/) binds these with ctypes; qex_b200/jax_ffi_shim.py shows the
+ * jax.ffi / jax.custom_vjp registration a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative QEXXC_ERR_* code; qexxc_last_error()
+ *     returns a thread-local human-readable message.  Nothing throws, nothing aborts.
+ *   - `*_dev` pointers are device pointers on the context's device; all arrays are float64,
+ *     C-order, unpadded (the library keeps its own padded copies).  `stream` is a cudaStream_t
+ *     passed as void*; all work is enqueued on it and no call synchronises the device unless
+ *     stated.  No hot call allocates: all workspaces are sized in qexxc_create().
+ *   - B = batch of independent molecules with identical (nao, ngrids_max, basis structure);
+ *     arrays carry a leading [B] dimension.  theta (network parameters) is shared by the batch
+ *     and theta_bar is summed over it.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef QEXXC_H
+#define QEXXC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QEXXC_VERSION 100
+
+#define QEXXC_OK 0
+#define QEXXC_ERR_CUDA (-1)        /* a CUDA runtime call or kernel launch failed */
+#define QEXXC_ERR_ARG (-2)         /* bad argument (null pointer, size out of range) */
+#define QEXXC_ERR_STATE (-3)       /* call order violated (e.g. no AO set before nr_rks) */
+#define QEXXC_ERR_UNSUPPORTED (-4) /* mirrors the reference's NotImplementedError / ValueError */
+#define QEXXC_ERR_NODEVICE (-5)    /* no CUDA device: there is no CPU fallback */
+
+/* xctype: the branch of nr_rks (qedft/train/td/numint_legacy.py:134-140) */
+#define QEXXC_XC_NN 0        /* "NN": local functional, LDA features (numint_legacy.py:290-310) */
+#define QEXXC_XC_NN_GLOBAL 1 /* "NN-AmplitudeEncoding": global functional (numint_legacy.py:311-334) */
+#define QEXXC_XC_GGA 2       /* "GGA" assembly (numint_legacy.py:175-198) with features (rho, sigma) */
+
+/* network kinds (qedft/models/networks.py) */
+#define QEXXC_NET_NONE 0       /* exc/vrho supplied by the caller (host eval_xc callback) */
+#define QEXXC_NET_LOCAL_MLP 1  /* LocalMLP networks.py:83-109, classical_models.py:123-174 */
+#define QEXXC_NET_GLOBAL_MLP 2 /* GlobalMLP networks.py:112-138, classical_models.py:177-224 */
+#define QEXXC_NET_LOCAL_QNN 3  /* LocalQNN networks.py:180-228, quantum_models.py:115-157 */
+
+/* activations (classical_models.py:39-49 ACTIVATION_MAP; swish for the flax MLP trainer :96-107) */
+#define QEXXC_ACT_TANH 0
+#define QEXXC_ACT_RELU 1
+#define QEXXC_ACT_SOFTPLUS 2
+#define QEXXC_ACT_SIGMOID 3
+#define QEXXC_ACT_ELU 4
+#define QEXXC_ACT_LEAKY_RELU 5
+#define QEXXC_ACT_SELU 6
+#define QEXXC_ACT_GELU 7
+#define QEXXC_ACT_SWISH 8
+
+#define QEXXC_PREC_F64 0
+#define QEXXC_PREC_F32 1
+
+#define QEXXC_MAX_LAYERS 8
+
+typedef struct qexxc_net_desc {
+    int kind;          /* QEXXC_NET_* */
+    int n_features;    /* MLP: inputs per point (1 = rho, 2 = rho,sigma); global MLP: ignored (= ngrids) */
+    int n_hidden;      /* MLP: number of hidden Dense+activation pairs; QNN: ansatz layers */
+    int width;         /* MLP: neurons per hidden layer; QNN: number of qubits */
+    int activation;    /* QEXXC_ACT_* */
+    int out_transform; /* 0 none; 1 = -out_scale*swish(.) (flax MLP, trainer_legacy_no_jit.py:107) */
+    int precision;     /* QEXXC_PREC_F64 (reference runs jax_enable_x64) or QEXXC_PREC_F32 */
+    int reserved;
+    double in_scale;   /* 1/density_normalization_factor (classical_models.py:169); QNN: 1.0 */
+    double out_scale;  /* 1e-2 for the flax MLP */
+} qexxc_net_desc;
+
+typedef struct qexxc_ctx qexxc_ctx;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int qexxc_version(void);
+const char* qexxc_last_error(void);
+/* number of network parameters (flat theta length) for a descriptor; global MLP needs ngrids */
+long qexxc_n_params(const qexxc_net_desc* net, int ngrids);
+/* Allocates every workspace for problems up to (nbatch, ncomp, ngrids_max, nao).  ncomp = 1
+ * (AO values, "LDA"/"NN") or 4 (values + gradient, "GGA").  Replaces nothing in the reference
+ * (JAX allocates implicitly); it is the price of "no allocation on the hot call". */
+int qexxc_create(qexxc_ctx** ctx, int device, int nbatch, int ncomp, int ngrids_max, int nao,
+                 const qexxc_net_desc* net);
+int qexxc_destroy(qexxc_ctx* ctx);
+/* bytes of device memory held by the context */
+size_t qexxc_workspace_bytes(const qexxc_ctx* ctx);
+
+/* ---- stage 1: grid + AO values ------------------------------------------------------------
+ * qexxc_set_grid: grids.coords [B][G][3], grids.weights [B][G] (device), as yielded by pyscf
+ *   block_loop (numint_legacy.py:292).  G <= ngrids_max.
+ * qexxc_set_basis: libcint tables mol._atm [natm][6], mol._bas [nbas][8] (HOST int32) and
+ *   mol._env [B][nenv] (HOST float64; per-batch geometry) -- what pyscf's eval_gto reads
+ *   (qedft/train/td/eval_gto.py:48-70).  Spherical shells, l <= 3.
+ * qexxc_eval_ao: K1 -- replaces numint.eval_ao / block_loop's eval_ao (numint_legacy.py:292,313;
+ *   trainer_legacy_no_jit.py:273): fills the context's AO tensor from basis + grid.
+ * qexxc_set_ao: alternative to K1: upload pre-evaluated AO [B][C][G][N] (e.g. from pyscf).
+ * qexxc_get_ao: copy the AO tensor out as [B][C][G][N] (eval_ao's return value). */
+int qexxc_set_grid(qexxc_ctx* ctx, const double* coords_dev, const double* weights_dev, int ngrids,
+                   void* stream);
+int qexxc_set_basis(qexxc_ctx* ctx, const int* atm, int natm, const int* bas, int nbas,
+                    const double* env, int nenv);
+int qexxc_eval_ao(qexxc_ctx* ctx, int deriv, void* stream);
+int qexxc_set_ao(qexxc_ctx* ctx, const double* ao_dev, int ncomp, int ngrids, void* stream);
+int qexxc_get_ao(qexxc_ctx* ctx, double* ao_dev, int ncomp, void* stream);
+
+/* ---- stage 2: density on the grid ----------------------------------------------------------
+ * eval_rho(mol, ao, dm, non0tab, xctype, hermi) numint_legacy.py:351-397.  dm [B][N][N];
+ * rho out [B][C][G] with C = 1 ("LDA") or 4 ("GGA": rho, 2<c0,d_x ao>, ...).  hermi=0
+ * symmetrises dm first (:362-365).  The VJP maps rho_bar [B][C][G] -> dm_bar [B][N][N]. */
+int qexxc_eval_rho(qexxc_ctx* ctx, const double* dm_dev, int ncomp, int hermi, double* rho_dev,
+                   void* stream);
+int qexxc_eval_rho_vjp(qexxc_ctx* ctx, const double* rho_bar_dev, int ncomp, int hermi,
+                       double* dm_bar_dev, void* stream);
+
+/* ---- stage 3: the learned XC functional -----------------------------------------------------
+ * qexxc_xc_fwd: eval_xc(..., rho, ..., params) trainer_legacy_no_jit.py:76-93 ->
+ *   exc_and_vrho_local :56-63 (xctype NN: exc [B][G], vrho [B][G]),
+ *   exc_and_vrho_global :46-53 (xctype NN_GLOBAL: exc [B] scalars, vrho [B][G]),
+ *   GGA extension (xctype GGA: rho [B][4][G] in; exc [B][G], vrho [B][G], vgamma [B][G]).
+ * qexxc_xc_vjp: reverse rule of the above w.r.t. (rho, theta): cotangents exc_bar, vrho_bar
+ *   (, vgamma_bar) -> rho_bar [B][C][G], theta_bar [n_params] (summed over batch and grid).
+ * qexxc_apply_fn_fwd/_vjp: network apply_fn(params, inputs) (networks.py:43-75;
+ *   classical_models.py:168-172; quantum_models.py:759-774): x [npts][n_features] -> y [npts]
+ *   (global MLP: x [ngrids] -> y [1]); VJP: y_bar -> x_bar, theta_bar. */
+int qexxc_xc_fwd(qexxc_ctx* ctx, int xctype, const double* rho_dev, const double* theta_dev,
+                 double* exc_dev, double* vrho_dev, double* vgamma_dev, void* stream);
+int qexxc_xc_vjp(qexxc_ctx* ctx, int xctype, const double* rho_dev, const double* theta_dev,
+                 const double* exc_bar_dev, const double* vrho_bar_dev,
+                 const double* vgamma_bar_dev, double* rho_bar_dev, double* theta_bar_dev,
+                 void* stream);
+int qexxc_apply_fn_fwd(qexxc_ctx* ctx, const double* x_dev, long npts, const double* theta_dev,
+                       double* y_dev, void* stream);
+int qexxc_apply_fn_vjp(qexxc_ctx* ctx, const double* x_dev, long npts, const double* theta_dev,
+                       const double* y_bar_dev, double* x_bar_dev, double* theta_bar_dev,
+                       void* stream);
+
+/* ---- stage 4: E_xc, nelec, V_xc from caller-supplied (exc, vxc) ------------------------------
+ * The body of the nr_rks block loop after eval_xc (numint_legacy.py:304-309 / :328-333 /
+ * :189-197) plus vmat + vmat.T (:336-337), for functionals evaluated by a host callback.
+ * out [B][N*N + 2] = vmat (N*N, C-order) | excsum | nelec.  exc: [B][G] (NN, GGA) or [B] (global).
+ * The VJP returns the cotangents of (rho, exc, vrho, vgamma) given (e_bar [B], v_bar [B][N][N]). */
+int qexxc_vxc_assemble(qexxc_ctx* ctx, int xctype, const double* rho_dev, const double* exc_dev,
+                       const double* vrho_dev, const double* vgamma_dev, double* out_dev,
+                       void* stream);
+int qexxc_vxc_assemble_vjp(qexxc_ctx* ctx, int xctype, const double* rho_dev,
+                           const double* exc_dev, const double* vrho_dev,
+                           const double* vgamma_dev, const double* e_bar_dev,
+                           const double* v_bar_dev, double* rho_bar_dev, double* exc_bar_dev,
+                           double* vrho_bar_dev, double* vgamma_bar_dev, void* stream);
+
+/* ---- the fused hot path --------------------------------------------------------------------
+ * qexxc_nr_rks_fwd: NumInt.nr_rks(mol, grids, xc_code, dms, hermi, params=params)
+ *   numint_legacy.py:122-348 for one dm per batch element (nset == 1), with the context's
+ *   network as ni.eval_xc.  out [B][N*N + 2] = vmat | excsum | nelec (one packed buffer so a
+ *   multi-GPU caller all-reduces it in a single collective).  resid (nullable) receives the
+ *   residuals the reverse pass needs: qexxc_resid_doubles(ctx) float64.
+ * qexxc_nr_rks_vjp: reverse rule JAX derives for the above under jax.value_and_grad
+ *   (trainer_legacy_no_jit.py:284): (e_bar [B], v_bar [B][N][N]) -> bar [B*N*N + n_params] =
+ *   dm_bar (B*N*N) | theta_bar (n_params, summed over batch); nelec is stop-gradient (:305). */
+size_t qexxc_resid_doubles(const qexxc_ctx* ctx);
+int qexxc_nr_rks_fwd(qexxc_ctx* ctx, int xctype, int hermi, const double* dm_dev,
+                     const double* theta_dev, double* out_dev, double* resid_dev, void* stream);
+int qexxc_nr_rks_vjp(qexxc_ctx* ctx, int xctype, int hermi, const double* theta_dev,
+                     const double* resid_dev, const double* e_bar_dev, const double* v_bar_dev,
+                     double* bar_dev, void* stream);
+
+/* ---- introspection for the benchmark -------------------------------------------------------
+ * Number of kernels this library launched on the context since creation (gpu_launches). */
+long qexxc_launch_count(const qexxc_ctx* ctx);
+/* Runs only the dominant contraction kernel once on the current AO/S buffers (roofline timing):
+ * which = 0 rowquad (rho-type), 1 wsyrk (vmat-type). */
+int qexxc_debug_run_contraction(qexxc_ctx* ctx, int which, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QEXXC_H */

@@ -1,0 +1,27 @@
+"""CPU oracle for the QEX 3D XC grid-integration hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``qex_b200/`` may import this package;
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs do.  It is a NumPy float64 restatement of the reference's
+pure-Python/JAX algorithm (pasqal-io/qex, package ``qedft``), each function citing
+the reference file:line it follows.
+
+PARITY PIN STATUS
+-----------------
+The reference cannot be executed in this environment (jax, pyscf, pyscfad, horqrux,
+flax are not installable: no network, not in the wheelhouse), and its own tests hold
+no golden vectors for this path.  What *is* pinned:
+
+* contraction / assembly conventions (``numint_ref``): pinned by the closed-form toy
+  functional of ``tests/test_numint.py:96-103`` (exc = 0.01 rho^2, vrho = 0.02 rho), by
+  the einsum restatement ``scf_functions_masked.py:143-159`` and by finite differences;
+* MLP / second-order VJP (``mlp_ref``): pinned by torch float64 double-autograd and
+  central finite differences (semantics of stax ``Dense``/``Tanh``/``Gelu`` are standard);
+* statevector circuit (``qnn_ref``): conventions pinned by the reference's known-answer
+  tests (``tests/test_measurements.py:31-61``, ``tests/test_quantum_measurement.py:46-59``);
+  gate matrices are the published horqrux 0.9.2 definitions -> circuit outputs
+  "parity unpinned";
+* AO evaluation (``gto_ref``): restates pyscf 2.9 ``GTOval_sph_deriv0/1`` (third-party C,
+  absent from /root/reference); pinned only by orthonormality (numerical overlap
+  integrals = identity for normalised shells) -> "parity unpinned".
+"""

@@ -1,0 +1,111 @@
+"""ctypes binding of libqexxc.so (the C ABI declared in include/qexxc.h).
+
+There is no fallback of any kind: if the shared library is missing or no CUDA device is
+visible, the compute entry points raise.  torch is used for device buffers and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libqexxc.so"
+
+# mirrors include/qexxc.h
+XC_NN, XC_NN_GLOBAL, XC_GGA = 0, 1, 2
+NET_NONE, NET_LOCAL_MLP, NET_GLOBAL_MLP, NET_LOCAL_QNN = 0, 1, 2, 3
+PREC_F64, PREC_F32 = 0, 1
+ACTIVATIONS = {
+    "tanh": 0, "relu": 1, "softplus": 2, "sigmoid": 3, "elu": 4, "leaky_relu": 5, "selu": 6, "gelu": 7, "swish": 8,
+}
+ERR_CUDA, ERR_ARG, ERR_STATE, ERR_UNSUPPORTED, ERR_NODEVICE = -1, -2, -3, -4, -5
+
+EXPORTS = [
+    "qexxc_version", "qexxc_last_error", "qexxc_n_params", "qexxc_create", "qexxc_destroy",
+    "qexxc_workspace_bytes", "qexxc_set_grid", "qexxc_set_basis", "qexxc_eval_ao", "qexxc_set_ao",
+    "qexxc_get_ao", "qexxc_eval_rho", "qexxc_eval_rho_vjp", "qexxc_xc_fwd", "qexxc_xc_vjp",
+    "qexxc_apply_fn_fwd", "qexxc_apply_fn_vjp", "qexxc_vxc_assemble", "qexxc_vxc_assemble_vjp",
+    "qexxc_resid_doubles", "qexxc_nr_rks_fwd", "qexxc_nr_rks_vjp", "qexxc_launch_count",
+    "qexxc_debug_run_contraction",
+]
+
+
+class NetDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("n_features", C.c_int), ("n_hidden", C.c_int), ("width", C.c_int),
+        ("activation", C.c_int), ("out_transform", C.c_int), ("precision", C.c_int), ("reserved", C.c_int),
+        ("in_scale", C.c_double), ("out_scale", C.c_double),
+    ]
+
+
+class QexxcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libqexxc error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = False):
+    """Load libqexxc.so (optionally compiling it first).  Raises if it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if build_if_missing or os.environ.get("QEXXC_AUTOBUILD") == "1":
+            from .build import build
+
+            build()
+        else:
+            raise FileNotFoundError(
+                f"{LIB_PATH} not found: run `python -m qex_b200.build` (nvcc, sm_100a). "
+                "There is no CPU/PyTorch fallback for this path."
+            )
+    lib = C.CDLL(str(LIB_PATH))
+    p, i, l, d, vp = C.c_void_p, C.c_int, C.c_long, C.c_double, C.c_void_p
+    sigs = {
+        "qexxc_version": (i, []),
+        "qexxc_last_error": (C.c_char_p, []),
+        "qexxc_n_params": (l, [C.POINTER(NetDesc), i]),
+        "qexxc_create": (i, [C.POINTER(vp), i, i, i, i, i, C.POINTER(NetDesc)]),
+        "qexxc_destroy": (i, [vp]),
+        "qexxc_workspace_bytes": (C.c_size_t, [vp]),
+        "qexxc_set_grid": (i, [vp, p, p, i, vp]),
+        "qexxc_set_basis": (i, [vp, p, i, p, i, p, i]),
+        "qexxc_eval_ao": (i, [vp, i, vp]),
+        "qexxc_set_ao": (i, [vp, p, i, i, vp]),
+        "qexxc_get_ao": (i, [vp, p, i, vp]),
+        "qexxc_eval_rho": (i, [vp, p, i, i, p, vp]),
+        "qexxc_eval_rho_vjp": (i, [vp, p, i, i, p, vp]),
+        "qexxc_xc_fwd": (i, [vp, i, p, p, p, p, p, vp]),
+        "qexxc_xc_vjp": (i, [vp, i, p, p, p, p, p, p, p, vp]),
+        "qexxc_apply_fn_fwd": (i, [vp, p, l, p, p, vp]),
+        "qexxc_apply_fn_vjp": (i, [vp, p, l, p, p, p, p, vp]),
+        "qexxc_vxc_assemble": (i, [vp, i, p, p, p, p, p, vp]),
+        "qexxc_vxc_assemble_vjp": (i, [vp, i, p, p, p, p, p, p, p, p, p, p, vp]),
+        "qexxc_resid_doubles": (C.c_size_t, [vp]),
+        "qexxc_nr_rks_fwd": (i, [vp, i, i, p, p, p, p, vp]),
+        "qexxc_nr_rks_vjp": (i, [vp, i, i, p, p, p, p, p, vp]),
+        "qexxc_launch_count": (l, [vp]),
+        "qexxc_debug_run_contraction": (i, [vp, i, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().qexxc_last_error().decode()
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = last_error()
+        if rc == ERR_UNSUPPORTED:
+            raise NotImplementedError(msg)  # the reference raises NotImplementedError / ValueError here
+        raise QexxcError(rc, msg)

@@ -1,0 +1,205 @@
+// Stage 1 (K1): atomic-orbital values and gradients on the grid, plus layout helpers.
+//
+// Replaces the pyscf C evaluator the reference calls on every nr_rks
+// (pyscf.gto.eval_gto "GTOval_sph_deriv0/1" via qedft/train/td/eval_gto.py:48-70, reached from
+// block_loop at numint_legacy.py:292,313 and numint.eval_ao at trainer_legacy_no_jit.py:273).
+// phi_lm(r) = S_lm(r - A) * sum_p c_p exp(-a_p |r-A|^2), S_lm real solid harmonics in pyscf order,
+// coefficients as stored in mol._env (already normalised).  Output goes straight into the
+// context's padded AO tensor ao[b][c][g][n] (n fastest, like pyscf's [comp, grid, ao]).
+#include "common.cuh"
+
+namespace qexxc {
+namespace {
+
+struct V4 {
+    double v, x, y, z;
+};
+__device__ __forceinline__ V4 mk(double v, double x, double y, double z) { return V4{v, x, y, z}; }
+
+// real solid harmonic m of order l (value + gradient) at (x,y,z)
+template <int L>
+__device__ __forceinline__ V4 solid(int m, double x, double y, double z);
+template <>
+__device__ __forceinline__ V4 solid<0>(int, double, double, double) {
+    return mk(0.28209479177387814, 0, 0, 0);
+}
+template <>
+__device__ __forceinline__ V4 solid<1>(int m, double x, double y, double z) {
+    const double c = 0.4886025119029199;
+    return m == 0 ? mk(c * x, c, 0, 0) : (m == 1 ? mk(c * y, 0, c, 0) : mk(c * z, 0, 0, c));
+}
+template <>
+__device__ __forceinline__ V4 solid<2>(int m, double x, double y, double z) {
+    const double c = 1.0925484305920792, a = 0.6307831305050401, h = 0.31539156525252005,
+                 e = 0.5462742152960396;
+    switch (m) {
+        case 0: return mk(c * x * y, c * y, c * x, 0);
+        case 1: return mk(c * y * z, 0, c * z, c * y);
+        case 2: return mk(a * z * z - h * (x * x + y * y), -2 * h * x, -2 * h * y, 2 * a * z);
+        case 3: return mk(c * x * z, c * z, 0, c * x);
+        default: return mk(e * (x * x - y * y), 2 * e * x, -2 * e * y, 0);
+    }
+}
+template <>
+__device__ __forceinline__ V4 solid<3>(int m, double x, double y, double z) {
+    const double A = 0.5900435899266435, B = 2.8906114426405543, C = 0.4570457994644657,
+                 D = 0.3731763325901154, E = 1.4453057213202771;
+    const double xx = x * x, yy = y * y, zz = z * z;
+    switch (m) {
+        case 0: return mk(A * (3 * xx * y - yy * y), A * 6 * x * y, A * (3 * xx - 3 * yy), 0);
+        case 1: return mk(B * x * y * z, B * y * z, B * x * z, B * x * y);
+        case 2: return mk(C * y * (4 * zz - xx - yy), -2 * C * x * y, C * (4 * zz - xx - 3 * yy), 8 * C * y * z);
+        case 3:
+            return mk(D * z * (2 * zz - 3 * xx - 3 * yy), -6 * D * x * z, -6 * D * y * z,
+                      D * (6 * zz - 3 * xx - 3 * yy));
+        case 4: return mk(C * x * (4 * zz - xx - yy), C * (4 * zz - 3 * xx - yy), -2 * C * x * y, 8 * C * x * z);
+        case 5: return mk(E * z * (xx - yy), 2 * E * x * z, -2 * E * y * z, E * (xx - yy));
+        default: return mk(A * (xx * x - 3 * x * yy), A * (3 * xx - 3 * yy), -6 * A * x * y, 0);
+    }
+}
+
+template <int L>
+__device__ __forceinline__ void emit_shell(double* __restrict__ row0, long cstride, int deriv, int off,
+                                           double x, double y, double z, double R0, double R1) {
+#pragma unroll
+    for (int m = 0; m < 2 * L + 1; ++m) {
+        const V4 s = solid<L>(m, x, y, z);
+        row0[off + m] = s.v * R0;
+        if (deriv) {
+            row0[cstride + off + m] = s.x * R0 + s.v * x * R1;
+            row0[2 * cstride + off + m] = s.y * R0 + s.v * y * R1;
+            row0[3 * cstride + off + m] = s.z * R0 + s.v * z * R1;
+        }
+    }
+}
+
+// one warp per grid point; lanes stride over shells
+__global__ void __launch_bounds__(256)
+eval_ao_kernel(const double* __restrict__ coords, const ShellDev* __restrict__ shells, int nshell,
+               const double* __restrict__ env, int nenv, double* __restrict__ ao, int G, int Gpad,
+               int GpadMax, int N, int Npad, int C, int deriv) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const long cstride = (long)GpadMax * Npad;
+    const double* envb = env + (long)b * nenv;
+    const int ncomp = deriv ? 4 : 1;
+    for (long gi = wid; gi < Gpad; gi += nwarps) {
+        double* row0 = ao + ((long)b * C * GpadMax + gi) * Npad;
+        if (gi >= G) {  // padding rows stay exactly zero
+            for (int c = 0; c < ncomp; ++c)
+                for (int n = lane; n < N; n += 32) row0[c * cstride + n] = 0.0;
+            continue;
+        }
+        const double* r = coords + ((long)b * GpadMax + gi) * 3;
+        const double rx = r[0], ry = r[1], rz = r[2];
+        for (int s = lane; s < nshell; s += 32) {
+            const ShellDev sh = shells[s];
+            const double x = rx - envb[sh.atom_coord], y = ry - envb[sh.atom_coord + 1],
+                         z = rz - envb[sh.atom_coord + 2];
+            const double rr = x * x + y * y + z * z;
+            const double* ex = envb + sh.ptr_exp;
+            const int nf = 2 * sh.l + 1;
+            for (int ic = 0; ic < sh.nctr; ++ic) {
+                const double* cf = envb + sh.ptr_coef + ic * sh.nprim;
+                double R0 = 0.0, R1 = 0.0;
+                for (int p = 0; p < sh.nprim; ++p) {
+                    const double a = ex[p];
+                    const double e = cf[p] * exp(-a * rr);
+                    R0 += e;
+                    R1 -= 2.0 * a * e;
+                }
+                const int off = sh.ao_off + ic * nf;
+                switch (sh.l) {
+                    case 0: emit_shell<0>(row0, cstride, deriv, off, x, y, z, R0, R1); break;
+                    case 1: emit_shell<1>(row0, cstride, deriv, off, x, y, z, R0, R1); break;
+                    case 2: emit_shell<2>(row0, cstride, deriv, off, x, y, z, R0, R1); break;
+                    default: emit_shell<3>(row0, cstride, deriv, off, x, y, z, R0, R1); break;
+                }
+            }
+        }
+    }
+}
+
+// user AO [B][ncomp][G][N] -> internal padded tensor (zero fill) and back
+__global__ void pack_ao_kernel(const double* __restrict__ src, double* __restrict__ ao, int ncomp, int G,
+                               int Gpad, int GpadMax, int N, int Npad, int C) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const long total = (long)Gpad * Npad;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long)gridDim.x * blockDim.x) {
+        const long gi = idx / Npad;
+        const int n = (int)(idx - gi * Npad);
+        double v = 0.0;
+        if (gi < G && n < N) v = src[(((long)b * ncomp + c) * G + gi) * N + n];
+        ao[(((long)b * C + c) * GpadMax + gi) * Npad + n] = v;
+    }
+}
+__global__ void unpack_ao_kernel(double* __restrict__ dst, const double* __restrict__ ao, int ncomp, int G,
+                                 int GpadMax, int N, int Npad, int C) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const long total = (long)G * N;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long)gridDim.x * blockDim.x) {
+        const long gi = idx / N;
+        const int n = (int)(idx - gi * N);
+        dst[(((long)b * ncomp + c) * G + gi) * N + n] = ao[(((long)b * C + c) * GpadMax + gi) * Npad + n];
+    }
+}
+
+__global__ void set_grid_kernel(const double* __restrict__ coords, const double* __restrict__ weights,
+                                double* __restrict__ cdst, double* __restrict__ wdst, int G, int GpadMax) {
+    const int b = blockIdx.y;
+    for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < GpadMax;
+         gi += (long)gridDim.x * blockDim.x) {
+        const bool in = gi < G;
+        wdst[(long)b * GpadMax + gi] = in ? weights[(long)b * G + gi] : 0.0;
+        if (coords) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                cdst[((long)b * GpadMax + gi) * 3 + k] = in ? coords[((long)b * G + gi) * 3 + k] : 0.0;
+        }
+    }
+}
+
+inline unsigned grid_for(long total, int threads, int num_sms) {
+    long blocks = (total + threads - 1) / threads;
+    const long cap = (long)num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace
+
+int launch_set_grid(qexxc_ctx* c, const double* coords, const double* weights, int G, cudaStream_t st) {
+    dim3 grid(grid_for(c->GpadMax, 256, c->num_sms), c->B);
+    set_grid_kernel<<<grid, 256, 0, st>>>(coords, weights, c->coords, c->weights, G, c->GpadMax);
+    QX_LAUNCH_CHECK(c);
+    return QEXXC_OK;
+}
+
+int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
+    dim3 grid(grid_for((long)c->Gpad * 32, 256, c->num_sms), c->B);
+    eval_ao_kernel<<<grid, 256, 0, st>>>(c->coords, c->shells, c->nshell, c->env, c->nenv, c->ao, c->G,
+                                         c->Gpad, c->GpadMax, c->N, c->Npad, c->C, deriv);
+    QX_LAUNCH_CHECK(c);
+    return QEXXC_OK;
+}
+
+int launch_pack_ao(qexxc_ctx* c, const double* src, int ncomp, int G, cudaStream_t st) {
+    dim3 grid(grid_for((long)c->Gpad * c->Npad, 256, c->num_sms), ncomp, c->B);
+    pack_ao_kernel<<<grid, 256, 0, st>>>(src, c->ao, ncomp, G, c->Gpad, c->GpadMax, c->N, c->Npad, c->C);
+    QX_LAUNCH_CHECK(c);
+    return QEXXC_OK;
+}
+
+int launch_unpack_ao(qexxc_ctx* c, double* dst, int ncomp, cudaStream_t st) {
+    dim3 grid(grid_for((long)c->G * c->N, 256, c->num_sms), ncomp, c->B);
+    unpack_ao_kernel<<<grid, 256, 0, st>>>(dst, c->ao, ncomp, c->G, c->GpadMax, c->N, c->Npad, c->C);
+    QX_LAUNCH_CHECK(c);
+    return QEXXC_OK;
+}
+
+}  // namespace qexxc

@@ -1,0 +1,170 @@
+// Internal declarations shared by the libqexxc translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qexxc.h"
+
+namespace qexxc {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define QX_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            qexxc::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                             cudaGetErrorString(_e));                                         \
+            return QEXXC_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+#define QX_LAUNCH_CHECK(ctx)                                                                  \
+    do {                                                                                      \
+        (ctx)->launches++;                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            qexxc::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,         \
+                             cudaGetErrorString(_e));                                         \
+            return QEXXC_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+#define QX_TRY(expr)                                                                          \
+    do {                                                                                      \
+        int _r = (expr);                                                                      \
+        if (_r != QEXXC_OK) return _r;                                                        \
+    } while (0)
+#define QX_ARG(cond, msg)                                                                     \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            qexxc::set_error("invalid argument: %s (%s:%d)", msg, __FILE__, __LINE__);        \
+            return QEXXC_ERR_ARG;                                                             \
+        }                                                                                     \
+    } while (0)
+
+constexpr int kGTile = 128;  // grid rows are padded to a multiple of this
+constexpr int kNTile = 32;   // AO columns are padded to a multiple of this
+inline int round_up(long x, int m) { return (int)(((x + m - 1) / m) * m); }
+
+// One contracted shell of the basis, flattened for the AO kernel.
+struct ShellDev {
+    int atom_coord;  // offset of the centre (x,y,z) in env
+    int l;
+    int nprim;
+    int nctr;
+    int ptr_exp;
+    int ptr_coef;
+    int ao_off;  // first AO index of this shell
+    int pad;
+};
+
+}  // namespace qexxc
+
+struct qexxc_ctx {
+    int device = 0;
+    int B = 1, C = 1, Gmax = 0, GpadMax = 0, N = 0, Npad = 0;
+    int G = 0, Gpad = 0;  // current grid
+    qexxc_net_desc net{};
+    long n_theta = 0;
+    int num_sms = 148;
+    long launches = 0;
+    size_t bytes = 0;
+
+    // stage 1
+    double* coords = nullptr;   // [B][GpadMax][3]
+    double* weights = nullptr;  // [B][GpadMax] (zero beyond G)
+    double* ao = nullptr;       // [B][C][GpadMax][Npad], zero padded
+    int ao_ncomp = 0;           // components currently valid in `ao`
+    bool have_grid = false, have_basis = false;
+    qexxc::ShellDev* shells = nullptr;
+    int nshell = 0;
+    double* env = nullptr;  // [B][nenv]
+    int nenv = 0;
+
+    // stage 2/4 workspaces (all [B][...][GpadMax] rows are zero beyond G)
+    double* S = nullptr;        // [B][Npad][Npad] padded symmetric operand (dm or V_bar + V_bar^T)
+    double* rho = nullptr;      // [B][C][GpadMax]
+    double* exc = nullptr;      // [B][GpadMax]
+    double* vrho = nullptr;     // [B][GpadMax]
+    double* vgamma = nullptr;   // [B][GpadMax]
+    double* wv = nullptr;       // [B][C][GpadMax]  per-point scale factors of the V_xc contraction
+    double* wvb = nullptr;      // [B][C][GpadMax]  cotangent of wv
+    double* rbar = nullptr;     // [B][C][GpadMax]
+    double* excb = nullptr;     // [B][GpadMax]
+    double* vrhob = nullptr;    // [B][GpadMax]
+    double* vgammab = nullptr;  // [B][GpadMax]
+    double* aow = nullptr;      // [B][GpadMax][Npad] (C == 4 only)
+    double* part = nullptr;     // split-G partial tiles [B][nsplit_max][Npad][Npad]
+    int nsplit_max = 1;
+    double* red = nullptr;      // per-CTA partial sums (excsum, nelec, theta_bar ...)
+    size_t red_doubles = 0;
+    void* tape = nullptr;       // MLP reverse-mode tape (per-CTA slots)
+    size_t tape_bytes = 0;
+    unsigned char* qperm = nullptr;  // QNN ring permutation tables (2 x 256 bytes)
+    std::vector<void*> allocs;
+};
+
+namespace qexxc {
+
+// ---- launchers implemented in the .cu files --------------------------------------------------
+// contract.cu
+int wsyrk_pick_nsplit(int num_sms, int Npad, int Gpad, int B, bool sym);
+int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, cudaStream_t st);  // 0: (a+a^T)/2, 1: a, 2: a+a^T
+// q[b][k][g] = fac[k] * sum_ij ao[b][k][g][i] S[b][i][j] ao[b][0][g][j], k < ncomp
+int launch_rowquad(qexxc_ctx* c, int ncomp, const double* fac4, double* q, long q_bstride, long q_cstride,
+                   cudaStream_t st);
+// H[b] = ao0^T diag(s) ao0 (Bsrc == nullptr, symmetric) or ao0^T Bsrc (general);
+// out[b][i][j] = scale * (H[i][j] + (tadd ? H[j][i] : 0)), i,j < N, row stride N
+int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bsrc, double scale, int tadd,
+                 double* out, long out_bstride, cudaStream_t st);
+// aow[b][g][n] = sum_c f[c] wv[b][c][g] ao[b][c][g][n]
+int launch_build_aow(qexxc_ctx* c, const double* wv, long wv_bstride, long wv_cstride, const double* fac4,
+                     cudaStream_t st);
+// ao.cu
+int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st);
+int launch_pack_ao(qexxc_ctx* c, const double* src, int ncomp, int G, cudaStream_t st);
+int launch_unpack_ao(qexxc_ctx* c, double* dst, int ncomp, cudaStream_t st);
+int launch_set_grid(qexxc_ctx* c, const double* coords, const double* weights, int G, cudaStream_t st);
+// pointwise.cu
+int stage4_nblocks(const qexxc_ctx* c);
+int launch_stage4_pointwise(qexxc_ctx* c, int xctype, const double* rho, const double* exc, const double* vrho,
+                            const double* vgamma, double* wv, double* sums, long sums_bstride, cudaStream_t st);
+int launch_stage4_pointwise_vjp(qexxc_ctx* c, int xctype, const double* rho, const double* exc,
+                                const double* vrho, const double* vgamma, const double* e_bar, const double* wvb,
+                                double* rho_bar, double* exc_bar, double* vrho_bar, double* vgamma_bar,
+                                cudaStream_t st);
+// dst[b][c][i] = i < n ? src[b][c][i] : 0 for i < n_pad
+int launch_copy_rows(qexxc_ctx* c, double* dst, long dst_bstride, long dst_cstride, const double* src,
+                     long src_bstride, long src_cstride, int nb, int nc, long n, long n_pad, cudaStream_t st);
+int launch_transpose_in(qexxc_ctx* c, double* feat, long ld, const double* x, long npts, int F, long n_pad,
+                        cudaStream_t st);
+int launch_transpose_out(qexxc_ctx* c, double* x, const double* feat, long ld, long npts, int F, cudaStream_t st);
+// xc_mlp.cu
+int mlp_local_grid(const qexxc_ctx* c);
+size_t mlp_local_tape_bytes(const qexxc_ctx* c);
+int launch_mlp_local_fwd(qexxc_ctx* c, int xctype, const double* rho, long rho_bstride, long rho_cstride,
+                         const double* theta, double* exc, double* vrho, double* vgamma, long out_bstride,
+                         int nbatch, long npts_per_batch, cudaStream_t st);
+int launch_mlp_local_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_bstride, long rho_cstride,
+                         const double* theta, const double* exc_bar, const double* vrho_bar,
+                         const double* vgamma_bar, long in_bstride, double* rho_bar, int accumulate,
+                         double* theta_bar, int accumulate_theta, int nbatch, long npts_per_batch,
+                         cudaStream_t st);
+// xc_global.cu
+size_t global_mlp_smem(int L, int H);
+int launch_global_mlp(qexxc_ctx* c, bool vjp, const double* rho, long ld, int G, const double* theta, double* exc,
+                      long exc_stride, double* vrho, const double* exc_bar, const double* vrho_bar,
+                      double* rho_bar, double* theta_bar, int accumulate_theta, int nbatch, cudaStream_t st);
+// xc_qnn.cu
+int qnn_grid(const qexxc_ctx* c, long npts);
+size_t qnn_red_doubles(const qexxc_ctx* c, long npts_max);
+int qnn_upload_perm(qexxc_ctx* c, unsigned char* dev_tables);
+int launch_qnn(qexxc_ctx* c, bool vjp, const unsigned char* tables, const double* x, long npts, const double* theta,
+               double* exc, double* vrho, const double* exc_bar, const double* vrho_bar, double* x_bar,
+               int accumulate, double* theta_bar, int accumulate_theta, cudaStream_t st);
+
+}  // namespace qexxc
