@@ -28,7 +28,7 @@ namespace {
 constexpr int HP = 64;        // padded hidden width
 constexpr int LD = HP + 4;    // shared-memory pitch of activation / weight rows
 constexpr int R = 128;        // rows per CTA iteration
-constexpr int LDX = 20;       // pitch of the layer-0 feature rows (4 used columns)
+constexpr int LDX = 4;        // pitch of the layer-0 feature rows (4 columns; 4 = 4 mod 16 is conflict-free)
 constexpr int NW = 16;        // warps: 4 (m) x 4 (n), warp tile 32 x 16
 constexpr int MLP_THREADS = NW * 32;
 constexpr int MB = 4, NB = 2;
