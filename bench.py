@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the XC grid-integration hot path (AO evaluation + nr_rks forward + its VJP).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one rank per GPU
+  python bench.py --impl reference --gpus N --steps K ...  # the reference math on the host cores
+
+One "step" = one pass of the hot path over the whole synthetic workload (default c5:
+1000 AOs x 1,000,000 grid points, LocalMLP XC, float64): K1 AO values on the grid, stage 2 rho,
+stage 3 network exc/vrho, stage 4 E_xc / V_xc, then the reverse pass (dm_bar, theta_bar).  For
+N > 1 the grid is sharded in contiguous point ranges (strong scaling: the global grid is fixed)
+and the packed outputs are all-reduced with NCCL (one collective per direction).
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events around exactly K steps, barrier +
+synchronize on both sides, max over ranks; inputs (8 GB AO tensor per pass) exceed L2.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "XC grid-integration grid-pts/s (fwd+VJP)"
+UNIT = "grid-pts/s"
+
+
+def _args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c5", choices=["c5", "c5gga", "c3", "c2"])
+    ap.add_argument("--ngrids", type=int, default=None, help="override the grid size (debugging)")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="network precision")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample duration")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle restatement of the reference math on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_step_time(wl, sample, repeats=1):
+    """Seconds for one oracle step (AO + fwd + VJP) on the first `sample` grid points."""
+    from oracle import step_ref
+
+    m = wl.mol
+    c, w = wl.coords[:sample], wl.weights[:sample]
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        step_ref.xc_step(m._atm, m._bas, m._env, c, w, wl.dm, wl.net, wl.theta, wl.xctype, wl.e_bar, wl.v_bar)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_baseline(wl, target_s):
+    """Bounded sample of the same workload (about `target_s` seconds of CPU work)."""
+    G = wl.ngrids
+    s0 = min(G, 2048)
+    t0 = cpu_step_time(wl, s0)  # calibration (also warms BLAS threads)
+    sample = int(min(G, max(s0, s0 * target_s / max(t0, 1e-6) / 2)))
+    sample = max(256, (sample // 256) * 256) if G >= 256 else G
+    t = cpu_step_time(wl, sample)
+    return {"value": sample / t, "unit": UNIT, "cores": _cpu_threads(), "kind": "port",
+            "sample": f"first {sample} of {G} grid points of the same workload, 1 step (AO eval + nr_rks fwd + VJP), "
+                      f"NumPy/BLAS float64 oracle restatement of the reference math (real JAX/pyscfad not installable); "
+                      f"{t:.2f} s", "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own math on the host cores (the oracle port; the
+    reference itself -- JAX + pyscfad -- cannot be installed in this image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from qex_b200 import workloads
+
+    wl = workloads.make(args.config, ngrids=args.ngrids)
+    G = wl.ngrids
+    s0 = min(G, 2048)
+    t0 = cpu_step_time(wl, s0)
+    budget = 120.0 / max(1, args.steps + args.warmup)  # whole run within a few minutes
+    sample = int(min(G, max(s0, s0 * min(budget, args.cpu_seconds) / max(t0, 1e-6) / 2)))
+    sample = max(256, (sample // 256) * 256) if G >= 256 else G
+    for _ in range(args.warmup):
+        cpu_step_time(wl, sample)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step_time(wl, sample)
+    dt = (time.perf_counter() - t) / max(1, args.steps)
+    val = sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.describe, "nao": wl.nao, "ngrids": G, "sample_ngrids": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": _cpu_threads(), "kind": "port",
+                         "sample": f"each step = first {sample} of {G} grid points (AO eval + nr_rks fwd + VJP), "
+                                   "NumPy/BLAS float64 oracle port; the reference's JAX/pyscfad stack is not installable here",
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def measure_dgemm_peak(torch, seconds=1.5):
+    """cuBLAS DGEMM TFLOP/s: burst (best of 5) and sustained (back to back for `seconds`).
+    MEASURED_PEAKS.json has no FP64 figure, so the FP64 denominator is measured in-run."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        torch.matmul(a, b)
+    torch.cuda.synchronize()
+    fl = 2.0 * n**3
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        best = max(best, fl / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(3, int(seconds / (fl / (best * 1e12))))
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b)
+    e1.record()
+    e1.synchronize()
+    sustained = fl * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b
+    return best, sustained
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from qex_b200 import workloads
+    from qex_b200.engine import XCContext
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl = workloads.make(args.config, ngrids=args.ngrids)
+    N, G = wl.nao, wl.ngrids
+    # contiguous grid shard of this rank (fixed map rank -> point range)
+    per = (G + world - 1) // world
+    lo, hi = min(G, rank * per), min(G, (rank + 1) * per)
+    Gl = hi - lo
+    net = workloads.net_spec(wl, args.precision)
+    ctx = XCContext(nao=N, ngrids_max=max(Gl, 1), ncomp=wl.ncomp, nbatch=1, net=net, device=local)
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env)
+    deriv = 1 if wl.ncomp == 4 else 0
+
+    # pinned host copies of every per-call input, and device-resident copies
+    def pin(x):
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).pin_memory()
+
+    h_coords, h_w = pin(wl.coords[lo:hi]), pin(wl.weights[lo:hi])
+    h_dm, h_th = pin(wl.dm), pin(wl.theta)
+    h_eb, h_vb = pin(np.array([wl.e_bar])), pin(wl.v_bar)
+    d_coords, d_w, d_dm, d_th, d_eb, d_vb = (t.cuda() for t in (h_coords, h_w, h_dm, h_th, h_eb, h_vb))
+    out = ctx.empty(1, N * N + 2)
+    bar = ctx.empty(N * N + wl.theta.size)
+    resid = ctx.empty(ctx.resid_doubles)
+    h_out, h_bar = torch.empty_like(out, device="cpu").pin_memory(), torch.empty_like(bar, device="cpu").pin_memory()
+
+    def step():
+        ctx.set_grid(d_coords, d_w)
+        ctx.eval_ao(deriv)
+        ctx.nr_rks_fwd(d_dm, d_th, wl.xctype, 0, out=out, resid=resid)
+        if world > 1:
+            dist.all_reduce(out)
+        ctx.nr_rks_vjp(d_th, resid, d_eb, d_vb, wl.xctype, 0, out=bar)
+        if world > 1:
+            dist.all_reduce(bar)
+
+    def step_e2e():
+        # host buffers in, host buffers out: what a caller of the drop-in nr_rks pays per call
+        d_coords.copy_(h_coords, non_blocking=True)
+        d_w.copy_(h_w, non_blocking=True)
+        d_dm.copy_(h_dm, non_blocking=True)
+        d_th.copy_(h_th, non_blocking=True)
+        d_eb.copy_(h_eb, non_blocking=True)
+        d_vb.copy_(h_vb, non_blocking=True)
+        step()
+        h_out.copy_(out, non_blocking=True)
+        h_bar.copy_(bar, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    peak_burst = peak_sus = None
+    if rank == 0:
+        peak_burst, peak_sus = measure_dgemm_peak(torch)
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    # ---- timed region: value ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.profile_enable(True)
+    l0 = ctx.launch_count
+    ms_total = timed(step, args.steps)
+    launches = ctx.launch_count - l0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = G / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers, copies inside the timed region ----
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    h2d = sum(t.numel() * 8 for t in (h_coords, h_w, h_dm, h_th, h_eb, h_vb))
+    d2h = (h_out.numel() + h_bar.numel()) * 8
+
+    if rank == 0:
+        # dominant kernel: the FP64 DMMA contractions (2 rowquad + 2 wsyrk launches per step,
+        # 2*G*N^2 algorithmic FLOP each -> 8*N^2 FLOP per grid point per step)
+        fl = 2.0 * Gl * N * N
+        kern = {}
+        for name in ("rowquad", "wsyrk", "xc_fwd", "xc_vjp", "eval_ao"):
+            ms, n = prof[name]
+            kern[name] = {"launches": n, "avg_ms": (ms / n) if n else None, "share_of_step": ms / ms_total if ms_total else None}
+        dom = max(("rowquad", "wsyrk"), key=lambda k: prof[k][0])
+        avg_ms = kern[dom]["avg_ms"] or float("nan")
+        achieved = fl / (avg_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "kernel": dom + "_kernel (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak_sus,
+            "unit": "TFLOP/s", "frac": achieved / peak_sus if peak_sus else None, "traffic": None,
+            "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, sustained (MEASURED_PEAKS.json has no FP64 figure); "
+                           f"burst {peak_burst:.1f} TFLOP/s",
+            "algorithmic_flop_per_launch": fl, "kernels": kern,
+            "contractions_frac_of_peak_all4": (4 * fl / ((prof["rowquad"][0] + prof["wsyrk"][0]) / args.steps * 1e-3) / 1e12 / peak_sus)
+            if peak_sus else None,
+        }
+        cpu = None if args.no_cpu_baseline or world > 1 else cpu_baseline(wl, args.cpu_seconds)
+        hbm = None
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": wl.describe, "nao": N, "ngrids": G, "ngrids_per_gpu": Gl, "ncomp": wl.ncomp,
+                       "network_precision": args.precision, "parallelism": f"grid-sharded x{world}, NCCL all-reduce of packed V_xc|E_xc|nelec and dm_bar|theta_bar",
+                       "l2": "inputs larger than L2 (AO tensor %.1f GB per pass)" % (Gl * ctx_npad(N) * 8 * wl.ncomp / 1e9),
+                       "step": "set_grid + eval_ao (K1) + nr_rks fwd + nr_rks VJP"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": G / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "hbm_peak_gbs": hbm,
+            "workspace_gb": ctx.workspace_bytes / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ctx_npad(N):
+    return ((N + 31) // 32) * 32
+
+
+if __name__ == "__main__":
+    a = _args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -176,6 +176,17 @@ int qexxc_nr_rks_vjp(qexxc_ctx* ctx, int xctype, int hermi, const double* theta_
 /* ---- introspection for the benchmark -------------------------------------------------------
  * Number of kernels this library launched on the context since creation (gpu_launches). */
 long qexxc_launch_count(const qexxc_ctx* ctx);
+/* Per-kernel-class device timing with CUDA events recorded on the caller's stream around the
+ * launches of one class (bench.py's roofline line).  qexxc_profile_read synchronises on the
+ * recorded events, returns the summed milliseconds and launch count and clears the class. */
+#define QEXXC_PROF_ROWQUAD 0
+#define QEXXC_PROF_WSYRK 1
+#define QEXXC_PROF_XC_FWD 2
+#define QEXXC_PROF_XC_VJP 3
+#define QEXXC_PROF_EVAL_AO 4
+#define QEXXC_PROF_NCLASS 5
+int qexxc_profile_enable(qexxc_ctx* ctx, int on);
+int qexxc_profile_read(qexxc_ctx* ctx, int cls, double* ms_total, long* count);
 /* Runs only the dominant contraction kernel once on the current AO/S buffers (roofline timing):
  * which = 0 rowquad (rho-type), 1 wsyrk (vmat-type). */
 int qexxc_debug_run_contraction(qexxc_ctx* ctx, int which, void* stream);

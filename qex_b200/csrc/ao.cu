@@ -182,6 +182,7 @@ int launch_set_grid(qexxc_ctx* c, const double* coords, const double* weights, i
 
 int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
     dim3 grid(grid_for((long)c->Gpad * 32, 256, c->num_sms), c->B);
+    ProfScope prof(c, QEXXC_PROF_EVAL_AO, st);
     eval_ao_kernel<<<grid, 256, 0, st>>>(c->coords, c->shells, c->nshell, c->env, c->nenv, c->ao, c->G,
                                          c->Gpad, c->GpadMax, c->N, c->Npad, c->C, deriv);
     QX_LAUNCH_CHECK(c);

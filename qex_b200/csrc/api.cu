@@ -661,6 +661,32 @@ int qexxc_nr_rks_vjp(qexxc_ctx* c, int xctype, int hermi, const double* theta_de
     return launch_wsyrk(c, nullptr, 0, c->aow, hermi ? 1.0 : 0.5, hermi ? 0 : 1, bar_dev, nn, st);
 }
 
+int qexxc_profile_enable(qexxc_ctx* c, int on) {
+    QX_ARG(c != nullptr, "ctx is null");
+    c->prof = on != 0;
+    return QEXXC_OK;
+}
+
+int qexxc_profile_read(qexxc_ctx* c, int cls, double* ms_total, long* count) {
+    QX_ARG(c != nullptr && ms_total && count, "null pointer");
+    QX_ARG(cls >= 0 && cls < QEXXC_PROF_NCLASS, "profile class out of range");
+    double tot = 0.0;
+    long n = 0;
+    for (auto& pr : c->prof_ev[cls]) {
+        QX_CUDA(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        QX_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms;
+        ++n;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    c->prof_ev[cls].clear();
+    *ms_total = tot;
+    *count = n;
+    return QEXXC_OK;
+}
+
 int qexxc_debug_run_contraction(qexxc_ctx* c, int which, void* stream) {
     QX_ARG(c != nullptr, "ctx is null");
     QX_TRY(need_ao(c, 1));

@@ -106,7 +106,32 @@ struct qexxc_ctx {
     size_t tape_bytes = 0;
     unsigned char* qperm = nullptr;  // QNN ring permutation tables (2 x 256 bytes)
     std::vector<void*> allocs;
+    // optional per-kernel-class CUDA-event timing (bench.py roofline): class -> (start, stop) pairs
+    bool prof = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[QEXXC_PROF_NCLASS];
 };
+
+namespace qexxc {
+// RAII: records an event pair around the launches made in its scope when profiling is on
+struct ProfScope {
+    qexxc_ctx* c;
+    int cls;
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(qexxc_ctx* ctx, int k, cudaStream_t s) : c(ctx), cls(k), st(s) {
+        if (c->prof) {
+            cudaEvent_t e0;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, st);
+            c->prof_ev[cls].push_back({e0, e1});
+        }
+    }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, st);
+    }
+};
+}  // namespace qexxc
 
 namespace qexxc {
 

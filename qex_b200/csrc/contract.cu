@@ -410,6 +410,7 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, const double* fac4, double* q, long 
             c->ao, c->S, q, c->Npad, ao_cs, ao_bs, S_bs, q_cstride, q_bstride, ncomp, fac4[0],   \
             fac4[1], fac4[2], fac4[3]);                                                          \
     } while (0)
+    ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
     if (BN == 128) QX_RQ(128);
     else if (BN == 64) QX_RQ(64);
     else QX_RQ(32);
@@ -438,9 +439,12 @@ int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bs
             c->ao, Bp, s, c->part, c->Npad, c->Gpad, rps, sym ? 1 : 0, ao_bs, B_bs, s_bstride,   \
             part_bs);                                                                            \
     } while (0)
-    if (BN == 128) QX_WS(128);
-    else if (BN == 64) QX_WS(64);
-    else QX_WS(32);
+    {
+        ProfScope prof(c, QEXXC_PROF_WSYRK, st);
+        if (BN == 128) QX_WS(128);
+        else if (BN == 64) QX_WS(64);
+        else QX_WS(32);
+    }
 #undef QX_WS
     QX_LAUNCH_CHECK(c);
     dim3 rgrid((c->N + 127) / 128, c->N, c->B);

@@ -655,6 +655,7 @@ int launch_mlp_local_fwd(qexxc_ctx* c, int xctype, const double* rho, long rho_b
     p.nblocks = p.blocks_per_batch * nbatch;
     const int grid = p.nblocks < c->num_sms ? p.nblocks : c->num_sms;
     if (grid <= 0) return QEXXC_OK;
+    ProfScope prof(c, QEXXC_PROF_XC_FWD, st);
 #define QX_FWD(T, NSV)                                                                      \
     do {                                                                                    \
         const size_t sm = smem_elems<T>(p.L, false) * sizeof(T);                            \
@@ -699,6 +700,7 @@ int launch_mlp_local_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_b
     const int grid = p.nblocks < c->num_sms ? p.nblocks : c->num_sms;
     if (grid <= 0) return QEXXC_OK;
     const bool f32 = c->net.precision == QEXXC_PREC_F32;
+    ProfScope prof(c, QEXXC_PROF_XC_VJP, st);
     if (f32) {
         const size_t sm = smem_elems<float>(p.L, true) * sizeof(float);
         QX_TRY(set_smem_attr(mlp_vjp_kernel<float>, sm));

@@ -304,3 +304,17 @@ class XCContext:
     def debug_run_contraction(self, which: int):
         with torch.cuda.device(self.device):
             check(self.lib.qexxc_debug_run_contraction(self._h, int(which), _stream()))
+
+    PROF_CLASSES = {"rowquad": 0, "wsyrk": 1, "xc_fwd": 2, "xc_vjp": 3, "eval_ao": 4}
+
+    def profile_enable(self, on: bool = True):
+        check(self.lib.qexxc_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self) -> dict:
+        """{class: (total_ms, launches)} since the last read (synchronises on the recorded events)."""
+        out = {}
+        for name, k in self.PROF_CLASSES.items():
+            ms, n = C.c_double(0), C.c_long(0)
+            check(self.lib.qexxc_profile_read(self._h, k, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out

@@ -1,0 +1,119 @@
+"""Seeded synthetic workloads for the BASELINE.json configs.
+
+Host-side set-up only (numpy): molecules as libcint tables, grids, density matrices, network
+parameters and cotangents.  Used by bench.py, __graft_entry__.smoke() and the tests so that all
+of them see identical inputs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import gen_grid, gto
+
+
+@dataclass
+class Workload:
+    name: str
+    describe: str
+    mol: gto.Mole
+    coords: np.ndarray   # [G, 3]
+    weights: np.ndarray  # [G]
+    dm: np.ndarray       # [N, N]
+    xctype: str          # "NN" | "GGA" | "NN-AmplitudeEncoding"
+    ncomp: int
+    net: dict            # kwargs for engine.NetSpec (kind by name)
+    theta: np.ndarray
+    e_bar: float
+    v_bar: np.ndarray    # [N, N]
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def nao(self):
+        return self.dm.shape[0]
+
+    @property
+    def ngrids(self):
+        return self.weights.shape[0]
+
+
+def _mlp_theta(sizes, seed=0):
+    """Glorot-normal W / N(0,1e-2) b, flat [W.ravel(), b] per Dense (stax defaults; seeded numpy)."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for fi, fo in zip(sizes[:-1], sizes[1:]):
+        parts.append((rng.standard_normal((fi, fo)) * np.sqrt(2.0 / (fi + fo))).ravel())
+        parts.append(rng.standard_normal(fo) * 1e-2)
+    return np.concatenate(parts)
+
+
+def _dm(N, rank, seed):
+    rng = np.random.default_rng(seed)
+    Cm = rng.standard_normal((N, rank)) / np.sqrt(N)
+    return 2.0 * Cm @ Cm.T
+
+
+def _cotangents(N, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((N, N)) / N
+    return 1.0, v
+
+
+def make(config: str = "c5", ngrids: int | None = None, seed: int = 0) -> Workload:
+    """config in {"c2", "c3", "c5", "c5gga"}; `ngrids` overrides the grid size (tests, CPU samples)."""
+    if config == "c5" or config == "c5gga":
+        # ~1000 AOs x 1M grid points, LocalMLP (BASELINE.json configs[4])
+        mol = gto.synthetic_molecule(50, (4, 2, 2), seed=seed)  # 50 atoms x (4s 2p 2d = 20 AOs) = 1000
+        G = ngrids or 1_000_000
+        grid = gen_grid.random_grid(mol, G, seed=seed + 1)
+        N = mol.nao_nr()
+        gga = config == "c5gga"
+        sizes = [2 if gga else 1, 64, 64, 64, 1]
+        e_bar, v_bar = _cotangents(N, seed + 3)
+        return Workload(
+            name=config, describe=f"synthetic large system: {N} AOs x {G} grid points, LocalMLP "
+            f"{'(rho,sigma)' if gga else 'rho'}->64->64->64->1 tanh, fwd+VJP",
+            mol=mol, coords=grid.coords, weights=grid.weights, dm=_dm(N, 150, seed + 2),
+            xctype="GGA" if gga else "NN", ncomp=4 if gga else 1,
+            net=dict(kind="local_mlp", n_features=2 if gga else 1, n_hidden=3, width=64, activation="tanh"),
+            theta=_mlp_theta(sizes, seed), e_bar=e_bar, v_bar=v_bar)
+    if config == "c3":
+        # water-size: ~120 AOs, ~50k grid points, LocalMLP GGA features (configs[2])
+        mol = gto.synthetic_molecule(3, (5, 5, 4), seed=seed)  # 3 atoms x 40 AOs
+        G = ngrids or 50_000
+        grid = gen_grid.random_grid(mol, G, seed=seed + 1)
+        N = mol.nao_nr()
+        e_bar, v_bar = _cotangents(N, seed + 3)
+        return Workload(
+            name="c3", describe=f"synthetic water-size system: {N} AOs x {G} grid points, LocalMLP "
+            "(rho,sigma)->64->64->64->1 GGA-feature XC, fwd+VJP",
+            mol=mol, coords=grid.coords, weights=grid.weights, dm=_dm(N, 5, seed + 2), xctype="GGA", ncomp=4,
+            net=dict(kind="local_mlp", n_features=2, n_hidden=3, width=64, activation="tanh"),
+            theta=_mlp_theta([2, 64, 64, 64, 1], seed), e_bar=e_bar, v_bar=v_bar)
+    if config == "c2":
+        # H2 / 6-31G with LocalQNN (6 qubits, 2 layers), ~1240 grid points (configs[1])
+        mol = gto.h2(0.74, "6-31g")
+        grid = gen_grid.Grids(mol, n_rad=31, n_theta=5, n_phi=4).build()  # 2 x 620 = 1240 points
+        if ngrids:
+            grid = gen_grid.Grids(mol, coords=grid.coords[:ngrids], weights=grid.weights[:ngrids])
+        N = mol.nao_nr()
+        rng = np.random.default_rng(seed)
+        e_bar, v_bar = _cotangents(N, seed + 3)
+        c = np.array([0.35, 0.28, 0.35, 0.28])[:, None]
+        return Workload(
+            name="c2", describe=f"H2/6-31G: {N} AOs x {grid.size} grid points, LocalQNN 6 qubits x 2 layers, fwd+VJP",
+            mol=mol, coords=grid.coords, weights=grid.weights, dm=2.0 * c @ c.T, xctype="NN", ncomp=1,
+            net=dict(kind="local_qnn", n_features=1, n_hidden=2, width=6, in_scale=1.0),
+            theta=rng.uniform(-0.1, 0.1, 36), e_bar=e_bar, v_bar=v_bar)
+    raise ValueError(f"unknown workload {config!r}")
+
+
+def net_spec(wl: Workload, precision: str = "f64"):
+    from . import _lib
+    from .engine import NetSpec
+
+    kinds = {"local_mlp": _lib.NET_LOCAL_MLP, "global_mlp": _lib.NET_GLOBAL_MLP, "local_qnn": _lib.NET_LOCAL_QNN}
+    kw = dict(wl.net)
+    kw["kind"] = kinds[kw["kind"]]
+    return NetSpec(precision=precision, **kw)
