@@ -388,8 +388,10 @@ int qexxc_eval_rho(qexxc_ctx* c, const double* dm_dev, int ncomp, int hermi, dou
     QX_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long ld = c->GpadMax;
-    QX_TRY(launch_pad_sym(c, dm_dev, hermi ? 1 : 0, st));
-    QX_TRY(launch_rowquad(c, ncomp, kFacGGA, c->rho, (long)c->C * ld, ld, st));
+    // LDA: rho is a quadratic form, which only sees the symmetric part of dm, so symmetrising is
+    // exact for hermi = 0 and 1 alike and lets rowquad use the upper triangle only
+    QX_TRY(launch_pad_sym(c, dm_dev, (ncomp == 1 || !hermi) ? 0 : 1, ncomp == 1, st));
+    QX_TRY(launch_rowquad(c, ncomp, ncomp == 1, kFacGGA, c->rho, (long)c->C * ld, ld, st));
     return launch_copy_rows(c, rho_dev, (long)ncomp * c->G, c->G, c->rho, (long)c->C * ld, ld, c->B, ncomp, c->G,
                             c->G, st);
 }
@@ -582,8 +584,8 @@ int qexxc_vxc_assemble_vjp(qexxc_ctx* c, int xctype, const double* rho_dev, cons
     QX_TRY(launch_copy_rows(c, c->vrho, ld, ld, vrho_dev, c->G, c->G, c->B, 1, c->G, c->Gpad, st));
     if (xctype == QEXXC_XC_GGA)
         QX_TRY(launch_copy_rows(c, c->vgamma, ld, ld, vgamma_dev, c->G, c->G, c->B, 1, c->G, c->Gpad, st));
-    QX_TRY(launch_pad_sym(c, v_bar_dev, 2, st));
-    QX_TRY(launch_rowquad(c, nc, kFacOne, c->wvb, (long)c->C * ld, ld, st));
+    QX_TRY(launch_pad_sym(c, v_bar_dev, 2, nc == 1, st));
+    QX_TRY(launch_rowquad(c, nc, nc == 1, kFacOne, c->wvb, (long)c->C * ld, ld, st));
     QX_TRY(launch_stage4_pointwise_vjp(c, xctype, c->rho, c->exc, c->vrho, c->vgamma, e_bar_dev, c->wvb, c->rbar,
                                        c->excb, c->vrhob, c->vgammab, st));
     QX_TRY(launch_copy_rows(c, rho_bar_dev, (long)nc * c->G, c->G, c->rbar, (long)c->C * ld, ld, c->B, nc, c->G, c->G,
@@ -611,8 +613,8 @@ int qexxc_nr_rks_fwd(qexxc_ctx* c, int xctype, int hermi, const double* dm_dev, 
     cudaStream_t st = (cudaStream_t)stream;
     const long ld = c->GpadMax;
     // stage 2: rho = rowdot(ao, ao sym(dm))            numint_legacy.py:294 -> :351-397
-    QX_TRY(launch_pad_sym(c, dm_dev, hermi ? 1 : 0, st));
-    QX_TRY(launch_rowquad(c, nc, kFacGGA, c->rho, (long)c->C * ld, ld, st));
+    QX_TRY(launch_pad_sym(c, dm_dev, (nc == 1 || !hermi) ? 0 : 1, nc == 1, st));
+    QX_TRY(launch_rowquad(c, nc, nc == 1, kFacGGA, c->rho, (long)c->C * ld, ld, st));
     // stage 3: exc, vrho (, vgamma)                    numint_legacy.py:295-303
     QX_TRY(net_fwd(c, xctype, c->rho, theta_dev, c->exc, c->vrho, c->vgamma, st));
     // stage 4: nelec, excsum, wv, vmat + vmat.T        numint_legacy.py:304-309, 336-337
@@ -647,8 +649,8 @@ int qexxc_nr_rks_vjp(qexxc_ctx* c, int xctype, int hermi, const double* theta_de
     const double* vgamma = resid_dev + n * (c->C + 2);
     const long nn = (long)c->N * c->N;
     // adjoint of vmat = H + H^T, H = ao^T aow: wv_bar_c = rowdot(ao_c, ao_0 (V_bar + V_bar^T))
-    QX_TRY(launch_pad_sym(c, v_bar_dev, 2, st));
-    QX_TRY(launch_rowquad(c, nc, kFacOne, c->wvb, (long)c->C * ld, ld, st));
+    QX_TRY(launch_pad_sym(c, v_bar_dev, 2, nc == 1, st));
+    QX_TRY(launch_rowquad(c, nc, nc == 1, kFacOne, c->wvb, (long)c->C * ld, ld, st));
     // adjoint of the per-point stage-4 algebra
     QX_TRY(launch_stage4_pointwise_vjp(c, xctype, rho, exc, vrho, vgamma, e_bar_dev, c->wvb, c->rbar, c->excb,
                                        c->vrhob, c->vgammab, st));
@@ -693,7 +695,7 @@ int qexxc_debug_run_contraction(qexxc_ctx* c, int which, void* stream) {
     QX_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long ld = c->GpadMax;
-    if (which == 0) return launch_rowquad(c, 1, kFacGGA, c->wvb, (long)c->C * ld, ld, st);
+    if (which == 0) return launch_rowquad(c, 1, 1, kFacGGA, c->wvb, (long)c->C * ld, ld, st);
     return launch_wsyrk(c, c->wv, (long)c->C * ld, nullptr, 1.0, 1, c->S, (long)c->N * c->N, st);
 }
 

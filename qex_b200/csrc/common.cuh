@@ -138,10 +138,12 @@ namespace qexxc {
 // ---- launchers implemented in the .cu files --------------------------------------------------
 // contract.cu
 int wsyrk_pick_nsplit(int num_sms, int Npad, int Gpad, int B, bool sym);
-int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, cudaStream_t st);  // 0: (a+a^T)/2, 1: a, 2: a+a^T
+// mode 0: (a+a^T)/2, 1: a, 2: a+a^T; tri: keep the upper triangle only (diagonal halved)
+int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, int tri, cudaStream_t st);
 // q[b][k][g] = fac[k] * sum_ij ao[b][k][g][i] S[b][i][j] ao[b][0][g][j], k < ncomp
-int launch_rowquad(qexxc_ctx* c, int ncomp, const double* fac4, double* q, long q_bstride, long q_cstride,
-                   cudaStream_t st);
+// tri: S was built with tri=1 (only valid for ncomp == 1, where the form is symmetric in i,j)
+int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride,
+                   long q_cstride, cudaStream_t st);
 // H[b] = ao0^T diag(s) ao0 (Bsrc == nullptr, symmetric) or ao0^T Bsrc (general);
 // out[b][i][j] = scale * (H[i][j] + (tadd ? H[j][i] : 0)), i,j < N, row stride N
 int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bsrc, double scale, int tadd,

@@ -43,7 +43,9 @@ template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, double* __restrict__ q,
                int Npad, long ao_cstride, long ao_bstride, long S_bstride, long q_cstride,
-               long q_bstride, int ncomp, double f0, double f1, double f2, double f3) {
+               long q_bstride, int ncomp, int tri, double f0, double f1, double f2, double f3) {
+    // tri != 0: S holds only its upper triangle (diagonal halved), so column tile nt needs the
+    // reduction rows k < (nt+1)*BN only; the caller folds the factor 2 into f0.
     using Cfg = RowquadCfg<BN>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
@@ -72,7 +74,8 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
         // ---------------- producer warp ----------------
         int it = 0;
         for (int nt = 0; nt < NT; ++nt) {
-            for (int kb = 0; kb < KB; ++kb, ++it) {
+            const int kend = tri ? min(KB, (nt + 1) * (BN / BK)) : KB;
+            for (int kb = 0; kb < kend; ++kb, ++it) {
                 const int s = it % NSTAGE;
                 const uint32_t u = (uint32_t)(it / NSTAGE);
                 mbar_wait(empty + s, (u & 1) ^ 1);
@@ -111,7 +114,8 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
 #pragma unroll
             for (int nj = 0; nj < NB; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
 
-        for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int kend = tri ? min(KB, (nt + 1) * (BN / BK)) : KB;
+        for (int kb = 0; kb < kend; ++kb, ++it) {
             const int s = it % NSTAGE;
             const uint32_t u = (uint32_t)(it / NSTAGE);
             mbar_wait(full + s, u & 1);
@@ -317,9 +321,10 @@ __global__ void wsyrk_reduce_kernel(const double* __restrict__ part, double* __r
     out[(long)b * out_bstride + (long)i * N + j] = scale * (tadd ? hij + hji : hij);
 }
 
-// S[b][i][j] (Npad x Npad, zero padded) from src[b][N][N]: mode 0 (a+a^T)/2, 1 a, 2 a+a^T
+// S[b][i][j] (Npad x Npad, zero padded) from src[b][N][N]: mode 0 (a+a^T)/2, 1 a, 2 a+a^T.
+// tri != 0 keeps the upper triangle only, diagonal halved:  x^T S x = 2 x^T triu'(S) x.
 __global__ void pad_sym_kernel(const double* __restrict__ src, double* __restrict__ S, int N, int Npad,
-                               int mode) {
+                               int mode, int tri) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y, b = blockIdx.z;
     if (j >= Npad) return;
@@ -328,6 +333,7 @@ __global__ void pad_sym_kernel(const double* __restrict__ src, double* __restric
         const double* a = src + (long)b * N * N;
         const double x = a[(long)i * N + j], y = a[(long)j * N + i];
         v = mode == 0 ? 0.5 * (x + y) : (mode == 1 ? x : x + y);
+        if (tri) v = i < j ? v : (i == j ? 0.5 * v : 0.0);
     }
     S[(long)b * Npad * Npad + (long)i * Npad + j] = v;
 }
@@ -391,14 +397,14 @@ int wsyrk_pick_nsplit(int num_sms, int Npad, int Gpad, int B, bool sym) {
     return best;
 }
 
-int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, cudaStream_t st) {
+int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, int tri, cudaStream_t st) {
     dim3 grid((c->Npad + 127) / 128, c->Npad, c->B);
-    pad_sym_kernel<<<grid, 128, 0, st>>>(src, c->S, c->N, c->Npad, mode);
+    pad_sym_kernel<<<grid, 128, 0, st>>>(src, c->S, c->N, c->Npad, mode, tri);
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;
 }
 
-int launch_rowquad(qexxc_ctx* c, int ncomp, const double* fac4, double* q, long q_bstride,
+int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride,
                    long q_cstride, cudaStream_t st) {
     const int BN = pick_bn(c->Npad);
     dim3 grid(c->Gpad / BM, c->B);
@@ -407,8 +413,8 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, const double* fac4, double* q, long 
     do {                                                                                         \
         QX_TRY(set_smem(rowquad_kernel<BNV>, RowquadCfg<BNV>::SMEM));                            \
         rowquad_kernel<BNV><<<grid, NTHREADS, RowquadCfg<BNV>::SMEM, st>>>(                      \
-            c->ao, c->S, q, c->Npad, ao_cs, ao_bs, S_bs, q_cstride, q_bstride, ncomp, fac4[0],   \
-            fac4[1], fac4[2], fac4[3]);                                                          \
+            c->ao, c->S, q, c->Npad, ao_cs, ao_bs, S_bs, q_cstride, q_bstride, ncomp, tri,       \
+            (tri ? 2.0 : 1.0) * fac4[0], fac4[1], fac4[2], fac4[3]);                                                          \
     } while (0)
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
     if (BN == 128) QX_RQ(128);
