@@ -1,0 +1,212 @@
+"""Host mirror of ``qedft/train/td/numint_legacy.py`` for the accelerated branches.
+
+``NumInt.nr_rks(mol, grids, xc_code, dms, relativity=0, hermi=0, max_memory=2000, verbose=None,
+params=None) -> (nelec, excsum, vmat)`` (numint_legacy.py:122-348,588), ``eval_rho`` (:351-397) and
+``eval_ao`` (pyscf ``numint.eval_ao`` as used at trainer_legacy_no_jit.py:273) with the same
+argument meaning and error behaviour.  ``mol`` / ``grids`` are duck-typed (``mol._atm/_bas/_env``,
+``mol.nao_nr()``, ``grids.coords``, ``grids.weights``), so pyscf objects work unchanged.
+
+Two ways to evaluate the functional, as in the reference where ``ni.eval_xc`` is whatever
+``define_xc_`` installed:
+  * ``ni.eval_xc = qex_b200.xc.make_eval_xc(network, is_global_xc)``  -> the whole call is ONE
+    fused device pass (``qexxc_nr_rks_fwd``), and ``nr_rks_vjp`` gives the reverse rule;
+  * any other Python callable ``eval_xc(xc_code, rho, spin, relativity, deriv, verbose, params)``
+    (the reference's tests use a toy ``0.01*rho**2``) -> rho is brought to the host for the callback
+    and stages 2/4 still run on the device (``qexxc_eval_rho`` + ``qexxc_vxc_assemble``).
+Differences from the reference, on purpose: no ``SWITCH_SIZE`` limit on nao (numint_legacy.py:451,465
+raise ``NotImplementedError`` above it); AO values are evaluated on the device, not by pyscf.
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import numpy as np
+
+from . import _lib
+from .engine import NetSpec, XCContext
+from .xc import _native_apply, _theta
+from .xc import eval_xc as _native_eval_xc
+
+
+def _np(x):
+    import torch
+
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def _xctype(ni, xc_code):
+    """numint_legacy.py:133-140."""
+    if isinstance(xc_code, str) and "NN" in xc_code:
+        return xc_code
+    if isinstance(xc_code, str) and xc_code.upper() in ("LDA", "GGA"):
+        return xc_code.upper()
+    t = getattr(ni, "_xc_type_override", None)
+    if t is not None:
+        return t
+    raise NotImplementedError(
+        f"xc_code {xc_code!r}: only 'NN', 'NN-AmplitudeEncoding', 'LDA' and 'GGA' (with a callable eval_xc) are on "
+        "the accelerated path; libxc functionals stay with pyscf")
+
+
+class NumInt:
+    """Drop-in for ``numint_legacy.NumInt`` on the accelerated branches."""
+
+    def __init__(self, device: int | None = None, cache_ao: bool = False):
+        self.eval_xc = None  # installed by the caller / define_xc_
+        self.device = device
+        self.cache_ao = cache_ao
+        self._ctxs = {}
+        self._ao_key = {}
+
+    # ---- context management ---------------------------------------------------------------
+    def _native(self):
+        fn = self.eval_xc
+        if isinstance(fn, partial) and fn.func is _native_eval_xc:
+            return _native_apply(fn.keywords["network"]), bool(fn.keywords.get("is_global_xc", True))
+        return None, None
+
+    def _ctx(self, nao, ngrids, ncomp, spec: NetSpec | None):
+        key = (nao, ncomp, None if spec is None else tuple(sorted(vars(spec).items())))
+        ctx = self._ctxs.get(key)
+        if ctx is None or ctx.ngrids_max < ngrids:
+            if ctx is not None:
+                ctx.close()
+            ctx = XCContext(nao=nao, ngrids_max=ngrids, ncomp=ncomp, net=spec, device=self.device)
+            self._ctxs[key] = ctx
+            self._ao_key.pop(id(ctx), None)
+        return ctx
+
+    def _load(self, ctx, mol, grids, deriv):
+        """Stage 1 on the device: grid upload + AO evaluation (re-done per call like the reference's
+        block_loop, unless cache_ao and the same mol/grid fingerprint)."""
+        coords, weights = np.asarray(grids.coords), np.asarray(grids.weights)
+        fp = (hash(np.asarray(mol._env).tobytes()), coords.shape, float(coords.sum()), float(weights.sum()), deriv)
+        if self.cache_ao and self._ao_key.get(id(ctx)) == fp:
+            return
+        ctx.set_grid(coords, weights)
+        ctx.set_basis(mol._atm, mol._bas, mol._env)
+        ctx.eval_ao(deriv)
+        self._ao_key[id(ctx)] = fp
+
+    # ---- B2 -------------------------------------------------------------------------------
+    def eval_ao(self, mol, coords, deriv=0, **kwargs):
+        """-> [G, N] (deriv=0) or [4, G, N] (deriv=1), float64 numpy."""
+        if deriv not in (0, 1):
+            raise NotImplementedError("eval_ao: deriv must be 0 or 1 on the accelerated path")
+        coords = np.asarray(coords, dtype=np.float64)
+        ncomp = 4 if deriv else 1
+        ctx = self._ctx(mol.nao_nr(), coords.shape[0], ncomp, None)
+        ctx.set_grid(coords, np.ones(coords.shape[0]))
+        ctx.set_basis(mol._atm, mol._bas, mol._env)
+        ctx.eval_ao(deriv)
+        self._ao_key.pop(id(ctx), None)
+        ao = ctx.get_ao(ncomp)[0].cpu().numpy()
+        return ao[0] if deriv == 0 else ao
+
+    def eval_rho(self, mol, ao, dm, non0tab=None, xctype="LDA", hermi=0, verbose=None):
+        """numint_legacy.py:351-397: ao [G,N] (LDA) or [4,G,N] (GGA) -> rho [G] or [4,G]."""
+        xctype = xctype.upper()
+        if xctype in ("LDA", "HF"):
+            ncomp = 1
+        elif xctype in ("GGA", "NLC"):
+            ncomp = 4
+        else:
+            raise NotImplementedError("eval_rho: meta-GGA is not on the accelerated path")
+        ao = _np(ao)
+        G, N = ao.shape[-2], ao.shape[-1]
+        ctx = self._ctx(N, G, ncomp, None)
+        ctx.set_grid(None, np.ones(G))
+        ctx.set_ao(ao, ncomp)
+        self._ao_key.pop(id(ctx), None)
+        rho = ctx.eval_rho(_np(dm), ncomp, hermi)[0].cpu().numpy()
+        return rho[0] if ncomp == 1 else rho
+
+    # ---- B1 -------------------------------------------------------------------------------
+    def nr_rks(self, mol, grids, xc_code, dms, relativity=0, hermi=0, max_memory=2000, verbose=None, params=None,
+               return_resid=False):
+        xctype = _xctype(self, xc_code)
+        dms = _np(dms)
+        single = dms.ndim == 2
+        dm_list = [dms] if single else list(dms)
+        fn, is_global = self._native()
+        gga = xctype == "GGA"
+        ncomp = 4 if gga else 1
+        N, G = mol.nao_nr(), int(np.asarray(grids.weights).shape[0])
+        nelec, excsum, vmat, resids = [], [], [], []
+        if fn is not None:
+            if xctype == "NN-AmplitudeEncoding" and not is_global:
+                raise ValueError("xctype 'NN-AmplitudeEncoding' needs eval_xc built with is_global_xc=True")
+            ctx = self._ctx(N, G, ncomp, fn.qex_spec)
+            self._load(ctx, mol, grids, 1 if gga else 0)
+            theta = _theta(fn, params)
+            for dm in dm_list:
+                out, resid = ctx.nr_rks_fwd(dm, theta, "NN" if xctype == "LDA" else xctype, hermi,
+                                            want_resid=return_resid)
+                o = out[0].cpu().numpy()
+                vmat.append(o[: N * N].reshape(N, N).copy())
+                excsum.append(float(o[N * N]))
+                nelec.append(float(o[N * N + 1]))
+                resids.append(resid)
+        else:
+            if not callable(self.eval_xc):
+                raise ValueError("NumInt.eval_xc is not set: install a functional first (define_xc_)")
+            ctx = self._ctx(N, G, ncomp, None)
+            self._load(ctx, mol, grids, 1 if gga else 0)
+            for dm in dm_list:
+                rho = ctx.eval_rho(dm, ncomp, hermi)
+                r = rho[0].cpu().numpy()
+                exc, vxc = self.eval_xc(xc_code, r[0] if ncomp == 1 else r, spin=0, relativity=relativity, deriv=1,
+                                        verbose=verbose, params=params)[:2]
+                kind = "NN-AmplitudeEncoding" if xctype == "NN-AmplitudeEncoding" else ("GGA" if gga else "NN")
+                out = ctx.vxc_assemble(rho, np.atleast_1d(_np(exc)), _np(vxc[0]), _np(vxc[1]) if gga else None, kind)
+                o = out[0].cpu().numpy()
+                vmat.append(o[: N * N].reshape(N, N).copy())
+                excsum.append(float(o[N * N]))
+                nelec.append(float(o[N * N + 1]))
+                resids.append(None)
+        if single:  # numint_legacy.py:344-348
+            res = (nelec[0], excsum[0], vmat[0])
+            return res + (resids[0],) if return_resid else res
+        res = (nelec, excsum, vmat)
+        return res + (resids,) if return_resid else res
+
+    def nr_rks_vjp(self, mol, grids, xc_code, resid, e_bar, v_bar, hermi=0, params=None):
+        """Reverse rule of ``nr_rks`` (native functional only): cotangents of (excsum, vmat) ->
+        (dm_bar [N,N], theta_bar flat).  ``resid`` comes from ``nr_rks(..., return_resid=True)``."""
+        fn, _ = self._native()
+        if fn is None:
+            raise NotImplementedError("nr_rks_vjp needs a native functional (xc.make_eval_xc)")
+        xctype = _xctype(self, xc_code)
+        gga = xctype == "GGA"
+        N, G = mol.nao_nr(), int(np.asarray(grids.weights).shape[0])
+        ctx = self._ctx(N, G, 4 if gga else 1, fn.qex_spec)
+        self._load(ctx, mol, grids, 1 if gga else 0)
+        theta = _theta(fn, params)
+        bar = ctx.nr_rks_vjp(theta, resid, np.atleast_1d(np.asarray(e_bar, dtype=np.float64)), _np(v_bar),
+                             "NN" if xctype == "LDA" else xctype, hermi).cpu().numpy()
+        return bar[: N * N].reshape(N, N), bar[N * N :]
+
+
+_default = None
+
+
+def _ni():
+    global _default
+    if _default is None:
+        _default = NumInt()
+    return _default
+
+
+def eval_ao(mol, coords, deriv=0, **kwargs):
+    """``pyscf.dft.numint.eval_ao`` as the trainer calls it (trainer_legacy_no_jit.py:273)."""
+    return _ni().eval_ao(mol, coords, deriv, **kwargs)
+
+
+def eval_rho(mol, ao, dm, non0tab=None, xctype="LDA", hermi=0, verbose=None):
+    """numint_legacy.py:351."""
+    return _ni().eval_rho(mol, ao, dm, non0tab, xctype, hermi, verbose)
+
+
+def nr_rks(ni, mol, grids, xc_code, dms, relativity=0, hermi=0, max_memory=2000, verbose=None, params=None):
+    """numint_legacy.py:122 (free-function form; ``NumInt.nr_rks = nr_rks`` at :588)."""
+    return ni.nr_rks(mol, grids, xc_code, dms, relativity, hermi, max_memory, verbose, params)

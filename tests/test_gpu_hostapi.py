@@ -1,0 +1,229 @@
+"""GPU tests of the reference-facing host API (numint / xc / networks / autograd) and of the
+full-size workload through size-independent properties."""
+import numpy as np
+import pytest
+
+from oracle import gto_ref, mlp_ref, numint_ref, qnn_ref, step_ref
+from tests._util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL64 = 1e-10
+
+
+def _h2():
+    from qex_b200 import gen_grid, gto
+
+    mol = gto.h2(0.74, "6-31g")
+    grids = gen_grid.Grids(mol, n_rad=31, n_theta=5, n_phi=4).build()  # 1240 points like the README run
+    rng = np.random.default_rng(0)
+    c = rng.standard_normal((mol.nao_nr(), 1)) * 0.4
+    return mol, grids, 2.0 * c @ c.T
+
+
+def test_local_mlp_network_interface_matches_reference_semantics():
+    from qex_b200.networks import LocalMLP, adapt_stax_for_training
+
+    G = 513
+    init_fn, apply_fn = LocalMLP({"n_neurons": 64, "n_layers": 3, "activation": "tanh"}).build_network(np.zeros(G))
+    out_shape, params = init_fn(0, (-1, G, 1))
+    assert out_shape == (-1, G, 1) and len(params) == 7 and params[1] == ()
+    assert params[0][0].shape == (1, 64) and params[6][0].shape == (64, 1)
+    rho = np.abs(np.random.default_rng(1).standard_normal(G))
+    y = apply_fn(params, rho)
+    spec = mlp_ref.MLPSpec([1, 64, 64, 64, 1], "tanh")
+    theta = mlp_ref.pack(*mlp_ref.from_stax(params))
+    assert isinstance(y, np.ndarray) and y.shape == (G,)
+    assert rel_err(y, mlp_ref.apply_local(spec, theta, rho)) <= TOL64
+    assert rel_err(apply_fn(params, rho[:, None]), y) == 0.0  # [G,1] accepted like the 3D local path
+    adapter, fparams = adapt_stax_for_training(init_fn, apply_fn, (G,))
+    assert rel_err(adapter.apply(fparams, rho), apply_fn(fparams["params"]["stax_params"], rho)) == 0.0
+    with pytest.raises(ValueError):
+        LocalMLP({"activation": "nope"}).build_network(np.zeros(G))
+    with pytest.raises(ValueError):
+        LocalMLP({"use_amplitude_encoding": True})
+
+
+def test_qnn_and_global_network_interfaces():
+    from qex_b200.networks import GlobalMLP, LocalQNN
+
+    G = 200
+    init_fn, apply_fn = LocalQNN({"n_qubits": 6, "n_layers": 2}).build_network(np.zeros(G))
+    _, theta = init_fn(3, None)
+    assert theta.shape == (36,) and np.abs(theta).max() <= 0.1
+    x = np.abs(np.random.default_rng(2).standard_normal(G))
+    y = apply_fn(theta, x)
+    assert rel_err(y, qnn_ref.apply(qnn_ref.QNNSpec(6, 2), theta, x)) <= TOL64
+    assert rel_err(apply_fn(theta, x[:, None]), y) == 0.0
+    with pytest.raises(ValueError):
+        apply_fn(theta, np.zeros((G, 2)))
+    ginit, gapply = GlobalMLP().build_network(np.zeros(G))
+    _, gp = ginit(0, None)
+    gy = gapply(gp, x)
+    gspec = mlp_ref.MLPSpec([G, 64, 64, 64, 1], "tanh")
+    assert gy.shape == (1,)
+    assert rel_err(gy, mlp_ref.apply_global(gspec, mlp_ref.pack(*mlp_ref.from_stax(gp)), x)) <= TOL64
+
+
+def test_numint_eval_ao_eval_rho_like_the_trainer_density_loss():
+    """trainer_legacy_no_jit.py:271-275: ao = numint.eval_ao(mol, coords); rho = eval_rho(mol, ao, dm)."""
+    from qex_b200 import numint
+
+    mol, grids, dm = _h2()
+    ao = numint.eval_ao(mol, grids.coords, deriv=0)
+    ref = gto_ref.eval_ao(mol._atm, mol._bas, mol._env, grids.coords, 0)
+    assert ao.shape == ref.shape and np.abs(ao - ref).max() <= 1e-13
+    rho = numint.eval_rho(mol, ao, dm, xctype="LDA")
+    assert rel_err(rho, numint_ref.eval_rho(ref, dm, "LDA")) <= TOL64
+    ao1 = numint.eval_ao(mol, grids.coords, deriv=1)
+    rho4 = numint.eval_rho(mol, ao1, dm, xctype="GGA")
+    assert rho4.shape == (4, grids.size)
+    assert rel_err(rho4, numint_ref.eval_rho(gto_ref.eval_ao(mol._atm, mol._bas, mol._env, grids.coords, 1), dm, "GGA")) <= TOL64
+    with pytest.raises(NotImplementedError):
+        numint.eval_rho(mol, ao1, dm, xctype="MGGA")
+
+
+def test_nr_rks_with_host_callback_like_reference_tests():
+    """tests/test_numint.py:81-205 of the reference: ni.eval_xc = toy functional; 'NN' and
+    'NN-AmplitudeEncoding' branches; here with numbers checked, not only types."""
+    from qex_b200.numint import NumInt
+
+    mol, grids, dm = _h2()
+    ao = gto_ref.eval_ao(mol._atm, mol._bas, mol._env, grids.coords, 0)
+
+    def eval_xc(xc_code, rho, *args, **kwargs):
+        return 0.01 * rho**2, (0.02 * rho, None, None, None), None, None
+
+    def eval_xc_amp(xc_code, rho, *args, **kwargs):
+        return np.sum(0.01 * rho**2), (0.02 * rho, None, None, None), None, None
+
+    ni = NumInt()
+    ni.eval_xc = eval_xc
+    nelec, exc, vxc = ni.nr_rks(mol, grids, "NN", dm, params={"weights": np.zeros(3)})
+    assert isinstance(nelec, float) and isinstance(exc, float) and vxc.ndim == 2
+    n0, e0, v0 = numint_ref.nr_rks(ao, grids.weights, dm, eval_xc, "NN")
+    assert abs(nelec - n0) <= 1e-9 and abs(exc - e0) <= 1e-9 and rel_err(vxc, v0) <= TOL64
+    ni.eval_xc = eval_xc_amp
+    nelec, exc, vxc = ni.nr_rks(mol, grids, "NN-AmplitudeEncoding", dm)
+    n1, e1, v1 = numint_ref.nr_rks(ao, grids.weights, dm, eval_xc_amp, "NN-AmplitudeEncoding")
+    assert abs(exc - e1) <= 1e-9 and rel_err(vxc, v1) <= TOL64
+    # nset > 1 returns lists (numint_legacy.py:344-348)
+    ni.eval_xc = eval_xc
+    nl, el, vl = ni.nr_rks(mol, grids, "NN", np.stack([dm, 0.5 * dm]))
+    assert len(nl) == 2 and abs(el[0] - e0) <= 1e-9
+    with pytest.raises(NotImplementedError):
+        ni.nr_rks(mol, grids, "b3lyp", dm)
+
+
+@pytest.mark.parametrize("kind", ["local", "global", "qnn"])
+def test_nr_rks_native_functional_and_vjp(kind):
+    from qex_b200 import xc
+    from qex_b200.networks import GlobalMLP, LocalMLP, LocalQNN
+    from qex_b200.numint import NumInt
+
+    mol, grids, dm = _h2()
+    G, N = grids.size, mol.nao_nr()
+    ao = gto_ref.eval_ao(mol._atm, mol._bas, mol._env, grids.coords, 0)
+    rng = np.random.default_rng(4)
+    e_bar, v_bar = 0.8, rng.standard_normal((N, N))
+    if kind == "local":
+        net = LocalMLP().build_network(grids.coords)
+        params = net[0](0, None)[1]
+        netd = dict(kind="local_mlp", n_features=1, n_hidden=3, width=64)
+        theta, code, glob = mlp_ref.pack(*mlp_ref.from_stax(params)), "NN", False
+    elif kind == "global":
+        net = GlobalMLP().build_network(grids.coords)
+        params = net[0](0, None)[1]
+        netd = dict(kind="global_mlp", n_hidden=3, width=64)
+        theta, code, glob = mlp_ref.pack(*mlp_ref.from_stax(params)), "NN-AmplitudeEncoding", True
+    else:
+        net = LocalQNN({"n_qubits": 6, "n_layers": 2}).build_network(grids.coords)
+        params = net[0](0, None)[1]
+        netd = dict(kind="local_qnn", n_hidden=2, width=6, in_scale=1.0)
+        theta, code, glob = params, "NN", False
+    ni = NumInt()
+    ni.eval_xc = xc.make_eval_xc(net, is_global_xc=glob)
+    nelec, exc, vmat, resid = ni.nr_rks(mol, grids, code, dm, params=params, return_resid=True)
+    D, tb = ni.nr_rks_vjp(mol, grids, code, resid, e_bar, v_bar, params=params)
+    ref = step_ref.xc_step(mol._atm, mol._bas, mol._env, grids.coords, grids.weights, dm, netd, theta, code, e_bar, v_bar)
+    assert abs(exc - ref["excsum"]) <= 1e-9 and abs(nelec - ref["nelec"]) <= 1e-9
+    assert rel_err(vmat, ref["vmat"]) <= TOL64
+    assert rel_err(D, ref["dm_bar"]) <= TOL64 and rel_err(tb, ref["theta_bar"]) <= TOL64
+    # the standalone eval_xc keeps the reference's return structure
+    rho = numint_ref.eval_rho(ao, dm, "LDA")
+    e, (v, a, b, c), f, k = ni.eval_xc(code, rho, params=params)
+    assert (a, b, c, f, k) == (None,) * 5 and v.shape == (G,)
+    assert np.ndim(e) == (0 if glob else 1)
+
+
+def test_torch_autograd_wiring_matches_oracle_vjp():
+    import torch
+
+    from qex_b200 import autograd, workloads
+    from qex_b200.engine import XCContext
+
+    wl = workloads.make("c5", ngrids=1536)
+    N = wl.nao
+    ctx = XCContext(nao=N, ngrids_max=wl.ngrids, net=workloads.net_spec(wl))
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env).set_grid(wl.coords, wl.weights).eval_ao(0)
+    dm = torch.tensor(wl.dm, device="cuda", requires_grad=True)
+    th = torch.tensor(wl.theta, device="cuda", requires_grad=True)
+    vb = torch.tensor(wl.v_bar, device="cuda")
+    nelec, exc, vmat = autograd.nr_rks(ctx, dm, th, "NN")
+    loss = wl.e_bar * exc.sum() + (vb * vmat[0]).sum()
+    loss.backward()
+    m = wl.mol
+    ref = step_ref.xc_step(m._atm, m._bas, m._env, wl.coords, wl.weights, wl.dm, wl.net, wl.theta, "NN", wl.e_bar, wl.v_bar)
+    assert rel_err(dm.grad.cpu().numpy()[0] if dm.grad.dim() == 3 else dm.grad.cpu().numpy(), ref["dm_bar"]) <= TOL64
+    assert rel_err(th.grad.cpu().numpy(), ref["theta_bar"]) <= TOL64
+    assert not nelec.requires_grad
+    # density loss path
+    dm2 = torch.tensor(wl.dm, device="cuda", requires_grad=True)
+    rho = autograd.eval_rho(ctx, dm2)
+    w = torch.tensor(wl.weights, device="cuda")
+    (rho[0, 0] ** 2 * w).sum().backward()
+    ao = gto_ref.eval_ao(m._atm, m._bas, m._env, wl.coords, 0)
+    r = numint_ref.eval_rho(ao, wl.dm, "LDA")
+    assert rel_err(dm2.grad.cpu().numpy().reshape(N, N), numint_ref.eval_rho_vjp(ao, 2 * r * wl.weights, "LDA")) <= TOL64
+
+
+def test_full_size_c5_properties():
+    """BASELINE config c5 at full size (1000 AOs x 1e6 points): determinism, symmetry, additivity
+    over grid shards, and the first shard against the oracle."""
+    import torch
+
+    from qex_b200 import workloads
+    from qex_b200.engine import XCContext
+
+    wl = workloads.make("c5")
+    N, G = wl.nao, wl.ngrids
+    ctx = XCContext(nao=N, ngrids_max=G, net=workloads.net_spec(wl))
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env)
+
+    def run(lo, hi):
+        ctx.set_grid(wl.coords[lo:hi], wl.weights[lo:hi]).eval_ao(0)
+        out, resid = ctx.nr_rks_fwd(wl.dm, wl.theta, "NN")
+        bar = ctx.nr_rks_vjp(wl.theta, resid, [wl.e_bar], wl.v_bar, "NN")
+        return out.clone(), bar.clone()
+
+    out, bar = run(0, G)
+    out2, bar2 = run(0, G)
+    assert torch.equal(out, out2) and torch.equal(bar, bar2)  # bitwise run-to-run determinism
+    o = out.cpu().numpy()[0]
+    V = o[: N * N].reshape(N, N)
+    D = bar.cpu().numpy()[: N * N].reshape(N, N)
+    assert np.array_equal(V, V.T) and np.abs(D - D.T).max() <= 1e-13 * np.abs(D).max()
+    assert np.isfinite(o).all() and np.isfinite(bar.cpu().numpy()).all()
+    # additivity: a local functional's outputs are sums over grid points
+    cut = 2048
+    oa, ba = run(0, cut)
+    ob, bb = run(cut, G)
+    assert rel_err((oa + ob).cpu().numpy(), out.cpu().numpy()) <= 1e-11
+    assert rel_err((ba + bb).cpu().numpy(), bar.cpu().numpy()) <= 1e-11
+    m = wl.mol
+    ref = step_ref.xc_step(m._atm, m._bas, m._env, wl.coords[:cut], wl.weights[:cut], wl.dm, wl.net, wl.theta, "NN",
+                           wl.e_bar, wl.v_bar)
+    oa, ba = oa.cpu().numpy()[0], ba.cpu().numpy()
+    assert rel_err(oa[: N * N].reshape(N, N), ref["vmat"]) <= TOL64
+    assert abs(oa[N * N] - ref["excsum"]) <= 1e-9
+    assert rel_err(ba[: N * N].reshape(N, N), ref["dm_bar"]) <= TOL64
+    assert rel_err(ba[N * N :], ref["theta_bar"]) <= TOL64
