@@ -122,6 +122,138 @@ eval_ao_kernel(const double* __restrict__ coords, const ShellDev* __restrict__ s
     }
 }
 
+
+// ---- tiled evaluator -------------------------------------------------------------------------------
+// CTA = P grid points.  Phase A: every (point, atom) gets its 16 real solid harmonics (and their
+// gradients), every (point, radial function) its contracted radial sum -- each exp is evaluated
+// exactly once and staged in shared memory.  Phase B: warps sweep (point, 32-AO chunk) pairs;
+// lane n multiplies harmonic x radial for AO n and the warp stores 256 contiguous bytes of the AO
+// row, so the 8*N bytes per point stream to HBM fully coalesced.
+template <int L>
+__device__ __forceinline__ void fill_harm(double* __restrict__ H, int stride, bool deriv, double x, double y, double z) {
+#pragma unroll
+    for (int m = 0; m < 2 * L + 1; ++m) {
+        const V4 s = solid<L>(m, x, y, z);
+        H[(L * L + m) * stride] = s.v;
+        if (deriv) {  // rows 17.., 33.., 49.. hold d/dx, d/dy, d/dz
+            H[(17 + L * L + m) * stride] = s.x;
+            H[(33 + L * L + m) * stride] = s.y;
+            H[(49 + L * L + m) * stride] = s.z;
+        }
+    }
+}
+
+template <bool DERIV>
+__global__ void __launch_bounds__(256)
+eval_ao_tiled_kernel(const double* __restrict__ coords, const ShellDev* __restrict__ shells,
+                     const int* __restrict__ shell_atom, const int* __restrict__ atom_coord,
+                     const AoMeta* __restrict__ meta, int nshell, int natm, int nrad, int lmax,
+                     const double* __restrict__ env, int nenv, double* __restrict__ ao, int G, int Gpad,
+                     int GpadMax, int N, int Npad, int C, int P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // Hs[row][col], col = p*natm + atom, odd column stride (conflict-free both ways).
+    // rows: 0..15 harmonics | 16 r^2 | (DERIV) 17..64 d/dx,d/dy,d/dz of the harmonics | 65..67 x,y,z
+    constexpr int NROW = DERIV ? 68 : 17;
+    constexpr int RS = DERIV ? 2 : 1;  // per (point, radial): R0 (+ R1)
+    const int hstr = (P * natm) | 1;
+    double* Hs = reinterpret_cast<double*>(smem_raw);
+    double* Rs = Hs + (size_t)NROW * hstr;  // [P][nrad][RS]
+    const int b = blockIdx.y;
+    const long g0 = (long)blockIdx.x * P;
+    const double* envb = env + (long)b * nenv;
+    const long cstride = (long)GpadMax * Npad;
+    const int tid = threadIdx.x;
+
+    // ---- phase A1: harmonics and r^2 per (point, atom) ----
+    for (int it = tid; it < P * natm; it += blockDim.x) {
+        const int p = it / natm, ia = it - p * natm;
+        const long gi = g0 + p;
+        double x = 0, y = 0, z = 0;
+        if (gi < G) {
+            const double* r = coords + ((long)b * GpadMax + gi) * 3;
+            const int ac = atom_coord[ia];
+            x = r[0] - envb[ac];
+            y = r[1] - envb[ac + 1];
+            z = r[2] - envb[ac + 2];
+        }
+        double* H = Hs + it;
+        fill_harm<0>(H, hstr, DERIV, x, y, z);
+        fill_harm<1>(H, hstr, DERIV, x, y, z);
+        if (lmax >= 2) fill_harm<2>(H, hstr, DERIV, x, y, z);
+        if (lmax >= 3) fill_harm<3>(H, hstr, DERIV, x, y, z);
+        H[16 * hstr] = x * x + y * y + z * z;
+        if (DERIV) {
+            H[65 * hstr] = x;
+            H[66 * hstr] = y;
+            H[67 * hstr] = z;
+        }
+    }
+    __syncthreads();
+    // ---- phase A2: radial sums; an item = one shell x two points (shell data loaded once) ----
+    const int npair = (P + 1) >> 1;
+    for (int it = tid; it < nshell * npair; it += blockDim.x) {
+        const int pp = it / nshell, s = it - pp * nshell;
+        const ShellDev sh = shells[s];
+        const int ia = shell_atom[s];
+        const double* ex = envb + sh.ptr_exp;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p = 2 * pp + h;
+            if (p >= P) break;
+            const bool live = g0 + p < G;
+            const double rr = Hs[16 * hstr + p * natm + ia];
+            for (int ic = 0; ic < sh.nctr; ++ic) {
+                const double* cf = envb + sh.ptr_coef + ic * sh.nprim;
+                double R0 = 0.0, R1 = 0.0;
+                for (int q = 0; q < sh.nprim; ++q) {
+                    const double a = ex[q];
+                    const double e = cf[q] * exp(-a * rr);
+                    R0 += e;
+                    if (DERIV) R1 -= 2.0 * a * e;
+                }
+                double* R = Rs + ((size_t)p * nrad + sh.rad_off + ic) * RS;
+                R[0] = live ? R0 : 0.0;  // padding rows come out exactly zero
+                if (DERIV) R[1] = live ? R1 : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase B: a warp owns a 32-AO chunk for all P points; 256-byte coalesced row stores ----
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int nchunk = Npad >> 5;
+    int pmax = P;
+    if (g0 + pmax > Gpad) pmax = (int)(Gpad - g0);
+    for (int ch = warp; ch < nchunk; ch += nwarps) {
+        const int n = (ch << 5) + lane;
+        const AoMeta m = meta[n];
+        const bool on = m.lm >= 0;
+        const double* H = Hs + (on ? m.lm * hstr + m.atom : 0);
+        const double* R = Rs + (on ? m.rad * RS : 0);
+        double* row = ao + ((long)b * C * GpadMax + g0) * Npad + n;
+        for (int p = 0; p < pmax; ++p, row += Npad) {
+            double v0 = 0.0, vx = 0.0, vy = 0.0, vz = 0.0;
+            if (on) {
+                const double* Hp = H + p * natm;
+                const double h = Hp[0], R0 = R[(size_t)p * nrad * RS];
+                v0 = h * R0;
+                if (DERIV) {
+                    const double R1 = R[(size_t)p * nrad * RS + 1];
+                    const double* Xp = Hs + p * natm + m.atom;
+                    vx = Hp[17 * hstr] * R0 + h * Xp[65 * hstr] * R1;
+                    vy = Hp[33 * hstr] * R0 + h * Xp[66 * hstr] * R1;
+                    vz = Hp[49 * hstr] * R0 + h * Xp[67 * hstr] * R1;
+                }
+            }
+            row[0] = v0;
+            if (DERIV) {
+                row[cstride] = vx;
+                row[2 * cstride] = vy;
+                row[3 * cstride] = vz;
+            }
+        }
+    }
+}
+
 // user AO [B][ncomp][G][N] -> internal padded tensor (zero fill) and back
 __global__ void pack_ao_kernel(const double* __restrict__ src, double* __restrict__ ao, int ncomp, int G,
                                int Gpad, int GpadMax, int N, int Npad, int C) {
@@ -181,8 +313,30 @@ int launch_set_grid(qexxc_ctx* c, const double* coords, const double* weights, i
 }
 
 int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
-    dim3 grid(grid_for((long)c->Gpad * 32, 256, c->num_sms), c->B);
     ProfScope prof(c, QEXXC_PROF_EVAL_AO, st);
+    // tiled kernel when the per-point staging fits in shared memory (it does up to ~1500 atoms)
+    const size_t per_pt = ((size_t)c->natm * (deriv ? 68 : 17) + (size_t)c->nrad * (deriv ? 2 : 1)) * 8;
+    int P = (int)((deriv ? 140 * 1024 : 100 * 1024) / (per_pt ? per_pt : 1));
+    if (P > 16) P = 16;
+    if (P >= 1) {
+        const size_t smem = ((size_t)(deriv ? 68 : 17) * (((size_t)P * c->natm) | 1) +
+                             (size_t)P * c->nrad * (deriv ? 2 : 1)) * 8;
+        dim3 tgrid((unsigned)((c->Gpad + P - 1) / P), c->B);
+        if (deriv) {
+            QX_CUDA(cudaFuncSetAttribute(eval_ao_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            eval_ao_tiled_kernel<true><<<tgrid, 256, smem, st>>>(c->coords, c->shells, c->shell_atom, c->atom_coord,
+                c->ao_meta, c->nshell, c->natm, c->nrad, c->lmax, c->env, c->nenv, c->ao, c->G, c->Gpad, c->GpadMax,
+                c->N, c->Npad, c->C, P);
+        } else {
+            QX_CUDA(cudaFuncSetAttribute(eval_ao_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            eval_ao_tiled_kernel<false><<<tgrid, 256, smem, st>>>(c->coords, c->shells, c->shell_atom, c->atom_coord,
+                c->ao_meta, c->nshell, c->natm, c->nrad, c->lmax, c->env, c->nenv, c->ao, c->G, c->Gpad, c->GpadMax,
+                c->N, c->Npad, c->C, P);
+        }
+        QX_LAUNCH_CHECK(c);
+        return QEXXC_OK;
+    }
+    dim3 grid(grid_for((long)c->Gpad * 32, 256, c->num_sms), c->B);
     eval_ao_kernel<<<grid, 256, 0, st>>>(c->coords, c->shells, c->nshell, c->env, c->nenv, c->ao, c->G,
                                          c->Gpad, c->GpadMax, c->N, c->Npad, c->C, deriv);
     QX_LAUNCH_CHECK(c);

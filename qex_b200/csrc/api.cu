@@ -302,7 +302,10 @@ int qexxc_set_basis(qexxc_ctx* c, const int* atm, int natm, const int* bas, int 
     QX_ARG(atm && bas && env && natm > 0 && nbas > 0 && nenv > 0, "null/empty basis tables");
     QX_CUDA(cudaSetDevice(c->device));
     std::vector<ShellDev> sh(nbas);
-    int off = 0;
+    std::vector<AoMeta> meta(c->Npad, AoMeta{0, 0, -1});
+    std::vector<int> acoord(natm), shatom(nbas);
+    for (int ia = 0; ia < natm; ++ia) acoord[ia] = atm[6 * ia + 1];
+    int off = 0, rad = 0, lmax = 0;
     for (int ib = 0; ib < nbas; ++ib) {
         const int* b = bas + 8 * ib;  // ATOM_OF, ANG_OF, NPRIM_OF, NCTR_OF, KAPPA_OF, PTR_EXP, PTR_COEFF
         const int ia = b[0], l = b[1], nprim = b[2], nctr = b[3];
@@ -315,9 +318,18 @@ int qexxc_set_basis(qexxc_ctx* c, const int* atm, int natm, const int* bas, int 
         QX_ARG(pc >= 0 && pc + 3 <= nenv && b[5] >= 0 && b[5] + nprim <= nenv && b[6] >= 0 &&
                    b[6] + nprim * nctr <= nenv,
                "bas/atm pointers exceed env");
-        sh[ib] = ShellDev{pc, l, nprim, nctr, b[5], b[6], off, 0};
+        sh[ib] = ShellDev{pc, l, nprim, nctr, b[5], b[6], off, rad};
+        shatom[ib] = ia;
+        if (l > lmax) lmax = l;
+        for (int ic = 0; ic < nctr; ++ic)
+            for (int m = 0; m < 2 * l + 1; ++m) {
+                const int n = off + ic * (2 * l + 1) + m;
+                if (n < c->Npad) meta[n] = AoMeta{rad + ic, (short)ia, (short)(l * l + m)};
+            }
         off += (2 * l + 1) * nctr;
+        rad += nctr;
     }
+    QX_ARG(natm < 32768, "too many atoms");
     if (off != c->N) {
         set_error("basis has %d spherical AOs but the context was created with nao = %d", off, c->N);
         return QEXXC_ERR_ARG;
@@ -332,6 +344,21 @@ int qexxc_set_basis(qexxc_ctx* c, const int* atm, int natm, const int* bas, int 
         QX_TRY(dev_alloc(c, &c->env, (size_t)c->B * nenv, false));
         c->nenv = nenv;
     }
+    if (!c->ao_meta) QX_TRY(dev_alloc(c, &c->ao_meta, (size_t)c->Npad, false));
+    if (c->natm != natm || !c->atom_coord) {
+        c->atom_coord = nullptr;
+        QX_TRY(dev_alloc(c, &c->atom_coord, (size_t)natm, false));
+    }
+    if (!c->shell_atom || c->nshell != nbas) {
+        c->shell_atom = nullptr;
+        QX_TRY(dev_alloc(c, &c->shell_atom, (size_t)nbas, false));
+    }
+    c->natm = natm;
+    c->nrad = rad;
+    c->lmax = lmax;
+    QX_CUDA(cudaMemcpy(c->ao_meta, meta.data(), sizeof(AoMeta) * c->Npad, cudaMemcpyHostToDevice));
+    QX_CUDA(cudaMemcpy(c->atom_coord, acoord.data(), sizeof(int) * natm, cudaMemcpyHostToDevice));
+    QX_CUDA(cudaMemcpy(c->shell_atom, shatom.data(), sizeof(int) * nbas, cudaMemcpyHostToDevice));
     QX_CUDA(cudaMemcpy(c->shells, sh.data(), sizeof(ShellDev) * nbas, cudaMemcpyHostToDevice));
     QX_CUDA(cudaMemcpy(c->env, env, sizeof(double) * (size_t)c->B * nenv, cudaMemcpyHostToDevice));
     c->have_basis = true;

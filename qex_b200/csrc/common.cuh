@@ -59,7 +59,13 @@ struct ShellDev {
     int ptr_exp;
     int ptr_coef;
     int ao_off;  // first AO index of this shell
-    int pad;
+    int rad_off; // first radial-function index (one per contraction) of this shell
+};
+// Per-AO lookup for the tiled AO kernel: which radial function, which atom, which harmonic.
+struct AoMeta {
+    int rad;     // radial-function index
+    short atom;  // atom index
+    short lm;    // l*l + m, m = 0..2l
 };
 
 }  // namespace qexxc
@@ -84,6 +90,10 @@ struct qexxc_ctx {
     int nshell = 0;
     double* env = nullptr;  // [B][nenv]
     int nenv = 0;
+    qexxc::AoMeta* ao_meta = nullptr;  // [Npad]
+    int* atom_coord = nullptr;         // [natm] offset of (x,y,z) in env
+    int* shell_atom = nullptr;         // [nshell]
+    int natm = 0, nrad = 0, lmax = 0;
 
     // stage 2/4 workspaces (all [B][...][GpadMax] rows are zero beyond G)
     double* S = nullptr;        // [B][Npad][Npad] padded symmetric operand (dm or V_bar + V_bar^T)
