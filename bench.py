@@ -329,12 +329,9 @@ def run_ours(args):
         # 2*G*N^2 algorithmic FLOP each -> 8*N^2 FLOP per grid point per step)
         fl = 2.0 * Gl * N * N
         # executed DMMA FLOPs per launch (zero-padded tiles, symmetric operands skipped):
-        Np, Gp = ctx_npad(N), ((Gl + 127) // 128) * 128
-        BN = 128 if Np % 128 == 0 else (64 if Np % 64 == 0 else 32)
-        NT = Np // BN
+        # (counted by the library with the same predicates the kernels use)
         tri = wl.ncomp == 1
-        ex = {"rowquad": 2.0 * Gp * BN * BN * (NT * (NT + 1) / 2 if tri else NT * NT),
-              "wsyrk": 2.0 * Gp * BN * BN * (NT * (NT + 1) / 2 if tri else NT * NT)}
+        ex = {"rowquad": ctx.contraction_flops(0, tri), "wsyrk": ctx.contraction_flops(1, tri)}
         kern = {}
         for name in ("rowquad", "wsyrk", "xc_fwd", "xc_vjp", "eval_ao"):
             ms, n = prof[name]
@@ -384,7 +381,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def ctx_npad(N):
+def ctx_npad(N):  # AO row pitch: a multiple of 32 columns (zeros in the pad)
     return ((N + 31) // 32) * 32
 
 

@@ -187,6 +187,9 @@ long qexxc_launch_count(const qexxc_ctx* ctx);
 #define QEXXC_PROF_NCLASS 5
 int qexxc_profile_enable(qexxc_ctx* ctx, int on);
 int qexxc_profile_read(qexxc_ctx* ctx, int cls, double* ms_total, long* count);
+/* DMMA FLOPs the contraction kernels actually execute for the current problem shape (zero-padded and
+ * structurally-zero blocks excluded): which = 0 rowquad, 1 wsyrk; symmetric = triangular variant. */
+int qexxc_contraction_flops(qexxc_ctx* ctx, int which, int symmetric, double* executed_flops);
 /* Runs only the dominant contraction kernel once on the current AO/S buffers (roofline timing):
  * which = 0 rowquad (rho-type), 1 wsyrk (vmat-type). */
 int qexxc_debug_run_contraction(qexxc_ctx* ctx, int which, void* stream);

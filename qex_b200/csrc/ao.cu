@@ -220,11 +220,12 @@ eval_ao_tiled_kernel(const double* __restrict__ coords, const ShellDev* __restri
     __syncthreads();
     // ---- phase B: a warp owns a 32-AO chunk for all P points; 256-byte coalesced row stores ----
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    const int nchunk = Npad >> 5;
+    const int nchunk = (Npad + 31) >> 5;
     int pmax = P;
     if (g0 + pmax > Gpad) pmax = (int)(Gpad - g0);
     for (int ch = warp; ch < nchunk; ch += nwarps) {
         const int n = (ch << 5) + lane;
+        if (n >= Npad) continue;
         const AoMeta m = meta[n];
         const bool on = m.lm >= 0;
         const double* H = Hs + (on ? m.lm * hstr + m.atom : 0);

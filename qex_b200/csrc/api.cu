@@ -195,6 +195,7 @@ int qexxc_create(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngrids_
     c->GpadMax = round_up(ngrids_max, kGTile);
     c->N = nao;
     c->Npad = round_up(nao, kNTile);
+    c->Nc = round_up(nao, kNBlock);
     if (net) c->net = *net;
     else c->net.kind = QEXXC_NET_NONE;
     c->n_theta = qexxc_n_params(&c->net, ngrids_max);
@@ -232,11 +233,17 @@ int qexxc_create(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngrids_
     QX_A(c->vgammab, B * Gp);
     if (C == 4) QX_A(c->aow, B * Gp * Np);
     {
-        const int ns_sym = wsyrk_pick_nsplit(c->num_sms, c->Npad, c->GpadMax, c->B, true);
-        const int ns_gen = wsyrk_pick_nsplit(c->num_sms, c->Npad, c->GpadMax, c->B, false);
-        c->nsplit_max = ns_sym > ns_gen ? ns_sym : ns_gen;
+        size_t part_doubles = 0;
+        wsyrk_workspace(c->num_sms, c->Nc, c->GpadMax, c->B, C == 4, &part_doubles, &c->ws_items_bytes);
+        QX_A(c->part, part_doubles);
+        c->ws_start_cap = (size_t)c->num_sms + 1;
+        for (int k = 0; k < 2; ++k) {
+            unsigned char* p = nullptr;
+            if (rc == QEXXC_OK) rc = dev_alloc(c, &p, c->ws_items_bytes);
+            c->ws_items[k] = p;
+            QX_A(c->ws_start[k], c->ws_start_cap);
+        }
     }
-    QX_A(c->part, B * (size_t)c->nsplit_max * Np * Np);
     size_t red = 2 * B * (size_t)stage4_nblocks(c) + 16;
     if (c->net.kind == QEXXC_NET_LOCAL_MLP) {
         const size_t r = (size_t)mlp_local_grid(c) * c->n_theta;
@@ -716,6 +723,12 @@ int qexxc_profile_read(qexxc_ctx* c, int cls, double* ms_total, long* count) {
     return QEXXC_OK;
 }
 
+int qexxc_contraction_flops(qexxc_ctx* c, int which, int symmetric, double* executed) {
+    QX_ARG(c != nullptr && executed != nullptr, "null pointer");
+    *executed = which == 0 ? rowquad_executed_flops(c, symmetric) : wsyrk_executed_flops(c, symmetric != 0);
+    return QEXXC_OK;
+}
+
 int qexxc_debug_run_contraction(qexxc_ctx* c, int which, void* stream) {
     QX_ARG(c != nullptr, "ctx is null");
     QX_TRY(need_ao(c, 1));
@@ -723,6 +736,7 @@ int qexxc_debug_run_contraction(qexxc_ctx* c, int which, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const long ld = c->GpadMax;
     if (which == 0) return launch_rowquad(c, 1, 1, kFacGGA, c->wvb, (long)c->C * ld, ld, st);
+    if (which == 2) return launch_rowquad(c, 1, 0, kFacGGA, c->wvb, (long)c->C * ld, ld, st);  // dense S (timing only)
     return launch_wsyrk(c, c->wv, (long)c->C * ld, nullptr, 1.0, 1, c->S, (long)c->N * c->N, st);
 }
 

@@ -47,7 +47,8 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 constexpr int kGTile = 128;  // grid rows are padded to a multiple of this
-constexpr int kNTile = 32;   // AO columns are padded to a multiple of this
+constexpr int kNTile = 32;   // AO row pitch (storage) is a multiple of this; pad columns hold real zeros
+constexpr int kNBlock = 8;   // compute extents are rounded to one DMMA block only
 inline int round_up(long x, int m) { return (int)(((x + m - 1) / m) * m); }
 
 // One contracted shell of the basis, flattened for the AO kernel.
@@ -72,7 +73,7 @@ struct AoMeta {
 
 struct qexxc_ctx {
     int device = 0;
-    int B = 1, C = 1, Gmax = 0, GpadMax = 0, N = 0, Npad = 0;
+    int B = 1, C = 1, Gmax = 0, GpadMax = 0, N = 0, Npad = 0, Nc = 0;  // Npad: storage pitch, Nc: compute extent
     int G = 0, Gpad = 0;  // current grid
     qexxc_net_desc net{};
     long n_theta = 0;
@@ -108,8 +109,11 @@ struct qexxc_ctx {
     double* vrhob = nullptr;    // [B][GpadMax]
     double* vgammab = nullptr;  // [B][GpadMax]
     double* aow = nullptr;      // [B][GpadMax][Npad] (C == 4 only)
-    double* part = nullptr;     // split-G partial tiles [B][nsplit_max][Npad][Npad]
-    int nsplit_max = 1;
+    double* part = nullptr;     // wsyrk partial tiles, one compact [BN][BN] slot per (batch, tile, grid chunk)
+    void* ws_items[2] = {nullptr, nullptr};  // wsyrk static schedules (general, symmetric)
+    int* ws_start[2] = {nullptr, nullptr};
+    long ws_key[2] = {-1, -1};
+    size_t ws_items_bytes = 0, ws_start_cap = 0;
     double* red = nullptr;      // per-CTA partial sums (excsum, nelec, theta_bar ...)
     size_t red_doubles = 0;
     void* tape = nullptr;       // MLP reverse-mode tape (per-CTA slots)
@@ -147,7 +151,10 @@ namespace qexxc {
 
 // ---- launchers implemented in the .cu files --------------------------------------------------
 // contract.cu
-int wsyrk_pick_nsplit(int num_sms, int Npad, int Gpad, int B, bool sym);
+void wsyrk_workspace(int num_sms, int Nc, int GpadMax, int B, bool general, size_t* part_doubles,
+                     size_t* item_bytes);
+double rowquad_executed_flops(const qexxc_ctx* c, int tri);
+double wsyrk_executed_flops(const qexxc_ctx* c, bool sym);
 // mode 0: (a+a^T)/2, 1: a, 2: a+a^T; tri: keep the upper triangle only (diagonal halved)
 int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, int tri, cudaStream_t st);
 // q[b][k][g] = fac[k] * sum_ij ao[b][k][g][i] S[b][i][j] ao[b][0][g][j], k < ncomp

@@ -7,12 +7,24 @@
 //             = _scale_ao + _dot_ao_ao + vmat+vmat.T   numint_legacy.py:308-309,336-337,432-456
 //             = adjoint of eval_rho w.r.t. dm (D_bar = ao_0^T t)
 //
-// Both kernels are warp-specialised: one producer warp streams operand tiles into a 3-stage
+// Both kernels are warp-specialised: one producer warp streams operand slabs into a 3-stage
 // shared-memory ring with 1-D bulk async copies (TMA engine, SASS UBLKCP) completing on
-// mbarriers; eight consumer warps issue DMMA.8x8x4 with register-blocked accumulators.  Rows
-// in shared memory are padded by 4 doubles so every fragment load is bank-conflict free.  The
-// split-G reduction of wsyrk goes through a workspace and a fixed-order reduce kernel: no
-// atomics, run-to-run deterministic.
+// mbarriers; eight consumer warps issue DMMA.8x8x4 with register-blocked accumulators.  Rows in
+// shared memory are padded by 4 doubles so every fragment load is bank-conflict free.
+//
+// Work that is structurally zero is never issued, at 8x8-block granularity:
+//   * AO columns are padded to a multiple of 8 only (N = 1000 stays 1000): ragged last tiles run
+//     with fewer n8/m8 blocks and fewer k4 steps;
+//   * symmetric operands: rowquad (one AO component) multiplies by the upper triangle of S only
+//     (x^T S x = 2 x^T triu'(S) x), wsyrk computes blocks on or above the diagonal only;
+//   * the (wm, wn) sub-tile of a warp is chosen so that the two warps sharing an SM sub-partition
+//     (warp % 4) carry equal DMMA counts in the triangular tiles.
+// wsyrk is a persistent kernel over a cost-aware static schedule of (tile, grid-chunk) items
+// built on the host (greedy list scheduling, chunk-major so concurrent CTAs share AO rows in
+// L2); every item owns a partial-tile slot and a fixed-order reduce kernel adds the chunks and
+// the transpose: no atomics, bitwise run-to-run deterministic.
+#include <algorithm>
+
 #include "common.cuh"
 #include "dmma.cuh"
 
@@ -24,7 +36,25 @@ constexpr int BM = 128;     // grid rows per CTA in rowquad
 constexpr int BK = 32;      // reduction-dimension slab per pipeline stage
 constexpr int NSTAGE = 3;
 constexpr int NCONS = 8;    // consumer warps (4 x 2)
-constexpr int NTHREADS = (NCONS + 1) * 32;
+constexpr int NTHREADS = (NCONS + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup (1 active warp)
+
+// Register re-partitioning between warpgroups (setmaxnreg): the kernels are compiled for 384 threads
+// (168 registers each); the producer warpgroup drops to 40 and the consumers grow to 232, which removes
+// the accumulator spills and lets the compiler software-pipeline fragment loads across k4 steps.
+// The two instructions sit on code paths that never re-join (the producer warpgroup returns).
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n"); }
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n"); }
+
+__host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ inline int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// warp -> sub-tile.  wn = warp >> 2, so warps w and w+4 (same SM sub-partition) hold the two column
+// halves; for wn = 1 the row quarter is permuted so that triangular tiles balance per sub-partition.
+__host__ __device__ inline void warp_tile(int warp, int& wm, int& wn) {
+    wn = warp >> 2;
+    wm = wn == 0 ? (warp & 3) : ((0x1023 >> (4 * (warp & 3))) & 0xF);
+}
 
 template <int BN>
 struct RowquadCfg {
@@ -35,17 +65,114 @@ struct RowquadCfg {
     static constexpr int STAGE = A_ELEMS + B_ELEMS;
     static constexpr int RED = 4 * 2 * BM;
     static constexpr size_t SMEM = (size_t)(NSTAGE * STAGE + RED) * 8 + 2 * NSTAGE * 8;
-    static constexpr uint32_t TX = (BM * BK + BK * BN) * 8;
     static constexpr int NB = BN / 16;  // n8 blocks per warp (warp tile 32 x BN/2)
 };
 
+// chunks of the reduction dimension needed by column tile nt (tri: rows k <= last column only)
+__host__ __device__ inline int rq_kend(int tri, int Nc, int BN, int nt) {
+    const int KB = (Nc + BK - 1) / BK;
+    if (!tri) return KB;
+    const int nw = imin(BN, Nc - nt * BN);
+    return imin(KB, (nt * BN + nw + BK - 1) / BK);
+}
+
+// ---- consumer-side view of the smem ring -------------------------------------------------------
+struct Ring {
+    double* sm;
+    uint64_t* full;
+    uint64_t* empty;
+    int it;
+};
+__device__ __forceinline__ int ring_wait(const Ring& r) {
+    const int s = r.it % NSTAGE;
+    mbar_wait(r.full + s, (uint32_t)(r.it / NSTAGE) & 1);
+    return s;
+}
+__device__ __forceinline__ void ring_release(Ring& r, int s, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(r.empty + s);
+    ++r.it;
+}
+__device__ __forceinline__ void ring_skip(Ring& r, int n, int lane) {
+    for (int k = 0; k < n; ++k) {
+        const int s = ring_wait(r);
+        ring_release(r, s, lane);
+    }
+}
+
+// One 32-deep slab of the rowquad product for a warp: acc[4][NV] += A(32 x 32) * B(32 x 8*NV).
+// REL < 0: dense.  REL = 0 / 32: the slab starts REL rows below the first column of the warp's
+// sub-tile inside the upper-triangular S, so column block nj only sees k4 steps with
+// (REL + 4*kk) >> 3 <= nj.  Every condition folds at compile time after unrolling: the skip
+// patterns cost no predicates or branches in the DMMA stream.
+// The two column-warps of a row quarter own the n8 blocks of the tile INTERLEAVED: warp wn holds
+// blocks 2*j + wn.  In the triangular region both warps then carry (almost) the same DMMA count in
+// every slab, so the sub-partition they share never idles on one of them.
+// SD < 0: dense.  SD = 0..3: the slab is the SD-th 32-row slab of the diagonal block of this column
+// tile; tile block nb only sees k4 steps with 4*SD + (kk >> 1) <= nb.
+template <int BN, int NV, int SD, int WN>
+__device__ __forceinline__ void rq_slab(double (&acc)[4][BN / 16][2], const double* __restrict__ As,
+                                        const double* __restrict__ Bs) {
+    using Cfg = RowquadCfg<BN>;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+        const int nbmin = SD < 0 ? 0 : 4 * SD + (kk >> 1);  // first tile block that sees rows of this k4 step
+        if (nbmin <= 2 * (NV - 1) + WN) {
+            // all fragment loads of the k4 step first, then the DMMAs (A-outer): keeps the shared-memory
+            // latency off the tensor pipe's critical path
+            double a[4], bf[NV];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * Cfg::LDA + kk * 4];
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+                if (2 * j + WN >= nbmin) bf[j] = Bs[kk * 4 * Cfg::LDB + j * 16];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int j = 0; j < NV; ++j)
+                    if (2 * j + WN >= nbmin) dmma884(acc[mi][j], a[mi], bf[j]);
+        }
+    }
+}
+template <int BN, int NV, int SD, int WN>
+__device__ __forceinline__ void rq_run(double (&acc)[4][BN / 16][2], Ring& r, int nslabs, int aoff, int boff,
+                                       int lane) {
+    using Cfg = RowquadCfg<BN>;
+    for (int k = 0; k < nslabs; ++k) {
+        const int s = ring_wait(r);
+        const double* st = r.sm + s * Cfg::STAGE;
+        rq_slab<BN, NV, SD, WN>(acc, st + aoff, st + Cfg::A_ELEMS + boff);
+        ring_release(r, s, lane);
+    }
+}
+// dense slabs with a run-time number of valid column blocks -> compile-time variant
+template <int BN, int NV>
+__device__ __forceinline__ void rq_dense(double (&acc)[4][BN / 16][2], Ring& r, int nslabs, int nvalid, int aoff,
+                                         int boff, int lane) {
+    if (nvalid == NV) rq_run<BN, NV, -1, 0>(acc, r, nslabs, aoff, boff, lane);
+    else if constexpr (NV > 1) rq_dense<BN, NV - 1>(acc, r, nslabs, nvalid, aoff, boff, lane);
+    else ring_skip(r, nslabs, lane);
+}
+// one full-width diagonal slab: run-time (sd, wn) -> compile-time variant
+template <int BN, int SD>
+__device__ __forceinline__ void rq_diag(double (&acc)[4][BN / 16][2], Ring& r, int sd, int wn, int aoff, int boff,
+                                        int lane) {
+    constexpr int NB = BN / 16;
+    if (sd == SD) {
+        if (wn == 0) rq_run<BN, NB, SD, 0>(acc, r, 1, aoff, boff, lane);
+        else rq_run<BN, NB, SD, 1>(acc, r, 1, aoff, boff, lane);
+    } else if constexpr (SD > 0) {
+        rq_diag<BN, SD - 1>(acc, r, sd, wn, aoff, boff, lane);
+    }
+}
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, double* __restrict__ q,
-               int Npad, long ao_cstride, long ao_bstride, long S_bstride, long q_cstride,
+               int Npad, int Nc, long ao_cstride, long ao_bstride, long S_bstride, long q_cstride,
                long q_bstride, int ncomp, int tri, double f0, double f1, double f2, double f3) {
-    // tri != 0: S holds only its upper triangle (diagonal halved), so column tile nt needs the
-    // reduction rows k < (nt+1)*BN only; the caller folds the factor 2 into f0.
+    // tri != 0: S holds only its upper triangle (diagonal halved); the caller folds the factor 2
+    // into f0.  Npad = storage pitch (multiple of 32, pad columns are zeros), Nc = compute extent
+    // (multiple of 8): slabs are always full, column blocks beyond Nc are never issued.
     using Cfg = RowquadCfg<BN>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
@@ -59,7 +186,7 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
     const double* ao_b = ao + (long)b * ao_bstride;
     const double* A0 = ao_b + g0 * Npad;
     const double* S_b = S + (long)b * S_bstride;
-    const int KB = Npad / BK, NT = Npad / BN;
+    const int NT = (Nc + BN - 1) / BN;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -70,34 +197,37 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
     }
     __syncthreads();
 
-    if (warp == NCONS) {
-        // ---------------- producer warp ----------------
+    if (warp >= NCONS) {
+        reg_dec();
+        // ---------------- producer warpgroup: 4 warps share the copy issue ----------------
+        // (the A slab is 128 row copies of 256 B: one warp alone cannot issue them fast enough to keep
+        // the cheap slabs of the triangular region fed).  Warp pw copies A rows 32*pw..32*pw+31; warp 0
+        // also arms the barrier with the slab's byte count and copies the S rows.
+        const int pw = warp - NCONS;
         int it = 0;
         for (int nt = 0; nt < NT; ++nt) {
-            const int kend = tri ? min(KB, (nt + 1) * (BN / BK)) : KB;
+            const int nw = imin(BN, Npad - nt * BN);  // copy width: storage columns (zeros beyond Nc)
+            const int kend = rq_kend(tri, Nc, BN, nt);
             for (int kb = 0; kb < kend; ++kb, ++it) {
                 const int s = it % NSTAGE;
                 const uint32_t u = (uint32_t)(it / NSTAGE);
                 mbar_wait(empty + s, (u & 1) ^ 1);
                 double* As = sm + s * Cfg::STAGE;
                 double* Bs = As + Cfg::A_ELEMS;
-                if (lane == 0) mbar_expect_tx(full + s, Cfg::TX);
-                __syncwarp();
-#pragma unroll
-                for (int r = lane; r < BM; r += 32)
-                    bulk_g2s(As + r * Cfg::LDA, A0 + (long)r * Npad + kb * BK, BK * 8, full + s);
-                {
-                    const int r = lane;  // BK == 32 rows of S
-                    bulk_g2s(Bs + r * Cfg::LDB, S_b + (long)(kb * BK + r) * Npad + nt * BN, BN * 8,
-                             full + s);
-                }
+                if (pw == 0 && lane == 0) mbar_expect_tx(full + s, (uint32_t)((BM * BK + BK * nw) * 8));
+                const int r = pw * 32 + lane;
+                bulk_g2s(As + r * Cfg::LDA, A0 + (long)r * Npad + kb * BK, BK * 8, full + s);
+                if (pw == 0)
+                    bulk_g2s(Bs + lane * Cfg::LDB, S_b + (long)(kb * BK + lane) * Npad + nt * BN, nw * 8, full + s);
             }
         }
         return;
     }
+    reg_inc();
 
     // ---------------- consumer warps ----------------
-    const int wm = warp >> 1, wn = warp & 1;
+    int wm, wn;
+    warp_tile(warp, wm, wn);
     const int g = lane >> 2, qd = lane & 3;
     constexpr int NB = Cfg::NB;
     double rp[4][4];
@@ -106,50 +236,45 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) rp[c][mi] = 0.0;
 
-    int it = 0;
+    Ring ring{sm, full, empty, 0};
+    const int aoff = (wm * 32 + g) * Cfg::LDA + qd;
+    const int boff = qd * Cfg::LDB + wn * 8 + g;  // this warp's blocks are 2*j + wn: 16 doubles apart
     for (int nt = 0; nt < NT; ++nt) {
+        const int nw = imin(BN, Nc - nt * BN);
+        const int kend = rq_kend(tri, Nc, BN, nt);
+        const int nbv = nw >> 3;                             // valid n8 blocks of this tile
+        const int nvalid = clampi((nbv - wn + 1) >> 1, 0, NB);  // ... of which this warp owns 2*j + wn < nbv
+        const int c0 = nt * BN;                              // first column of the tile
         double acc[4][NB][2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int nj = 0; nj < NB; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
 
-        const int kend = tri ? min(KB, (nt + 1) * (BN / BK)) : KB;
-        for (int kb = 0; kb < kend; ++kb, ++it) {
-            const int s = it % NSTAGE;
-            const uint32_t u = (uint32_t)(it / NSTAGE);
-            mbar_wait(full + s, u & 1);
-            const double* As = sm + s * Cfg::STAGE + (wm * 32 + g) * Cfg::LDA + qd;
-            const double* Bs = sm + s * Cfg::STAGE + Cfg::A_ELEMS + qd * Cfg::LDB + wn * (BN / 2) + g;
-#pragma unroll
-            for (int kk = 0; kk < BK / 4; ++kk) {
-                double a[4], bf[NB];
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * Cfg::LDA + kk * 4];
-#pragma unroll
-                for (int nj = 0; nj < NB; ++nj) bf[nj] = Bs[kk * 4 * Cfg::LDB + nj * 8];
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                    for (int nj = 0; nj < NB; ++nj) dmma884(acc[mi][nj], a[mi], bf[nj]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + s);
+        // leading slabs entirely above the diagonal block of the triangular S: dense
+        const int kd = tri ? imin(kend, c0 / BK) : kend;
+        rq_dense<BN, NB>(acc, ring, kd, nvalid, aoff, boff, lane);
+        // slabs of the diagonal block (tri only).  A ragged last tile runs the full-tile variants: its
+        // extra column blocks read zeros / stale data and are ignored by the epilogue.
+        for (int kb = kd; kb < kend; ++kb) {
+            if (nvalid == 0) ring_skip(ring, 1, lane);
+            else rq_diag<BN, BN / BK - 1>(acc, ring, (kb * BK - c0) / BK, wn, aoff, boff, lane);
         }
         // epilogue of this column tile: row-dot the (ao_0 S) tile with each AO component
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if (c < ncomp) {
-                const double* P = ao_b + (long)c * ao_cstride + (g0 + wm * 32 + g) * Npad + nt * BN +
-                                  wn * (BN / 2) + 2 * qd;
+                const double* P = ao_b + (long)c * ao_cstride + (g0 + wm * 32 + g) * Npad + c0 + wn * 8 + 2 * qd;
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi) {
                     double sum = 0.0;
 #pragma unroll
                     for (int nj = 0; nj < NB; ++nj) {
-                        const double2 v = *reinterpret_cast<const double2*>(P + (long)mi * 8 * Npad + nj * 8);
-                        sum = fma(acc[mi][nj][0], v.x, sum);
-                        sum = fma(acc[mi][nj][1], v.y, sum);
+                        if (nj < nvalid) {
+                            const double2 v = *reinterpret_cast<const double2*>(P + (long)mi * 8 * Npad + nj * 16);
+                            sum = fma(acc[mi][nj][0], v.x, sum);
+                            sum = fma(acc[mi][nj][1], v.y, sum);
+                        }
                     }
                     rp[c][mi] += sum;
                 }
@@ -180,6 +305,17 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// wsyrk
+// ---------------------------------------------------------------------------------------------
+struct WsItem {
+    int b, ti, tj;   // batch element, output tile (row, column)
+    int g0, kb;      // first grid row and number of 32-row slabs of this item
+    int slot;        // partial-tile slot
+    int diag;        // symmetric diagonal tile: only blocks on or above the diagonal
+    int pad;
+};
+
 template <int BN>
 struct WsyrkCfg {
     static constexpr int LD = BN + 4;
@@ -190,12 +326,56 @@ struct WsyrkCfg {
     static constexpr int NB = BN / 16;
 };
 
+// One 32-row slab of the wsyrk product for a warp: acc[MB][NV] += (A .* s)^T(8*MB x 32) * B(32 x 8*NV).
+// DS is the triangular shift of a diagonal tile: block (mi, nj) is needed iff nj >= DS + mi
+// (DS <= -(MB-1): dense).  Conditions fold at compile time.
+template <int BN, int NV, int DS>
+__device__ __forceinline__ void ws_slab(double (&acc)[BN / 32][BN / 16][2], const double* __restrict__ As,
+                                        const double* __restrict__ Bs, const double* __restrict__ Ss, bool scaled) {
+    using Cfg = WsyrkCfg<BN>;
+    constexpr int MB = Cfg::MB;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[MB];
+        const double sv = scaled ? Ss[kk * 4] : 1.0;
+#pragma unroll
+        for (int mi = 0; mi < MB; ++mi) a[mi] = As[kk * 4 * Cfg::LD + mi * 8] * sv;
+        double bf[NV];
+#pragma unroll
+        for (int nj = 0; nj < NV; ++nj)
+            if (nj >= DS) bf[nj] = Bs[kk * 4 * Cfg::LD + nj * 8];
+#pragma unroll
+        for (int mi = 0; mi < MB; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < NV; ++nj)
+                if (nj >= DS + mi) dmma884(acc[mi][nj], a[mi], bf[nj]);
+    }
+}
+template <int BN, int NV, int DS>
+__device__ __forceinline__ void ws_run(double (&acc)[BN / 32][BN / 16][2], Ring& r, int nslabs, int aoff, int boff,
+                                       int soff, bool scaled, int lane) {
+    using Cfg = WsyrkCfg<BN>;
+    for (int k = 0; k < nslabs; ++k) {
+        const int s = ring_wait(r);
+        const double* st = r.sm + s * Cfg::STAGE;
+        ws_slab<BN, NV, DS>(acc, st + aoff, st + Cfg::T_ELEMS + boff, st + 2 * Cfg::T_ELEMS + soff, scaled);
+        ring_release(r, s, lane);
+    }
+}
+template <int BN, int NV>
+__device__ __forceinline__ void ws_dense(double (&acc)[BN / 32][BN / 16][2], Ring& r, int nslabs, int nvalid,
+                                         int aoff, int boff, int soff, bool scaled, int lane) {
+    if (nvalid == NV) ws_run<BN, NV, -100>(acc, r, nslabs, aoff, boff, soff, scaled, lane);
+    else if constexpr (NV > 1) ws_dense<BN, NV - 1>(acc, r, nslabs, nvalid, aoff, boff, soff, scaled, lane);
+    else ring_skip(r, nslabs, lane);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 wsyrk_kernel(const double* __restrict__ ao0, const double* __restrict__ Bsrc,
-             const double* __restrict__ sc, double* __restrict__ part, int Npad, int Gpad,
-             int rows_per_split, int sym, long ao_bstride, long B_bstride, long s_bstride,
-             long part_bstride) {
+             const double* __restrict__ sc, double* __restrict__ part, int Npad, int Nc,
+             const WsItem* __restrict__ items, const int* __restrict__ cta_start, long ao_bstride,
+             long B_bstride, long s_bstride) {
     using Cfg = WsyrkCfg<BN>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
@@ -203,29 +383,7 @@ wsyrk_kernel(const double* __restrict__ ao0, const double* __restrict__ Bsrc,
     uint64_t* empty = full + NSTAGE;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NT = Npad / BN;
-    int ti, tj;
-    if (sym) {  // upper-triangular tile pairs, row by row
-        int x = blockIdx.x;
-        ti = 0;
-        while (x >= NT - ti) {
-            x -= NT - ti;
-            ++ti;
-        }
-        tj = ti + x;
-    } else {
-        ti = blockIdx.x / NT;
-        tj = blockIdx.x % NT;
-    }
-    const int split = blockIdx.y, b = blockIdx.z;
-    const long gbeg = (long)split * rows_per_split;
-    long gend = gbeg + rows_per_split;
-    if (gend > Gpad) gend = Gpad;
-    const int KB = gend > gbeg ? (int)((gend - gbeg) / BK) : 0;
-    const double* Ag = ao0 + (long)b * ao_bstride + gbeg * Npad + ti * BN;
-    const double* Bg = Bsrc + (long)b * B_bstride + gbeg * Npad + tj * BN;
-    const double* sg = sc ? sc + (long)b * s_bstride + gbeg : nullptr;
-    const uint32_t tx = (uint32_t)((2 * BK * BN + (sc ? BK : 0)) * 8);
+    const int first = cta_start[blockIdx.x], last = cta_start[blockIdx.x + 1];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -236,89 +394,111 @@ wsyrk_kernel(const double* __restrict__ ao0, const double* __restrict__ Bsrc,
     }
     __syncthreads();
 
-    if (warp == NCONS) {
-        for (int it = 0; it < KB; ++it) {
-            const int s = it % NSTAGE;
-            const uint32_t u = (uint32_t)(it / NSTAGE);
-            mbar_wait(empty + s, (u & 1) ^ 1);
-            double* As = sm + s * Cfg::STAGE;
-            double* Bs = As + Cfg::T_ELEMS;
-            double* Ss = Bs + Cfg::T_ELEMS;
-            if (lane == 0) {
-                mbar_expect_tx(full + s, tx);
-                if (sg) bulk_g2s(Ss, sg + (long)it * BK, BK * 8, full + s);
+    if (warp >= NCONS) {
+        reg_dec();
+        // producer warpgroup: the 64 row copies of a slab are spread over 4 warps (warp pw: slab rows
+        // 8*pw..8*pw+7, lanes 0-7 the A rows, lanes 8-15 the B rows); warp 0 arms the barrier
+        const int pw = warp - NCONS;
+        int it = 0;
+        for (int w = first; w < last; ++w) {
+            const WsItem im = items[w];
+            const int iw = imin(BN, Npad - im.ti * BN), jw = imin(BN, Npad - im.tj * BN);
+            const double* Ag = ao0 + (long)im.b * ao_bstride + (long)im.g0 * Npad + im.ti * BN;
+            const double* Bg = Bsrc + (long)im.b * B_bstride + (long)im.g0 * Npad + im.tj * BN;
+            const double* sg = sc ? sc + (long)im.b * s_bstride + im.g0 : nullptr;
+            const uint32_t tx = (uint32_t)((BK * (iw + jw) + (sc ? BK : 0)) * 8);
+            const int r = pw * 8 + (lane & 7);
+            for (int kc = 0; kc < im.kb; ++kc, ++it) {
+                const int s = it % NSTAGE;
+                const uint32_t u = (uint32_t)(it / NSTAGE);
+                mbar_wait(empty + s, (u & 1) ^ 1);
+                double* As = sm + s * Cfg::STAGE;
+                double* Bs = As + Cfg::T_ELEMS;
+                double* Ss = Bs + Cfg::T_ELEMS;
+                if (pw == 0 && lane == 0) {
+                    mbar_expect_tx(full + s, tx);
+                    if (sg) bulk_g2s(Ss, sg + (long)kc * BK, BK * 8, full + s);
+                }
+                const long row = (long)kc * BK + r;
+                if (lane < 8) bulk_g2s(As + r * Cfg::LD, Ag + row * Npad, iw * 8, full + s);
+                else if (lane < 16) bulk_g2s(Bs + r * Cfg::LD, Bg + row * Npad, jw * 8, full + s);
             }
-            __syncwarp();
-            const long row = (long)it * BK + lane;  // BK == 32: one slab row per lane
-            bulk_g2s(As + lane * Cfg::LD, Ag + row * Npad, BN * 8, full + s);
-            bulk_g2s(Bs + lane * Cfg::LD, Bg + row * Npad, BN * 8, full + s);
         }
         return;
     }
+    reg_inc();
 
-    const int wm = warp >> 1, wn = warp & 1;
+    int wm, wn;
+    warp_tile(warp, wm, wn);
     const int g = lane >> 2, qd = lane & 3;
     constexpr int MB = Cfg::MB, NB = Cfg::NB;
-    double acc[MB][NB][2];
+    Ring ring{sm, full, empty, 0};
+    const int aoff = qd * Cfg::LD + wm * (BN / 4) + g;
+    const int boff = qd * Cfg::LD + wn * (BN / 2) + g;
+    const int soff = qd;
+    const bool scaled = sc != nullptr;
+    for (int w = first; w < last; ++w) {
+        const WsItem im = items[w];
+        const int iw = imin(BN, Nc - im.ti * BN), jw = imin(BN, Nc - im.tj * BN);  // compute extents
+        const int mvalid = clampi((iw - wm * (BN / 4)) / 8, 0, MB);
+        const int nvalid = clampi((jw - wn * (BN / 2)) / 8, 0, NB);
+        double acc[MB][NB][2];
 #pragma unroll
-    for (int mi = 0; mi < MB; ++mi)
+        for (int mi = 0; mi < MB; ++mi)
 #pragma unroll
-        for (int nj = 0; nj < NB; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
+            for (int nj = 0; nj < NB; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
 
-    for (int it = 0; it < KB; ++it) {
-        const int s = it % NSTAGE;
-        const uint32_t u = (uint32_t)(it / NSTAGE);
-        mbar_wait(full + s, u & 1);
-        const double* As = sm + s * Cfg::STAGE + qd * Cfg::LD + wm * (BN / 4) + g;
-        const double* Bs = sm + s * Cfg::STAGE + Cfg::T_ELEMS + qd * Cfg::LD + wn * (BN / 2) + g;
-        const double* Ss = sm + s * Cfg::STAGE + 2 * Cfg::T_ELEMS + qd;
-#pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
-            double a[MB], bf[NB];
-            const double sv = sc ? Ss[kk * 4] : 1.0;
-#pragma unroll
-            for (int mi = 0; mi < MB; ++mi) a[mi] = As[kk * 4 * Cfg::LD + mi * 8] * sv;
-#pragma unroll
-            for (int nj = 0; nj < NB; ++nj) bf[nj] = Bs[kk * 4 * Cfg::LD + nj * 8];
-#pragma unroll
-            for (int mi = 0; mi < MB; ++mi)
-#pragma unroll
-                for (int nj = 0; nj < NB; ++nj) dmma884(acc[mi][nj], a[mi], bf[nj]);
+        // Variant of the slab loop for this (item, warp).  Ragged rows of the tile are computed on
+        // stale shared-memory data and ignored downstream (separate accumulators, never read).
+        const int ds = wm * MB - wn * NB;  // diagonal tile: block (mi, nj) needed iff nj >= ds + mi
+        if (!im.diag) {
+            ws_dense<BN, NB>(acc, ring, im.kb, mvalid > 0 ? nvalid : 0, aoff, boff, soff, scaled, lane);
+        } else {
+            // diagonal tile (ragged or not): compile-time triangular variants; blocks beyond Nc are
+            // computed on zeros / stale data and ignored by the reduce kernel
+            if (ds <= -(MB - 1)) ws_run<BN, NB, -100>(acc, ring, im.kb, aoff, boff, soff, scaled, lane);
+            else if (ds >= NB) ring_skip(ring, im.kb, lane);
+            else if (ds == 0) ws_run<BN, NB, 0>(acc, ring, im.kb, aoff, boff, soff, scaled, lane);
+            else ws_run<BN, NB, MB>(acc, ring, im.kb, aoff, boff, soff, scaled, lane);  // ds == MB
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);
+        // compact partial tile [BN][BN] of this item
+        double* P = part + (long)im.slot * BN * BN + (long)(wm * (BN / 4) + g) * BN + wn * (BN / 2) + 2 * qd;
+#pragma unroll
+        for (int mi = 0; mi < MB; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < NB; ++nj)
+                *reinterpret_cast<double2*>(P + (long)mi * 8 * BN + nj * 8) = make_double2(acc[mi][nj][0], acc[mi][nj][1]);
     }
-    double* P = part + (long)b * part_bstride + (long)split * Npad * Npad +
-                (long)(ti * BN + wm * (BN / 4) + g) * Npad + tj * BN + wn * (BN / 2) + 2 * qd;
-#pragma unroll
-    for (int mi = 0; mi < MB; ++mi)
-#pragma unroll
-        for (int nj = 0; nj < NB; ++nj)
-            *reinterpret_cast<double2*>(P + (long)mi * 8 * Npad + nj * 8) =
-                make_double2(acc[mi][nj][0], acc[mi][nj][1]);
 }
 
-// out[i][j] = scale * (H[i][j] + H[j][i]), H = sum over splits (fixed order) of the partial tiles.
-// With sym != 0 only tile pairs ti <= tj were computed; H is symmetric there by construction.
-__global__ void wsyrk_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, int N,
-                                    int Npad, int BN, int nsplit, int sym, double scale, int tadd,
-                                    long part_bstride, long out_bstride) {
+// out[i][j] = scale * (H[i][j] + (tadd ? H[j][i] : 0)), H = sum over grid chunks (fixed order) of the
+// partial tiles.  With sym != 0 only 8x8 blocks on or above the diagonal were computed (H symmetric).
+__global__ void wsyrk_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, int N, int BN,
+                                    int NT, int nchunk, int ntile, int sym, double scale, int tadd,
+                                    long out_bstride) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     const int b = blockIdx.z;
     if (j >= N) return;
-    const double* P = part + (long)b * part_bstride;
-    const long NN = (long)Npad * Npad;
-    double hij = 0.0, hji = 0.0;
-    const int ti = i / BN, tj = j / BN;
-    const bool ij_ok = !sym || ti <= tj, ji_ok = !sym || tj <= ti;
-    for (int s = 0; s < nsplit; ++s) {
-        if (ij_ok) hij += P[s * NN + (long)i * Npad + j];
-        if (ji_ok) hji += P[s * NN + (long)j * Npad + i];
+    const long tsz = (long)BN * BN;
+    auto H = [&](int r, int c) {
+        const int tr = r / BN, tc = c / BN;
+        const int tile = sym ? tr * NT - tr * (tr - 1) / 2 + (tc - tr) : tr * NT + tc;
+        const double* P = part + ((long)(b * ntile + tile) * nchunk) * tsz + (long)(r - tr * BN) * BN + (c - tc * BN);
+        double h = 0.0;
+        for (int k = 0; k < nchunk; ++k) h += P[(long)k * tsz];
+        return h;
+    };
+    double v;
+    if (sym) {
+        const bool up = (j >> 3) >= (i >> 3), lo = (i >> 3) >= (j >> 3);
+        const double hij = up ? H(i, j) : H(j, i);
+        const double hji = lo ? H(j, i) : hij;
+        v = tadd ? hij + hji : hij;
+    } else {
+        v = tadd ? H(i, j) + H(j, i) : H(i, j);
     }
-    if (!ij_ok) hij = hji;
-    if (!ji_ok) hji = hij;
-    out[(long)b * out_bstride + (long)i * N + j] = scale * (tadd ? hij + hji : hij);
+    out[(long)b * out_bstride + (long)i * N + j] = scale * v;
 }
 
 // S[b][i][j] (Npad x Npad, zero padded) from src[b][N][N]: mode 0 (a+a^T)/2, 1 a, 2 a+a^T.
@@ -364,7 +544,7 @@ __global__ void build_aow_kernel(const double* __restrict__ ao, const double* __
     }
 }
 
-int pick_bn(int Npad) { return Npad % 128 == 0 ? 128 : (Npad % 64 == 0 ? 64 : 32); }
+int pick_bn(int Npad) { return Npad > 64 ? 128 : (Npad > 32 ? 64 : 32); }
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
@@ -372,29 +552,180 @@ int set_smem(K kernel, size_t bytes) {
     return QEXXC_OK;
 }
 
+// ---- host-side cost model (the same predicates as the kernels) -------------------------------------
+// number of 8x8x4 DMMAs per k4 step issued by consumer warp `w` for a wsyrk tile
+int ws_warp_blocks(int BN, int Nc, int ti, int tj, int diag, int w) {
+    int wm, wn;
+    warp_tile(w, wm, wn);
+    const int MB = BN / 32, NB = BN / 16;
+    const int iw = std::min(BN, Nc - ti * BN), jw = std::min(BN, Nc - tj * BN);
+    const int mvalid = clampi((iw - wm * (BN / 4)) / 8, 0, MB), nvalid = clampi((jw - wn * (BN / 2)) / 8, 0, NB);
+    if (!diag) return mvalid > 0 ? MB * nvalid : 0;  // ragged rows run dense (results ignored)
+    int n = 0;  // diagonal tiles always run the full-tile triangular variants
+    for (int mi = 0; mi < MB; ++mi)
+        for (int nj = 0; nj < NB; ++nj)
+            if (nj >= wm * MB - wn * NB + mi) ++n;
+    return n;
+}
+// cost of a tile per 32-row slab: the busiest SM sub-partition (warps w and w+4 share one)
+int ws_tile_cost(int BN, int Nc, int ti, int tj, int diag, long* total_blocks) {
+    int worst = 0;
+    long tot = 0;
+    for (int sp = 0; sp < 4; ++sp) {
+        const int a = ws_warp_blocks(BN, Nc, ti, tj, diag, sp), b = ws_warp_blocks(BN, Nc, ti, tj, diag, sp + 4);
+        worst = std::max(worst, a + b);
+        tot += a + b;
+    }
+    if (total_blocks) *total_blocks = tot;
+    return std::max(worst, 1);
+}
+
+struct WsPlan {
+    int BN = 0, NT = 0, ntile = 0, nchunk = 0, chunk_rows = 0, nitems = 0, nctas = 0;
+};
+
+// Layout of the wsyrk work: tiles x grid chunks (x batch), and the partial-slot count.
+void ws_shape(int num_sms, int Nc, int Gpad, int B, bool sym, WsPlan& p) {
+    p.BN = pick_bn(Nc);
+    p.NT = (Nc + p.BN - 1) / p.BN;
+    p.ntile = sym ? p.NT * (p.NT + 1) / 2 : p.NT * p.NT;
+    // ~16 items per CTA keeps greedy scheduling within a few percent of perfect balance
+    long rows = ((long)Gpad * p.ntile * B + 16L * num_sms - 1) / (16L * num_sms);
+    rows = ((rows + 255) / 256) * 256;
+    if (rows < 256) rows = 256;
+    if (rows > Gpad) rows = Gpad;
+    p.chunk_rows = (int)rows;
+    p.nchunk = (Gpad + p.chunk_rows - 1) / p.chunk_rows;
+    p.nitems = p.ntile * p.nchunk * B;
+    p.nctas = std::min(num_sms, p.nitems);
+}
+
+// Build (or reuse) the static schedule for the current (Npad, Gpad, B, sym) and upload it.
+int ws_schedule(qexxc_ctx* c, bool sym, WsPlan& plan, cudaStream_t st) {
+    ws_shape(c->num_sms, c->Nc, c->Gpad, c->B, sym, plan);
+    const int sl = sym ? 1 : 0;
+    const long key = ((long)c->Gpad << 20) ^ ((long)c->Npad << 4) ^ (long)c->B;
+    if (c->ws_key[sl] == key) return QEXXC_OK;
+    const int BN = plan.BN, NT = plan.NT;
+    std::vector<int> tcost(plan.ntile);
+    std::vector<std::pair<int, int>> tiles(plan.ntile);
+    {
+        int t = 0;
+        for (int ti = 0; ti < NT; ++ti)
+            for (int tj = sym ? ti : 0; tj < NT; ++tj, ++t) {
+                tiles[t] = {ti, tj};
+                tcost[t] = ws_tile_cost(BN, c->Nc, ti, tj, sym && ti == tj, nullptr);
+            }
+    }
+    std::vector<WsItem> items;
+    items.reserve(plan.nitems);
+    std::vector<long> load(plan.nctas, 0);
+    std::vector<std::vector<int>> lists(plan.nctas);
+    // chunk-major order, heavier tiles first within a chunk; each item goes to the least-loaded CTA
+    std::vector<int> order(plan.ntile);
+    for (int t = 0; t < plan.ntile; ++t) order[t] = t;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tcost[a] > tcost[b]; });
+    for (int ch = 0; ch < plan.nchunk; ++ch) {
+        const int g0 = ch * plan.chunk_rows;
+        const int rows = std::min(plan.chunk_rows, c->Gpad - g0);
+        for (int b = 0; b < c->B; ++b)
+            for (int oi = 0; oi < plan.ntile; ++oi) {
+                const int t = order[oi];
+                WsItem im;
+                im.b = b;
+                im.ti = tiles[t].first;
+                im.tj = tiles[t].second;
+                im.g0 = g0;
+                im.kb = rows / BK;
+                im.slot = (b * plan.ntile + t) * plan.nchunk + ch;
+                im.diag = (sym && im.ti == im.tj) ? 1 : 0;
+                im.pad = 0;
+                int best = 0;
+                for (int k = 1; k < plan.nctas; ++k)
+                    if (load[k] < load[best]) best = k;
+                load[best] += (long)tcost[t] * im.kb;
+                lists[best].push_back((int)items.size());
+                items.push_back(im);
+            }
+    }
+    if (getenv("QEXXC_DEBUG")) {
+        long mx = 0, sum = 0;
+        for (long l : load) {
+            mx = std::max(mx, l);
+            sum += l;
+        }
+        fprintf(stderr, "[qexxc] wsyrk schedule: sym=%d BN=%d tiles=%d chunks=%d (rows %d) items=%d ctas=%d imbalance=%.4f\n",
+                (int)sym, BN, plan.ntile, plan.nchunk, plan.chunk_rows, plan.nitems, plan.nctas,
+                (double)mx * plan.nctas / (double)std::max(sum, 1L));
+    }
+    std::vector<WsItem> flat;
+    flat.reserve(items.size());
+    std::vector<int> start(plan.nctas + 1, 0);
+    for (int k = 0; k < plan.nctas; ++k) {
+        start[k] = (int)flat.size();
+        for (int id : lists[k]) flat.push_back(items[id]);
+    }
+    start[plan.nctas] = (int)flat.size();
+    if (flat.size() * sizeof(WsItem) > c->ws_items_bytes || (size_t)(plan.nctas + 1) > c->ws_start_cap) {
+        set_error("internal: wsyrk schedule exceeds its workspace (%zu items)", flat.size());
+        return QEXXC_ERR_STATE;
+    }
+    // (re)built only when the problem shape changes; make sure no kernel still reads the old tables
+    QX_CUDA(cudaStreamSynchronize(st));
+    QX_CUDA(cudaMemcpy(c->ws_items[sl], flat.data(), flat.size() * sizeof(WsItem), cudaMemcpyHostToDevice));
+    QX_CUDA(cudaMemcpy(c->ws_start[sl], start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c->ws_key[sl] = key;
+    return QEXXC_OK;
+}
+
 }  // namespace
 
-int wsyrk_pick_nsplit(int num_sms, int Npad, int Gpad, int B, bool sym) {
-    const int BN = Npad % 128 == 0 ? 128 : (Npad % 64 == 0 ? 64 : 32);
-    const int NT = Npad / BN;
-    const long tiles = (long)(sym ? NT * (NT + 1) / 2 : NT * NT) * B;
-    const int cap = Gpad / 256 > 0 ? Gpad / 256 : 1;
-    int best = 1;
-    double best_eff = 0.0;
-    for (int w = 1; w <= 4; ++w) {
-        long ns = (long)num_sms * w / tiles;
-        if (ns < 1) ns = 1;
-        if (ns > cap) ns = cap;
-        const long ctas = tiles * ns;
-        const long waves = (ctas + num_sms - 1) / num_sms;
-        const double eff = (double)ctas / (double)(waves * num_sms);
-        if (eff > best_eff + 1e-9) {
-            best_eff = eff;
-            best = (int)ns;
-        }
-        if (eff >= 0.9) break;
+void wsyrk_workspace(int num_sms, int Nc, int GpadMax, int B, bool general, size_t* part_doubles,
+                     size_t* item_bytes) {
+    WsPlan a, b;
+    ws_shape(num_sms, Nc, GpadMax, B, true, a);
+    size_t n = (size_t)a.nitems * a.BN * a.BN, it = a.nitems;
+    if (general) {
+        ws_shape(num_sms, Nc, GpadMax, B, false, b);
+        n = std::max(n, (size_t)b.nitems * b.BN * b.BN);
+        it = std::max(it, (size_t)b.nitems);
     }
-    return best;
+    *part_doubles = n;
+    *item_bytes = it * sizeof(WsItem);
+}
+
+double rowquad_executed_flops(const qexxc_ctx* c, int tri) {
+    const int BN = pick_bn(c->Nc), NB = BN / 16, NT = (c->Nc + BN - 1) / BN;
+    double blocks = 0.0;  // DMMAs per 8-row block of grid points
+    for (int nt = 0; nt < NT; ++nt) {
+        const int nw = std::min(BN, c->Nc - nt * BN), kend = rq_kend(tri, c->Nc, BN, nt), nbv = nw >> 3;
+        const int kd = tri ? std::min(kend, nt * BN / BK) : kend;
+        for (int wn = 0; wn < 2; ++wn) {
+            const int nvalid = clampi((nbv - wn + 1) >> 1, 0, NB);
+            blocks += (double)kd * 8 * nvalid;  // dense slabs: 8 k4 steps x nvalid blocks
+            if (nvalid == 0) continue;
+            for (int kb = kd; kb < kend; ++kb)  // diagonal slabs run the full-tile triangular variants
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int nbmin = 4 * ((kb * BK - nt * BN) / BK) + (kk >> 1);
+                    for (int j = 0; j < NB; ++j)
+                        if (2 * j + wn >= nbmin) blocks += 1.0;
+                }
+        }
+    }
+    return blocks * 512.0 * (c->Gpad / 8) * c->B;
+}
+
+double wsyrk_executed_flops(const qexxc_ctx* c, bool sym) {
+    WsPlan p;
+    ws_shape(c->num_sms, c->Nc, c->Gpad, c->B, sym, p);
+    double fl = 0.0;
+    for (int ti = 0; ti < p.NT; ++ti)
+        for (int tj = sym ? ti : 0; tj < p.NT; ++tj) {
+            long tot = 0;
+            ws_tile_cost(p.BN, c->Nc, ti, tj, sym && ti == tj, &tot);
+            fl += (double)tot * 512.0 * (c->Gpad / 4) * c->B;
+        }
+    return fl;
 }
 
 int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, int tri, cudaStream_t st) {
@@ -406,15 +737,15 @@ int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, int tri, cudaStrea
 
 int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride,
                    long q_cstride, cudaStream_t st) {
-    const int BN = pick_bn(c->Npad);
+    const int BN = pick_bn(c->Nc);
     dim3 grid(c->Gpad / BM, c->B);
     const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = ao_cs * c->C, S_bs = (long)c->Npad * c->Npad;
 #define QX_RQ(BNV)                                                                               \
     do {                                                                                         \
         QX_TRY(set_smem(rowquad_kernel<BNV>, RowquadCfg<BNV>::SMEM));                            \
         rowquad_kernel<BNV><<<grid, NTHREADS, RowquadCfg<BNV>::SMEM, st>>>(                      \
-            c->ao, c->S, q, c->Npad, ao_cs, ao_bs, S_bs, q_cstride, q_bstride, ncomp, tri,       \
-            (tri ? 2.0 : 1.0) * fac4[0], fac4[1], fac4[2], fac4[3]);                                                          \
+            c->ao, c->S, q, c->Npad, c->Nc, ao_cs, ao_bs, S_bs, q_cstride, q_bstride, ncomp, tri, \
+            (tri ? 2.0 : 1.0) * fac4[0], fac4[1], fac4[2], fac4[3]);                             \
     } while (0)
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
     if (BN == 128) QX_RQ(128);
@@ -427,35 +758,31 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double*
 
 int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bsrc, double scale, int tadd,
                  double* out, long out_bstride, cudaStream_t st) {
-    const int BN = pick_bn(c->Npad);
-    const int NT = c->Npad / BN;
     const bool sym = (Bsrc == nullptr);
-    int nsplit = wsyrk_pick_nsplit(c->num_sms, c->Npad, c->Gpad, c->B, sym);
-    if (nsplit > c->nsplit_max) nsplit = c->nsplit_max;
-    int rps = round_up((c->Gpad + nsplit - 1) / nsplit, BK);
+    WsPlan plan;
+    QX_TRY(ws_schedule(c, sym, plan, st));
     const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = ao_cs * c->C;
-    const long part_bs = (long)c->nsplit_max * c->Npad * c->Npad;
     const double* Bp = sym ? c->ao : Bsrc;
     const long B_bs = sym ? ao_bs : (long)c->GpadMax * c->Npad;
-    dim3 grid(sym ? NT * (NT + 1) / 2 : NT * NT, nsplit, c->B);
+    const WsItem* items = reinterpret_cast<const WsItem*>(c->ws_items[sym ? 1 : 0]);
+    const int* starts = c->ws_start[sym ? 1 : 0];
 #define QX_WS(BNV)                                                                               \
     do {                                                                                         \
         QX_TRY(set_smem(wsyrk_kernel<BNV>, WsyrkCfg<BNV>::SMEM));                                \
-        wsyrk_kernel<BNV><<<grid, NTHREADS, WsyrkCfg<BNV>::SMEM, st>>>(                          \
-            c->ao, Bp, s, c->part, c->Npad, c->Gpad, rps, sym ? 1 : 0, ao_bs, B_bs, s_bstride,   \
-            part_bs);                                                                            \
+        wsyrk_kernel<BNV><<<plan.nctas, NTHREADS, WsyrkCfg<BNV>::SMEM, st>>>(                    \
+            c->ao, Bp, s, c->part, c->Npad, c->Nc, items, starts, ao_bs, B_bs, s_bstride);  \
     } while (0)
     {
         ProfScope prof(c, QEXXC_PROF_WSYRK, st);
-        if (BN == 128) QX_WS(128);
-        else if (BN == 64) QX_WS(64);
+        if (plan.BN == 128) QX_WS(128);
+        else if (plan.BN == 64) QX_WS(64);
         else QX_WS(32);
     }
 #undef QX_WS
     QX_LAUNCH_CHECK(c);
     dim3 rgrid((c->N + 127) / 128, c->N, c->B);
-    wsyrk_reduce_kernel<<<rgrid, 128, 0, st>>>(c->part, out, c->N, c->Npad, BN, nsplit, sym ? 1 : 0,
-                                              scale, tadd, part_bs, out_bstride);
+    wsyrk_reduce_kernel<<<rgrid, 128, 0, st>>>(c->part, out, c->N, plan.BN, plan.NT, plan.nchunk, plan.ntile,
+                                              sym ? 1 : 0, scale, tadd, out_bstride);
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;
 }

@@ -305,6 +305,12 @@ class XCContext:
         with torch.cuda.device(self.device):
             check(self.lib.qexxc_debug_run_contraction(self._h, int(which), _stream()))
 
+    def contraction_flops(self, which: int, symmetric: bool) -> float:
+        """DMMA FLOPs one launch of rowquad (0) / wsyrk (1) executes for the current shape."""
+        v = C.c_double(0)
+        check(self.lib.qexxc_contraction_flops(self._h, int(which), 1 if symmetric else 0, C.byref(v)))
+        return v.value
+
     PROF_CLASSES = {"rowquad": 0, "wsyrk": 1, "xc_fwd": 2, "xc_vjp": 3, "eval_ao": 4}
 
     def profile_enable(self, on: bool = True):

@@ -227,3 +227,38 @@ def test_full_size_c5_properties():
     assert abs(oa[N * N] - ref["excsum"]) <= 1e-9
     assert rel_err(ba[: N * N].reshape(N, N), ref["dm_bar"]) <= TOL64
     assert rel_err(ba[N * N :], ref["theta_bar"]) <= TOL64
+
+
+def test_batched_h2_dissociation_geometries():
+    """Config c4's shape: a batch of H2 molecules at different bond lengths in ONE launch per stage
+    (per-batch env = per-batch geometry), each checked against the oracle."""
+    from qex_b200 import _lib, gen_grid, gto
+    from qex_b200.engine import NetSpec, XCContext
+
+    bonds = np.linspace(0.4, 3.0, 8)
+    mols = [gto.h2(float(b), "6-31g") for b in bonds]
+    grids = [gen_grid.Grids(m, n_rad=31, n_theta=5, n_phi=4).build() for m in mols]
+    B, N, G = len(mols), 4, grids[0].size
+    rng = np.random.default_rng(0)
+    dms = np.stack([2.0 * np.outer(c, c) for c in rng.standard_normal((B, N)) * 0.4])
+    spec = mlp_ref.MLPSpec([1, 64, 64, 64, 1], "tanh")
+    theta = mlp_ref.pack(*mlp_ref.init_params(spec, 0))
+    net = NetSpec(kind=_lib.NET_LOCAL_MLP, n_features=1, n_hidden=3, width=64)
+    ctx = XCContext(nao=N, ngrids_max=G, nbatch=B, net=net)
+    ctx.set_grid(np.stack([g.coords for g in grids]), np.stack([g.weights for g in grids]))
+    ctx.set_basis(mols[0]._atm, mols[0]._bas, np.stack([m._env for m in mols])).eval_ao(0)
+    out, resid = ctx.nr_rks_fwd(dms, theta, "NN")
+    e_bar, v_bar = rng.standard_normal(B), rng.standard_normal((B, N, N))
+    bar = ctx.nr_rks_vjp(theta, resid, e_bar, v_bar, "NN").cpu().numpy()
+    out = out.cpu().numpy()
+    netd = dict(kind="local_mlp", n_features=1, n_hidden=3, width=64)
+    tsum = 0
+    for b in range(B):
+        m = mols[b]
+        ref = step_ref.xc_step(m._atm, m._bas, m._env, grids[b].coords, grids[b].weights, dms[b], netd, theta, "NN",
+                               e_bar[b], v_bar[b])
+        assert rel_err(out[b, : N * N].reshape(N, N), ref["vmat"]) <= TOL64
+        assert abs(out[b, N * N] - ref["excsum"]) <= 1e-9 and abs(out[b, N * N + 1] - ref["nelec"]) <= 1e-9
+        assert rel_err(bar[b * N * N : (b + 1) * N * N].reshape(N, N), ref["dm_bar"]) <= TOL64
+        tsum = tsum + ref["theta_bar"]
+    assert rel_err(bar[B * N * N :], tsum) <= TOL64
