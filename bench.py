@@ -317,6 +317,26 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = G / (ms_step * 1e-3)
 
+    # ---- extra: the same step with the MO form of rho (dm tagged with mo_coeff/mo_occ takes pyscf's
+    # eval_rho2 branch, numint_legacy.py:527-545).  Reported separately; the headline stays dense-dm. ----
+    mo_ms = None
+    if "mo_coeff" in wl.extra and wl.xctype != "GGA":
+        d_C, d_occ = ctx.dev(wl.extra["mo_coeff"]), ctx.dev(wl.extra["mo_occ"])
+
+        def step_mo():
+            ctx.set_grid(d_coords, d_w)
+            ctx.eval_ao(deriv)
+            ctx.nr_rks_fwd_mo(d_C, d_occ, d_th, wl.xctype, out=out, resid=resid)
+            if world > 1:
+                dist.all_reduce(out)
+            ctx.nr_rks_vjp(d_th, resid, d_eb, d_vb, wl.xctype, 0, out=bar)
+            if world > 1:
+                dist.all_reduce(bar)
+
+        for _ in range(2):
+            step_mo()
+        mo_ms = timed(step_mo, args.steps) / args.steps
+
     # ---- e2e: host buffers, copies inside the timed region ----
     for _ in range(2):
         step_e2e()
@@ -373,6 +393,10 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": G / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
+            "mo_path": None if mo_ms is None else {
+                "value": G / (mo_ms * 1e-3), "unit": UNIT, "ms_per_step": mo_ms,
+                "note": "same step with stage 2 in its MO form rho = sum_k occ_k (ao C_k)^2 (150 occupied orbitals), the "
+                        "branch the reference takes when dm carries mo_coeff/mo_occ (numint_legacy.py:527-545); not the headline"},
             "gpu_launches": int(launches), "clocks": clocks, "hbm_peak_gbs": hbm,
             "workspace_gb": ctx.workspace_bytes / 1e9,
         }

@@ -167,6 +167,15 @@ int qexxc_vxc_assemble_vjp(qexxc_ctx* ctx, int xctype, const double* rho_dev,
  *   (trainer_legacy_no_jit.py:284): (e_bar [B], v_bar [B][N][N]) -> bar [B*N*N + n_params] =
  *   dm_bar (B*N*N) | theta_bar (n_params, summed over batch); nelec is stop-gradient (:305). */
 size_t qexxc_resid_doubles(const qexxc_ctx* ctx);
+/* MO form of the density: NumInt._gen_rho_evaluator's `dms.mo_coeff` branch (numint_legacy.py:527-545 ->
+ * pyscf eval_rho2): rho = sum_k occ_k (ao C_k)^2 over orbitals with |occ_k| > 1e-12 (negative occupations
+ * subtract).  mo_coeff [B][N][nmo], mo_occ [B][nmo], nmo <= N; 2*G*N*nmo instead of 2*G*N^2 FLOPs.
+ * qexxc_nr_rks_fwd_mo = qexxc_nr_rks_fwd with that stage 2 (LDA-type branches); outputs, residuals and
+ * the reverse pass (qexxc_nr_rks_vjp, cotangent w.r.t. dm = C occ C^T) are unchanged. */
+int qexxc_eval_rho_mo(qexxc_ctx* ctx, const double* mo_coeff_dev, const double* mo_occ_dev, int nmo,
+                      double* rho_dev, void* stream);
+int qexxc_nr_rks_fwd_mo(qexxc_ctx* ctx, int xctype, const double* mo_coeff_dev, const double* mo_occ_dev, int nmo,
+                        const double* theta_dev, double* out_dev, double* resid_dev, void* stream);
 int qexxc_nr_rks_fwd(qexxc_ctx* ctx, int xctype, int hermi, const double* dm_dev,
                      const double* theta_dev, double* out_dev, double* resid_dev, void* stream);
 int qexxc_nr_rks_vjp(qexxc_ctx* ctx, int xctype, int hermi, const double* theta_dev,

@@ -63,6 +63,26 @@ def eval_rho(ao, dm, xctype="LDA", hermi=0):
     raise NotImplementedError("oracle eval_rho: xctype " + xctype)
 
 
+def eval_rho2(ao, mo_coeff, mo_occ, xctype="LDA"):
+    """pyscf ``numint.eval_rho2`` (LDA part), reached through ``NumInt._gen_rho_evaluator`` when the
+    density matrix carries ``mo_coeff`` / ``mo_occ`` (numint_legacy.py:527-545):
+    rho = sum_k occ_k (ao C_k)^2 for occ_k > OCCDROP, minus the same for occ_k < -OCCDROP."""
+    if xctype.upper() not in ("LDA", "HF"):
+        raise NotImplementedError("oracle eval_rho2: LDA only")
+    OCCDROP = 1e-12
+    mo_coeff, mo_occ = np.asarray(mo_coeff, dtype=np.float64), np.asarray(mo_occ, dtype=np.float64)
+    rho = np.zeros(ao.shape[0])
+    pos = mo_occ > OCCDROP
+    if pos.sum() > 0:
+        c0 = ao @ (mo_coeff[:, pos] * np.sqrt(mo_occ[pos]))
+        rho += contract_rho(c0, c0)
+    neg = mo_occ < -OCCDROP
+    if neg.sum() > 0:
+        c0 = ao @ (mo_coeff[:, neg] * np.sqrt(-mo_occ[neg]))
+        rho -= contract_rho(c0, c0)
+    return rho
+
+
 def scale_ao(ao, wv):
     """numint_legacy.py:432-442: aow[p,i] = sum_n ao[n,p,i] wv[n,p]."""
     if wv.ndim == 2:

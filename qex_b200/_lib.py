@@ -27,7 +27,7 @@ EXPORTS = [
     "qexxc_get_ao", "qexxc_eval_rho", "qexxc_eval_rho_vjp", "qexxc_xc_fwd", "qexxc_xc_vjp",
     "qexxc_apply_fn_fwd", "qexxc_apply_fn_vjp", "qexxc_vxc_assemble", "qexxc_vxc_assemble_vjp",
     "qexxc_resid_doubles", "qexxc_nr_rks_fwd", "qexxc_nr_rks_vjp", "qexxc_launch_count",
-    "qexxc_debug_run_contraction", "qexxc_profile_enable", "qexxc_profile_read", "qexxc_contraction_flops",
+    "qexxc_debug_run_contraction", "qexxc_profile_enable", "qexxc_profile_read", "qexxc_contraction_flops", "qexxc_eval_rho_mo", "qexxc_nr_rks_fwd_mo",
 ]
 
 
@@ -91,6 +91,8 @@ def load(build_if_missing: bool = False):
         "qexxc_launch_count": (l, [vp]),
         "qexxc_debug_run_contraction": (i, [vp, i, vp]),
         "qexxc_profile_enable": (i, [vp, i]),
+        "qexxc_eval_rho_mo": (i, [vp, p, p, i, p, vp]),
+        "qexxc_nr_rks_fwd_mo": (i, [vp, i, p, p, i, p, p, p, vp]),
         "qexxc_contraction_flops": (i, [vp, i, i, C.POINTER(C.c_double)]),
         "qexxc_profile_read": (i, [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     }

@@ -134,6 +134,28 @@ static int assemble_vmat(qexxc_ctx* c, int xctype, const double* wv, double* out
     return launch_wsyrk(c, wv, (long)c->C * ld, nullptr, 1.0, 1, out, ob, st);
 }
 
+// stages 3 and 4 of nr_rks on the context's rho buffer, plus the residual copy-out
+static int nr_rks_after_rho(qexxc_ctx* c, int xctype, const double* theta_dev, double* out_dev, double* resid_dev,
+                            cudaStream_t st) {
+    const long ld = c->GpadMax;
+    // stage 3: exc, vrho (, vgamma)                    numint_legacy.py:295-303
+    QX_TRY(net_fwd(c, xctype, c->rho, theta_dev, c->exc, c->vrho, c->vgamma, st));
+    // stage 4: nelec, excsum, wv, vmat + vmat.T        numint_legacy.py:304-309, 336-337
+    const long ob = (long)c->N * c->N + 2;
+    QX_TRY(launch_stage4_pointwise(c, xctype, c->rho, c->exc, c->vrho, c->vgamma, c->wv,
+                                   out_dev + (long)c->N * c->N, ob, st));
+    QX_TRY(assemble_vmat(c, xctype, c->wv, out_dev, st));
+    if (resid_dev) {
+        const size_t n = (size_t)c->B * ld;
+        QX_CUDA(cudaMemcpyAsync(resid_dev, c->rho, sizeof(double) * n * c->C, cudaMemcpyDeviceToDevice, st));
+        QX_CUDA(cudaMemcpyAsync(resid_dev + n * c->C, c->exc, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        QX_CUDA(cudaMemcpyAsync(resid_dev + n * (c->C + 1), c->vrho, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        QX_CUDA(cudaMemcpyAsync(resid_dev + n * (c->C + 2), c->vgamma, sizeof(double) * n, cudaMemcpyDeviceToDevice,
+                                st));
+    }
+    return QEXXC_OK;
+}
+
 static int need_ao(const qexxc_ctx* c, int ncomp) {
     if (!c->have_grid) {
         set_error("qexxc_set_grid has not been called");
@@ -221,6 +243,7 @@ int qexxc_create(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngrids_
     QX_A(c->weights, B * Gp);
     QX_A(c->ao, B * C * Gp * Np);
     QX_A(c->S, B * Np * Np);
+    QX_A(c->mosgn, B * Np);
     QX_A(c->rho, B * C * Gp);
     QX_A(c->exc, B * Gp);
     QX_A(c->vrho, B * Gp);
@@ -649,22 +672,41 @@ int qexxc_nr_rks_fwd(qexxc_ctx* c, int xctype, int hermi, const double* dm_dev, 
     // stage 2: rho = rowdot(ao, ao sym(dm))            numint_legacy.py:294 -> :351-397
     QX_TRY(launch_pad_sym(c, dm_dev, (nc == 1 || !hermi) ? 0 : 1, nc == 1, st));
     QX_TRY(launch_rowquad(c, nc, nc == 1, kFacGGA, c->rho, (long)c->C * ld, ld, st));
-    // stage 3: exc, vrho (, vgamma)                    numint_legacy.py:295-303
-    QX_TRY(net_fwd(c, xctype, c->rho, theta_dev, c->exc, c->vrho, c->vgamma, st));
-    // stage 4: nelec, excsum, wv, vmat + vmat.T        numint_legacy.py:304-309, 336-337
-    const long ob = (long)c->N * c->N + 2;
-    QX_TRY(launch_stage4_pointwise(c, xctype, c->rho, c->exc, c->vrho, c->vgamma, c->wv,
-                                   out_dev + (long)c->N * c->N, ob, st));
-    QX_TRY(assemble_vmat(c, xctype, c->wv, out_dev, st));
-    if (resid_dev) {
-        const size_t n = (size_t)c->B * ld;
-        QX_CUDA(cudaMemcpyAsync(resid_dev, c->rho, sizeof(double) * n * c->C, cudaMemcpyDeviceToDevice, st));
-        QX_CUDA(cudaMemcpyAsync(resid_dev + n * c->C, c->exc, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-        QX_CUDA(cudaMemcpyAsync(resid_dev + n * (c->C + 1), c->vrho, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-        QX_CUDA(cudaMemcpyAsync(resid_dev + n * (c->C + 2), c->vgamma, sizeof(double) * n, cudaMemcpyDeviceToDevice,
-                                st));
+    return nr_rks_after_rho(c, xctype, theta_dev, out_dev, resid_dev, st);
+}
+
+int qexxc_eval_rho_mo(qexxc_ctx* c, const double* mo_coeff_dev, const double* mo_occ_dev, int nmo, double* rho_dev,
+                      void* stream) {
+    QX_ARG(c != nullptr && mo_coeff_dev && mo_occ_dev && rho_dev, "null pointer");
+    QX_ARG(nmo >= 1 && nmo <= c->N, "nmo must be in [1, nao]");
+    QX_TRY(need_ao(c, 1));
+    QX_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long ld = c->GpadMax;
+    const int ldL = round_up(nmo, kNTile);
+    QX_TRY(launch_pack_mo(c, mo_coeff_dev, mo_occ_dev, nmo, c->S, c->mosgn, ldL, st));
+    QX_TRY(launch_rowquad_mo(c, c->S, ldL, nmo, c->mosgn, c->rho, (long)c->C * ld, st));
+    return launch_copy_rows(c, rho_dev, c->G, c->G, c->rho, (long)c->C * ld, ld, c->B, 1, c->G, c->G, st);
+}
+
+int qexxc_nr_rks_fwd_mo(qexxc_ctx* c, int xctype, const double* mo_coeff_dev, const double* mo_occ_dev, int nmo,
+                        const double* theta_dev, double* out_dev, double* resid_dev, void* stream) {
+    QX_ARG(c != nullptr && mo_coeff_dev && mo_occ_dev && theta_dev && out_dev, "null pointer");
+    QX_ARG(nmo >= 1 && nmo <= c->N, "nmo must be in [1, nao]");
+    QX_TRY(check_xctype(c, xctype, true));
+    if (xctype == QEXXC_XC_GGA) {
+        set_error("the MO form of rho is implemented for the LDA-type branches (NN, NN-AmplitudeEncoding) only");
+        return QEXXC_ERR_UNSUPPORTED;
     }
-    return QEXXC_OK;
+    QX_TRY(need_ao(c, 1));
+    QX_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long ld = c->GpadMax;
+    const int ldL = round_up(nmo, kNTile);
+    // stage 2, MO form: rho = sum_k occ_k (ao C_k)^2   numint_legacy.py:527-545 -> pyscf eval_rho2
+    QX_TRY(launch_pack_mo(c, mo_coeff_dev, mo_occ_dev, nmo, c->S, c->mosgn, ldL, st));
+    QX_TRY(launch_rowquad_mo(c, c->S, ldL, nmo, c->mosgn, c->rho, (long)c->C * ld, st));
+    return nr_rks_after_rho(c, xctype, theta_dev, out_dev, resid_dev, st);
 }
 
 int qexxc_nr_rks_vjp(qexxc_ctx* c, int xctype, int hermi, const double* theta_dev, const double* resid_dev,

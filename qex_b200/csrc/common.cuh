@@ -97,7 +97,8 @@ struct qexxc_ctx {
     int natm = 0, nrad = 0, lmax = 0;
 
     // stage 2/4 workspaces (all [B][...][GpadMax] rows are zero beyond G)
-    double* S = nullptr;        // [B][Npad][Npad] padded symmetric operand (dm or V_bar + V_bar^T)
+    double* S = nullptr;        // [B][Npad][Npad] padded symmetric operand (dm or V_bar + V_bar^T); also MO factor L
+    double* mosgn = nullptr;    // [B][Npad] occupation signs of the MO form
     double* rho = nullptr;      // [B][C][GpadMax]
     double* exc = nullptr;      // [B][GpadMax]
     double* vrho = nullptr;     // [B][GpadMax]
@@ -165,6 +166,11 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double*
 // out[b][i][j] = scale * (H[i][j] + (tadd ? H[j][i] : 0)), i,j < N, row stride N
 int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bsrc, double scale, int tadd,
                  double* out, long out_bstride, cudaStream_t st);
+// MO form of rho (pyscf eval_rho2, reached by numint_legacy.py:527-545)
+int launch_pack_mo(qexxc_ctx* c, const double* C, const double* occ, int nmo, double* L, double* sgn, int ldL,
+                   cudaStream_t st);
+int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, long q_bstride,
+                      cudaStream_t st);
 // aow[b][g][n] = sum_c f[c] wv[b][c][g] ao[b][c][g][n]
 int launch_build_aow(qexxc_ctx* c, const double* wv, long wv_bstride, long wv_cstride, const double* fac4,
                      cudaStream_t st);

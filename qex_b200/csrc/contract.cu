@@ -169,10 +169,14 @@ template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, double* __restrict__ q,
                int Npad, int Nc, long ao_cstride, long ao_bstride, long S_bstride, long q_cstride,
-               long q_bstride, int ncomp, int tri, double f0, double f1, double f2, double f3) {
+               long q_bstride, int ncomp, int tri, double f0, double f1, double f2, double f3, int ldS, int Sc,
+               const double* __restrict__ sgn) {
     // tri != 0: S holds only its upper triangle (diagonal halved); the caller folds the factor 2
     // into f0.  Npad = storage pitch (multiple of 32, pad columns are zeros), Nc = compute extent
     // (multiple of 8): slabs are always full, column blocks beyond Nc are never issued.
+    // S is [Npad rows][ldS pitch] with Sc compute columns: the square symmetric operand (ldS = Npad,
+    // Sc = Nc) or, when sgn != nullptr, the occupation-scaled MO coefficients L = C sqrt|occ| of pyscf's
+    // eval_rho2 (numint_legacy.py:527-545): then q[g] = f0 * sum_k sgn_k ((ao L)[g,k])^2.
     using Cfg = RowquadCfg<BN>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
@@ -186,7 +190,7 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
     const double* ao_b = ao + (long)b * ao_bstride;
     const double* A0 = ao_b + g0 * Npad;
     const double* S_b = S + (long)b * S_bstride;
-    const int NT = (Nc + BN - 1) / BN;
+    const int NT = (Sc + BN - 1) / BN;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -206,7 +210,7 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
         const int pw = warp - NCONS;
         int it = 0;
         for (int nt = 0; nt < NT; ++nt) {
-            const int nw = imin(BN, Npad - nt * BN);  // copy width: storage columns (zeros beyond Nc)
+            const int nw = imin(BN, ldS - nt * BN);  // copy width: storage columns (zeros beyond Sc)
             const int kend = rq_kend(tri, Nc, BN, nt);
             for (int kb = 0; kb < kend; ++kb, ++it) {
                 const int s = it % NSTAGE;
@@ -218,7 +222,7 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
                 const int r = pw * 32 + lane;
                 bulk_g2s(As + r * Cfg::LDA, A0 + (long)r * Npad + kb * BK, BK * 8, full + s);
                 if (pw == 0)
-                    bulk_g2s(Bs + lane * Cfg::LDB, S_b + (long)(kb * BK + lane) * Npad + nt * BN, nw * 8, full + s);
+                    bulk_g2s(Bs + lane * Cfg::LDB, S_b + (long)(kb * BK + lane) * ldS + nt * BN, nw * 8, full + s);
             }
         }
         return;
@@ -240,7 +244,7 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
     const int aoff = (wm * 32 + g) * Cfg::LDA + qd;
     const int boff = qd * Cfg::LDB + wn * 8 + g;  // this warp's blocks are 2*j + wn: 16 doubles apart
     for (int nt = 0; nt < NT; ++nt) {
-        const int nw = imin(BN, Nc - nt * BN);
+        const int nw = imin(BN, Sc - nt * BN);
         const int kend = rq_kend(tri, Nc, BN, nt);
         const int nbv = nw >> 3;                             // valid n8 blocks of this tile
         const int nvalid = clampi((nbv - wn + 1) >> 1, 0, NB);  // ... of which this warp owns 2*j + wn < nbv
@@ -259,6 +263,24 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
         for (int kb = kd; kb < kend; ++kb) {
             if (nvalid == 0) ring_skip(ring, 1, lane);
             else rq_diag<BN, BN / BK - 1>(acc, ring, (kb * BK - c0) / BK, wn, aoff, boff, lane);
+        }
+        if (sgn != nullptr) {
+            // MO form: signed sum of squares of the (ao L) tile
+            const double* sg = sgn + (long)b * ldS + c0 + wn * 8 + 2 * qd;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                double sum = 0.0;
+#pragma unroll
+                for (int nj = 0; nj < NB; ++nj) {
+                    if (nj < nvalid) {
+                        const double2 sv = *reinterpret_cast<const double2*>(sg + nj * 16);
+                        sum = fma(acc[mi][nj][0] * acc[mi][nj][0], sv.x, sum);
+                        sum = fma(acc[mi][nj][1] * acc[mi][nj][1], sv.y, sum);
+                    }
+                }
+                rp[0][mi] += sum;
+            }
+            continue;
         }
         // epilogue of this column tile: row-dot the (ao_0 S) tile with each AO component
 #pragma unroll
@@ -544,6 +566,24 @@ __global__ void build_aow_kernel(const double* __restrict__ ao, const double* __
     }
 }
 
+// L[b][i][k] = C[b][i][k] * sqrt(|occ[b][k]|) for |occ| > 1e-12 (pyscf OCCDROP), zero padded; sgn = sign(occ)
+__global__ void pack_mo_kernel(const double* __restrict__ C, const double* __restrict__ occ, double* __restrict__ L,
+                               double* __restrict__ sgn, int N, int nmo, int Npad, int ldL) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y, b = blockIdx.z;
+    if (k >= ldL) return;
+    double v = 0.0, s = 0.0;
+    if (k < nmo) {
+        const double o = occ[(long)b * nmo + k];
+        if (fabs(o) > 1e-12) {
+            s = o > 0 ? 1.0 : -1.0;
+            if (i < N) v = C[((long)b * N + i) * nmo + k] * sqrt(fabs(o));
+        }
+    }
+    L[((long)b * Npad + i) * ldL + k] = v;
+    if (i == 0) sgn[(long)b * ldL + k] = s;
+}
+
 int pick_bn(int Npad) { return Npad > 64 ? 128 : (Npad > 32 ? 64 : 32); }
 
 template <typename K>
@@ -750,9 +790,41 @@ double wsyrk_executed_flops(const qexxc_ctx* c, bool sym) {
     return fl;
 }
 
+int launch_pack_mo(qexxc_ctx* c, const double* C, const double* occ, int nmo, double* L, double* sgn, int ldL,
+                   cudaStream_t st) {
+    dim3 grid((ldL + 127) / 128, c->Npad, c->B);
+    pack_mo_kernel<<<grid, 128, 0, st>>>(C, occ, L, sgn, c->N, nmo, c->Npad, ldL);
+    QX_LAUNCH_CHECK(c);
+    return QEXXC_OK;
+}
+
 int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, int tri, cudaStream_t st) {
     dim3 grid((c->Npad + 127) / 128, c->Npad, c->B);
     pad_sym_kernel<<<grid, 128, 0, st>>>(src, c->S, c->N, c->Npad, mode, tri);
+    QX_LAUNCH_CHECK(c);
+    return QEXXC_OK;
+}
+
+// MO form of the density (pyscf eval_rho2): L [B][Npad][ldL] = C sqrt|occ| (zero padded), sgn [B][ldL] = sign of
+// the occupation (0 for padding); q[b][g] = sum_k sgn_k ((ao L)[g,k])^2 with nk compute columns.
+int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, long q_bstride,
+                      cudaStream_t st) {
+    const int Sc = round_up(nk > 0 ? nk : 1, kNBlock);
+    const int BN = pick_bn(Sc);
+    dim3 grid(c->Gpad / BM, c->B);
+    const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = ao_cs * c->C, L_bs = (long)c->Npad * ldL;
+#define QX_RQM(BNV)                                                                              \
+    do {                                                                                         \
+        QX_TRY(set_smem(rowquad_kernel<BNV>, RowquadCfg<BNV>::SMEM));                            \
+        rowquad_kernel<BNV><<<grid, NTHREADS, RowquadCfg<BNV>::SMEM, st>>>(                      \
+            c->ao, L, q, c->Npad, c->Nc, ao_cs, ao_bs, L_bs, 0, q_bstride, 1, 0, 1.0, 0.0, 0.0,  \
+            0.0, ldL, Sc, sgn);                                                                  \
+    } while (0)
+    ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
+    if (BN == 128) QX_RQM(128);
+    else if (BN == 64) QX_RQM(64);
+    else QX_RQM(32);
+#undef QX_RQM
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;
 }
@@ -767,7 +839,7 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double*
         QX_TRY(set_smem(rowquad_kernel<BNV>, RowquadCfg<BNV>::SMEM));                            \
         rowquad_kernel<BNV><<<grid, NTHREADS, RowquadCfg<BNV>::SMEM, st>>>(                      \
             c->ao, c->S, q, c->Npad, c->Nc, ao_cs, ao_bs, S_bs, q_cstride, q_bstride, ncomp, tri, \
-            (tri ? 2.0 : 1.0) * fac4[0], fac4[1], fac4[2], fac4[3]);                             \
+            (tri ? 2.0 : 1.0) * fac4[0], fac4[1], fac4[2], fac4[3], c->Npad, c->Nc, nullptr);    \
     } while (0)
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
     if (BN == 128) QX_RQ(128);

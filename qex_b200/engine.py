@@ -287,6 +287,35 @@ class XCContext:
                                             self._p(resid if want_resid else None), _stream()))
         return out, (resid if want_resid else None)
 
+    def _mo(self, mo_coeff, mo_occ):
+        B, N = self.nbatch, self.nao
+        occ = self.dev(mo_occ).reshape(B, -1)
+        nmo = occ.shape[1]
+        return self.dev(mo_coeff, (B, N, nmo)), occ, nmo
+
+    def eval_rho_mo(self, mo_coeff, mo_occ) -> torch.Tensor:
+        """rho = sum_k occ_k (ao C_k)^2 (pyscf eval_rho2, numint_legacy.py:527-545) -> [B, 1, G]."""
+        C_, occ, nmo = self._mo(mo_coeff, mo_occ)
+        out = self.empty(self.nbatch, 1, self.ngrids)
+        with torch.cuda.device(self.device):
+            check(self.lib.qexxc_eval_rho_mo(self._h, self._p(C_), self._p(occ), nmo, self._p(out), _stream()))
+        return out
+
+    def nr_rks_fwd_mo(self, mo_coeff, mo_occ, theta, xctype="NN", want_resid: bool = True, out=None, resid=None):
+        """nr_rks forward with the MO form of stage 2 (dm = C occ C^T is never formed)."""
+        xt = _xct(xctype)
+        B, N = self.nbatch, self.nao
+        C_, occ, nmo = self._mo(mo_coeff, mo_occ)
+        th = self.dev(theta)
+        if out is None:
+            out = self.empty(B, N * N + 2)
+        if want_resid and resid is None:
+            resid = self.empty(self.resid_doubles)
+        with torch.cuda.device(self.device):
+            check(self.lib.qexxc_nr_rks_fwd_mo(self._h, xt, self._p(C_), self._p(occ), nmo, self._p(th), self._p(out),
+                                               self._p(resid if want_resid else None), _stream()))
+        return out, (resid if want_resid else None)
+
     def nr_rks_vjp(self, theta, resid, e_bar, v_bar, xctype="NN", hermi: int = 0, out=None):
         """-> bar [B*N*N + n_theta] = dm_bar | theta_bar."""
         xt = _xct(xctype)

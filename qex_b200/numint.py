@@ -28,6 +28,17 @@ from .xc import _native_apply, _theta
 from .xc import eval_xc as _native_eval_xc
 
 
+class NPArrayWithTag(np.ndarray):
+    """ndarray carrying attributes, like ``pyscf.lib.tag_array`` (how pyscf attaches ``mo_coeff`` /
+    ``mo_occ`` to a density matrix; read by ``_gen_rho_evaluator``, numint_legacy.py:527-545)."""
+
+
+def tag_array(a, **kwargs):
+    t = np.asarray(a).view(NPArrayWithTag)
+    t.__dict__.update(kwargs)
+    return t
+
+
 def _np(x):
     import torch
 
@@ -125,6 +136,7 @@ class NumInt:
     def nr_rks(self, mol, grids, xc_code, dms, relativity=0, hermi=0, max_memory=2000, verbose=None, params=None,
                return_resid=False):
         xctype = _xctype(self, xc_code)
+        dms_in = dms
         dms = _np(dms)
         single = dms.ndim == 2
         dm_list = [dms] if single else list(dms)
@@ -133,6 +145,14 @@ class NumInt:
         ncomp = 4 if gga else 1
         N, G = mol.nao_nr(), int(np.asarray(grids.weights).shape[0])
         nelec, excsum, vmat, resids = [], [], [], []
+        # numint_legacy.py:527-545: a dm tagged with mo_coeff / mo_occ takes the MO form of rho (eval_rho2)
+        mo_coeff, mo_occ = getattr(dms_in, "mo_coeff", None), getattr(dms_in, "mo_occ", None)
+        use_mo = mo_coeff is not None and mo_occ is not None and single and not gga
+        if use_mo:
+            mo_coeff, mo_occ = _np(mo_coeff), _np(mo_occ)
+            keep = np.abs(mo_occ) > 1e-12  # OCCDROP: only occupied orbitals enter (pos/neg handled by sign)
+            mo_coeff, mo_occ = np.ascontiguousarray(mo_coeff[:, keep]), np.ascontiguousarray(mo_occ[keep])
+            use_mo = mo_occ.size > 0
         if fn is not None:
             if xctype == "NN-AmplitudeEncoding" and not is_global:
                 raise ValueError("xctype 'NN-AmplitudeEncoding' needs eval_xc built with is_global_xc=True")
@@ -140,8 +160,12 @@ class NumInt:
             self._load(ctx, mol, grids, 1 if gga else 0)
             theta = _theta(fn, params)
             for dm in dm_list:
-                out, resid = ctx.nr_rks_fwd(dm, theta, "NN" if xctype == "LDA" else xctype, hermi,
-                                            want_resid=return_resid)
+                if use_mo:
+                    out, resid = ctx.nr_rks_fwd_mo(mo_coeff, mo_occ, theta, "NN" if xctype == "LDA" else xctype,
+                                                   want_resid=return_resid)
+                else:
+                    out, resid = ctx.nr_rks_fwd(dm, theta, "NN" if xctype == "LDA" else xctype, hermi,
+                                                want_resid=return_resid)
                 o = out[0].cpu().numpy()
                 vmat.append(o[: N * N].reshape(N, N).copy())
                 excsum.append(float(o[N * N]))
@@ -153,7 +177,7 @@ class NumInt:
             ctx = self._ctx(N, G, ncomp, None)
             self._load(ctx, mol, grids, 1 if gga else 0)
             for dm in dm_list:
-                rho = ctx.eval_rho(dm, ncomp, hermi)
+                rho = ctx.eval_rho_mo(mo_coeff, mo_occ) if use_mo else ctx.eval_rho(dm, ncomp, hermi)
                 r = rho[0].cpu().numpy()
                 exc, vxc = self.eval_xc(xc_code, r[0] if ncomp == 1 else r, spin=0, relativity=relativity, deriv=1,
                                         verbose=verbose, params=params)[:2]

@@ -48,10 +48,16 @@ def _mlp_theta(sizes, seed=0):
     return np.concatenate(parts)
 
 
-def _dm(N, rank, seed):
+def _mo(N, rank, seed):
+    """`rank` doubly occupied orbitals: dm = C occ C^T with occ = 2."""
     rng = np.random.default_rng(seed)
     Cm = rng.standard_normal((N, rank)) / np.sqrt(N)
-    return 2.0 * Cm @ Cm.T
+    return Cm, np.full(rank, 2.0)
+
+
+def _dm(N, rank, seed):
+    Cm, occ = _mo(N, rank, seed)
+    return (Cm * occ) @ Cm.T
 
 
 def _cotangents(N, seed):
@@ -77,7 +83,8 @@ def make(config: str = "c5", ngrids: int | None = None, seed: int = 0) -> Worklo
             mol=mol, coords=grid.coords, weights=grid.weights, dm=_dm(N, 150, seed + 2),
             xctype="GGA" if gga else "NN", ncomp=4 if gga else 1,
             net=dict(kind="local_mlp", n_features=2 if gga else 1, n_hidden=3, width=64, activation="tanh"),
-            theta=_mlp_theta(sizes, seed), e_bar=e_bar, v_bar=v_bar)
+            theta=_mlp_theta(sizes, seed), e_bar=e_bar, v_bar=v_bar,
+            extra=dict(zip(("mo_coeff", "mo_occ"), _mo(N, 150, seed + 2))))
     if config == "c3":
         # water-size: ~120 AOs, ~50k grid points, LocalMLP GGA features (configs[2])
         mol = gto.synthetic_molecule(3, (5, 5, 4), seed=seed)  # 3 atoms x 40 AOs

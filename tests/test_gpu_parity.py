@@ -406,6 +406,39 @@ def test_end_to_end_from_basis_tables():
     assert abs(out[N * N + 1] - nelec) <= 1e-9 * max(1.0, abs(nelec))
 
 
+@pytest.mark.parametrize("N,G,nmo", [(4, 1240, 1), (120, 2000, 5), (200, 515, 37), (257, 1100, 150)])
+def test_mo_form_of_rho_and_nr_rks(N, G, nmo):
+    """NumInt._gen_rho_evaluator's mo_coeff branch (numint_legacy.py:527-545 -> eval_rho2): same rho and
+    the same nr_rks outputs as the dense-dm path with dm = C occ C^T (one negative occupation included)."""
+    rng = np.random.default_rng(N + nmo)
+    ao = rng.standard_normal((G, N)) * np.exp(-np.abs(rng.standard_normal((G, 1))) * 1.5) * 0.6
+    w = np.abs(rng.standard_normal(G)) * 10.0 / G
+    Cm = rng.standard_normal((N, nmo)) / np.sqrt(N)
+    occ = np.full(nmo, 2.0)
+    occ[-1] = 1.0
+    if nmo > 2:
+        occ[1] = -0.5
+        occ[2] = 0.0  # dropped (|occ| <= OCCDROP)
+    dm = (Cm * occ) @ Cm.T
+    spec = mlp_ref.MLPSpec([1, 64, 64, 64, 1], "tanh")
+    theta = mlp_ref.pack(*mlp_ref.init_params(spec, 2))
+    ctx = _ctx(nao=N, ngrids_max=G, net=_mlp_net())
+    ctx.set_grid(None, w).set_ao(ao, 1)
+    rho = _to_np(ctx.eval_rho_mo(Cm, occ))[0, 0]
+    assert rel_err(rho, numint_ref.eval_rho2(ao, Cm, occ)) <= TOL64
+    assert rel_err(rho, numint_ref.eval_rho(ao, dm, "LDA")) <= 1e-9  # the two forms agree up to rounding
+    out_mo, resid = ctx.nr_rks_fwd_mo(Cm, occ, theta, "NN")
+    out_dm, _ = ctx.nr_rks_fwd(dm, theta, "NN")
+    assert rel_err(_to_np(out_mo), _to_np(out_dm)) <= 1e-9
+    e_bar, v_bar = rng.standard_normal(1), rng.standard_normal((1, N, N))
+    bar = _to_np(ctx.nr_rks_vjp(theta, resid, e_bar, v_bar, "NN"))
+    D, tb = numint_ref.nr_rks_vjp(
+        ao, w, dm, lambda r, p: mlp_ref.exc_and_vrho_local(spec, theta, r),
+        lambda r, p, eb, vb: mlp_ref.exc_and_vrho_local_vjp(spec, theta, r, eb, vb), e_bar[0], v_bar[0], "NN")
+    assert rel_err(bar[: N * N].reshape(N, N), D) <= 1e-9
+    assert rel_err(bar[N * N :], tb) <= 1e-9
+
+
 def test_errors_are_loud():
     from qex_b200 import _lib
 
