@@ -111,14 +111,15 @@ struct Smem {
     T* buf0;   // [R][LD]
     T* buf1;   // [R][LD]
     T* u;      // [R]
-    T* gacc;   // [L+2][HP]    reverse: bias / last-layer weight gradient accumulators
+    T* gacc;   // [L+4][HP]    reverse: bias, last-layer and first-layer weight gradient accumulators
+    T* scratch;  // [8][HP]     reverse: partial column sums
 };
 
 template <typename T>
 __host__ __device__ inline size_t smem_elems(int L, bool vjp) {
     size_t n = 8 * LD + (size_t)(L - 1) * HP * LD + HP + (size_t)(L + 1) * HP + (size_t)R * LDX +
                2 * (size_t)R * LD + R;
-    if (vjp) n += (size_t)(L + 2) * HP;
+    if (vjp) n += (size_t)(L + 4) * HP + 8 * HP;
     return n;
 }
 
@@ -135,6 +136,7 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L, bool vjp) {
     s.buf1 = p; p += (size_t)R * LD;
     s.u = p; p += R;
     s.gacc = vjp ? p : nullptr;
+    s.scratch = vjp ? p + (size_t)(L + 4) * HP : nullptr;
     return s;
 }
 
@@ -219,15 +221,35 @@ __device__ __forceinline__ void act_store(const T (&acc)[MB][NB][2], T* dst, int
 // u[r] = sum_j buf[r][j] * wl[j]  (rotated start => conflict-free)
 template <typename T>
 __device__ __forceinline__ void last_layer_dots(const T* buf, const T* wl, T* u) {
-    if (threadIdx.x < R) {
-        const int r = threadIdx.x;
-        T acc = (T)0;
+    // 4 threads per row, 16 columns each (rotated start => conflict-free), fixed-order quad reduction
+    const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
+    T acc = (T)0;
 #pragma unroll 8
-        for (int jj = 0; jj < HP; ++jj) {
-            const int j = (jj + r) & (HP - 1);
-            acc = fma(buf[(size_t)r * LD + j], wl[j], acc);
-        }
-        u[r] = acc;
+    for (int jj = 0; jj < HP / 4; ++jj) {
+        const int j = part * (HP / 4) + ((jj + r + 4 * part) & (HP / 4 - 1));
+        acc = fma(buf[(size_t)r * LD + j], wl[j], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) u[r] = acc;
+}
+
+// gout[j] += sum_{r < nrows} coef(r) * M[rowmap(r)][j] for j < HP, using all 512 threads: 8 row slices
+// summed in parallel into `scratch` [8][HP], then added in fixed order.  Contains its own barriers.
+template <typename T, typename RowMap, typename Coef>
+__device__ __forceinline__ void col_sums(T* scratch, T* gout, const T* M, int nrows, RowMap rowmap, Coef coef) {
+    const int j = threadIdx.x & (HP - 1), part = threadIdx.x >> 6;  // 512 threads = 8 parts x 64 columns
+    const int per = nrows >> 3;
+    T a = (T)0;
+    for (int r = part * per; r < (part + 1) * per; ++r) a = fma(coef(r), M[(size_t)rowmap(r) * LD + j], a);
+    __syncthreads();
+    scratch[part * HP + j] = a;
+    __syncthreads();
+    if (threadIdx.x < HP) {
+        T sacc = (T)0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sacc += scratch[k * HP + j];
+        gout[j] += sacc;
     }
 }
 
@@ -239,8 +261,11 @@ __device__ __forceinline__ void block_to_bg(const MlpParams& p, int blk, int& b,
 // =================================================================================================
 // forward: exc, vrho (, vgamma)
 // =================================================================================================
-template <typename T, int NS>
+// ACT >= 0: activation fixed at compile time (tanh, the reference default: keeps the 9-way switch and
+// its exp/log code out of the instruction stream); ACT < 0: run-time p.act.
+template <typename T, int NS, int ACT>
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpParams p) {
+    const int act = ACT >= 0 ? ACT : p.act;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem<T> s = carve<T>(smem_raw, p.L, false);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, qd = lane & 3;
@@ -291,7 +316,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpParams
             else
                 WarpGemm<T, MB, NB, false, false>::run(acc, cur + (size_t)row0 * LD, LD,
                                                        s.Wh + (size_t)(l - 1) * HP * LD + col0, LD, HP, g, qd);
-            act_store<T, NS>(acc, nxt, row0, col0, g, qd, p.act);
+            act_store<T, NS>(acc, nxt, row0, col0, g, qd, act);
             __syncthreads();
             T* t = cur;
             cur = nxt;
@@ -321,8 +346,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpParams
 // =================================================================================================
 // reverse: (exc_bar, vrho_bar[, vgamma_bar]) -> rho_bar, theta_bar partials
 // =================================================================================================
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams p) {
+    const int act = ACT >= 0 ? ACT : p.act;
     constexpr int NS = 2;
     constexpr int P = R / NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -335,7 +361,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
     T2* tape = reinterpret_cast<T2*>(p.tape) + (size_t)blockIdx.x * L * NW * MB * NB * 32;
 
     load_weights<T>(p, s);
-    for (int i = threadIdx.x; i < (L + 2) * HP; i += blockDim.x) s.gacc[i] = (T)0;
+    for (int i = threadIdx.x; i < (L + 4) * HP; i += blockDim.x) s.gacc[i] = (T)0;
     // weight-gradient accumulators: hidden layers 2..L as 16x16 warp tiles, layer 1 per thread
     T wacc[MAXL - 1][2][2][2];
 #pragma unroll
@@ -344,7 +370,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
         for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int c = 0; c < 2; ++c) wacc[l][a][c][0] = wacc[l][a][c][1] = (T)0;
-    T w1acc = (T)0;  // thread t < 2*HP owns dW1[f = t / HP][j = t % HP]
     __syncthreads();
 
     for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
@@ -394,7 +419,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
             for (int mi = 0; mi < MB; ++mi)
 #pragma unroll
                 for (int nj = 0; nj < NB; ++nj) tp[(mi * NB + nj) * 32] = Vec2<T>::make(acc[mi][nj][0], acc[mi][nj][1]);
-            act_store<T, NS>(acc, nxt, row0, col0, g, qd, p.act);
+            act_store<T, NS>(acc, nxt, row0, col0, g, qd, act);
             __syncthreads();
             T* t = cur;
             cur = nxt;
@@ -421,15 +446,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
             s.u[r1] = udb;
         }
         __syncthreads();
-        if (threadIdx.x < HP) {  // d wl[j], and d b_last on thread 0
-            const int j = threadIdx.x;
-            T a = (T)0, bsum = (T)0;
-            for (int r = 0; r < R; ++r) a = fma(s.u[r], cur[(size_t)r * LD + j], a);
-            s.gacc[(L + 1) * HP + j] += a;
-            if (j == 0) {
-                for (int pt = 0; pt < P; ++pt) bsum += s.u[row_of(pt, 0, NS)];
-                s.gacc[L * HP] += bsum;
-            }
+        // d wl[j] = sum_r u[r] h_L[r][j] (all rows, both streams); d b_last = sum of the value-row seeds
+        col_sums<T>(s.scratch, s.gacc + (L + 1) * HP, cur, R, [](int r) { return r; },
+                    [&](int r) { return s.u[r]; });
+        if (warp == 0) {
+            T bsum = s.u[row_of(lane, 0, NS)] + s.u[row_of(lane + 32, 0, NS)];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+            if (lane == 0) s.gacc[L * HP] += bsum;
         }
         // adjoint of the last hidden activations, directly in accumulator layout
 #pragma unroll
@@ -460,7 +484,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             T s0, s1, s2;
-                            act_d012<T>(p.act, zz[e], s0, s1, s2);
+                            act_d012<T>(act, zz[e], s0, s1, s2);
                             const T hb = acc[pg * NS][nj][e], hdb = acc[pg * NS + 1][nj][e];
                             d[e] = hb * s1 + hdb * s2 * zzd[e];  // z_bar
                             d[8 * LD + e] = hdb * s1;            // zdot_bar
@@ -476,16 +500,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
                             acc[mi][nj][0] = t2.x;
                             acc[mi][nj][1] = t2.y;
                         }
-                    act_store<T, NS>(acc, Bh, row0, col0, g, qd, p.act);
+                    act_store<T, NS>(acc, Bh, row0, col0, g, qd, act);
                 }
                 __syncthreads();
                 // bias gradient: column sums of z_bar over the value rows
-                if (threadIdx.x < HP) {
-                    const int j = threadIdx.x;
-                    T a = (T)0;
-                    for (int pt = 0; pt < P; ++pt) a += Bz[(size_t)row_of(pt, 0, NS) * LD + j];
-                    s.gacc[l * HP + j] += a;
-                }
+                col_sums<T>(s.scratch, s.gacc + l * HP, Bz, P, [](int r) { return row_of(r, 0, NS); },
+                            [](int) { return (T)1; });
                 if (l > 0) {
                     // dW_l (64x64) += [h; hdot]^T [z_bar; zdot_bar], warp tile 16 x 16
                     WarpGemm<T, 2, 2, true, false>::run(wacc[l - 1 < MAXL - 1 ? l - 1 : 0], Bh + wm * 16, LD,
@@ -499,26 +519,28 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
                                                           s.Wh + (size_t)(l - 1) * HP * LD + (size_t)col0 * LD, LD, HP, g, qd);
                 } else {
                     // dW_1 [F][H] and the input cotangent
-                    if (threadIdx.x < 2 * HP) {
-                        const int f = threadIdx.x / HP, j = threadIdx.x % HP;
-                        if (f < p.F) {
-                            T a = (T)0;
-                            for (int r = 0; r < R; ++r) a = fma(s.X0[(size_t)r * LDX + f], Bz[(size_t)r * LD + j], a);
-                            w1acc += a;
-                        }
-                    }
-                    if (threadIdx.x >= 256 && threadIdx.x < 256 + P) {
-                        const int pt = threadIdx.x - 256;
+                    for (int f = 0; f < p.F; ++f)
+                        col_sums<T>(s.scratch, s.gacc + (L + 2 + f) * HP, Bz, R, [](int r) { return r; },
+                                    [&](int r) { return s.X0[(size_t)r * LDX + f]; });
+                    if (threadIdx.x < 4 * P) {  // 4 threads per point, 16 columns each, quad reduction
+                        const int pt = threadIdx.x >> 2, part = threadIdx.x & 3;
                         const int r = row_of(pt, 0, NS);
                         T xb[2] = {(T)0, (T)0};
-                        for (int jj = 0; jj < HP; ++jj) {
-                            const int j = (jj + pt) & (HP - 1);
+                        for (int jj = 0; jj < HP / 4; ++jj) {
+                            const int j = part * (HP / 4) + ((jj + pt + 4 * part) & (HP / 4 - 1));
                             const T zb = Bz[(size_t)r * LD + j];
                             xb[0] = fma(zb, s.W1[j], xb[0]);
                             xb[1] = fma(zb, s.W1[LD + j], xb[1]);
                         }
-                        s.u[pt] = xb[0] * (T)p.in_scale;
-                        s.u[P + pt] = xb[1] * (T)p.in_scale;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            xb[e] += __shfl_xor_sync(0xffffffffu, xb[e], 1);
+                            xb[e] += __shfl_xor_sync(0xffffffffu, xb[e], 2);
+                        }
+                        if (part == 0) {
+                            s.u[pt] = xb[0] * (T)p.in_scale;
+                            s.u[P + pt] = xb[1] * (T)p.in_scale;
+                        }
                     }
                 }
                 __syncthreads();
@@ -546,9 +568,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
     // ---------------- per-CTA theta_bar partial ----------------
     double* out = p.theta_part + (size_t)blockIdx.x * p.n_theta;
     const int H = p.H, F = p.F;
+    __syncthreads();
     if (threadIdx.x < 2 * HP) {
         const int f = threadIdx.x / HP, j = threadIdx.x % HP;
-        if (f < F && j < H) out[(long)f * H + j] = (double)w1acc;
+        if (f < F && j < H) out[(long)f * H + j] = (double)s.gacc[(L + 2 + f) * HP + j];
     }
 #pragma unroll
     for (int l = 1; l < MAXL; ++l) {
@@ -659,8 +682,13 @@ int launch_mlp_local_fwd(qexxc_ctx* c, int xctype, const double* rho, long rho_b
 #define QX_FWD(T, NSV)                                                                      \
     do {                                                                                    \
         const size_t sm = smem_elems<T>(p.L, false) * sizeof(T);                            \
-        QX_TRY(set_smem_attr(mlp_fwd_kernel<T, NSV>, sm));                                  \
-        mlp_fwd_kernel<T, NSV><<<grid, MLP_THREADS, sm, st>>>(p);                           \
+        if (p.act == QEXXC_ACT_TANH) {                                                      \
+            QX_TRY(set_smem_attr(mlp_fwd_kernel<T, NSV, QEXXC_ACT_TANH>, sm));              \
+            mlp_fwd_kernel<T, NSV, QEXXC_ACT_TANH><<<grid, MLP_THREADS, sm, st>>>(p);       \
+        } else {                                                                            \
+            QX_TRY(set_smem_attr(mlp_fwd_kernel<T, NSV, -1>, sm));                          \
+            mlp_fwd_kernel<T, NSV, -1><<<grid, MLP_THREADS, sm, st>>>(p);                   \
+        }                                                                                   \
     } while (0)
     if (f32) {
         if (NS == 2) QX_FWD(float, 2);
@@ -701,15 +729,21 @@ int launch_mlp_local_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_b
     if (grid <= 0) return QEXXC_OK;
     const bool f32 = c->net.precision == QEXXC_PREC_F32;
     ProfScope prof(c, QEXXC_PROF_XC_VJP, st);
+#define QX_VJP(T, A)                                                                        \
+    do {                                                                                    \
+        const size_t sm = smem_elems<T>(p.L, true) * sizeof(T);                             \
+        QX_TRY(set_smem_attr(mlp_vjp_kernel<T, A>, sm));                                    \
+        mlp_vjp_kernel<T, A><<<grid, MLP_THREADS, sm, st>>>(p);                             \
+    } while (0)
+    const bool tanh_act = p.act == QEXXC_ACT_TANH;
     if (f32) {
-        const size_t sm = smem_elems<float>(p.L, true) * sizeof(float);
-        QX_TRY(set_smem_attr(mlp_vjp_kernel<float>, sm));
-        mlp_vjp_kernel<float><<<grid, MLP_THREADS, sm, st>>>(p);
+        if (tanh_act) QX_VJP(float, QEXXC_ACT_TANH);
+        else QX_VJP(float, -1);
     } else {
-        const size_t sm = smem_elems<double>(p.L, true) * sizeof(double);
-        QX_TRY(set_smem_attr(mlp_vjp_kernel<double>, sm));
-        mlp_vjp_kernel<double><<<grid, MLP_THREADS, sm, st>>>(p);
+        if (tanh_act) QX_VJP(double, QEXXC_ACT_TANH);
+        else QX_VJP(double, -1);
     }
+#undef QX_VJP
     QX_LAUNCH_CHECK(c);
     theta_reduce_kernel<<<(unsigned)((c->n_theta + 255) / 256), 256, 0, st>>>(c->red, grid, c->n_theta, theta_bar,
                                                                            accumulate_theta);
