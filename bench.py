@@ -38,10 +38,13 @@ def _args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c5", choices=["c5", "c5gga", "c3", "c2"])
+    ap.add_argument("--config", default="c5", choices=["c5", "c5gga", "c3", "c2", "c4"])
     ap.add_argument("--ngrids", type=int, default=None, help="override the grid size (debugging)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="network precision")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the whole step as one CUDA graph (auto: single GPU and <= 200k grid points, where the "
+                         "step is launch-latency bound)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample duration")
     return ap.parse_args()
 
@@ -122,8 +125,18 @@ def cpu_step_time(wl, sample, repeats=1):
     from oracle import step_ref
 
     m = wl.mol
-    c, w = wl.coords[:sample], wl.weights[:sample]
     best = float("inf")
+    if "batch" in wl.extra:  # c4: `sample` counts grid points over whole molecules
+        nmol = max(1, min(wl.extra["batch"], sample // wl.ngrids))
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            for b in range(nmol):
+                mb = wl.extra["mols"][b]
+                step_ref.xc_step(mb._atm, mb._bas, mb._env, wl.coords[b], wl.weights[b], wl.dm[b], wl.net, wl.theta,
+                                 wl.xctype, wl.e_bar, wl.v_bar)
+            best = min(best, time.perf_counter() - t0)
+        return best
+    c, w = wl.coords[:sample], wl.weights[:sample]
     for _ in range(repeats):
         t0 = time.perf_counter()
         step_ref.xc_step(m._atm, m._bas, m._env, c, w, wl.dm, wl.net, wl.theta, wl.xctype, wl.e_bar, wl.v_bar)
@@ -133,7 +146,7 @@ def cpu_step_time(wl, sample, repeats=1):
 
 def cpu_baseline(wl, target_s):
     """Bounded sample of the same workload (about `target_s` seconds of CPU work)."""
-    G = wl.ngrids
+    G = wl.ngrids * (wl.extra.get("batch") or 1)
     s0 = min(G, 2048)
     t0 = cpu_step_time(wl, s0)  # calibration (also warms BLAS threads)
     sample = int(min(G, max(s0, s0 * target_s / max(t0, 1e-6) / 2)))
@@ -154,7 +167,7 @@ def run_reference(args):
     from qex_b200 import workloads
 
     wl = workloads.make(args.config, ngrids=args.ngrids)
-    G = wl.ngrids
+    G = wl.ngrids * (wl.extra.get("batch") or 1)
     s0 = min(G, 2048)
     t0 = cpu_step_time(wl, s0)
     budget = 120.0 / max(1, args.steps + args.warmup)  # whole run within a few minutes
@@ -233,25 +246,41 @@ def run_ours(args):
 
     wl = workloads.make(args.config, ngrids=args.ngrids)
     N, G = wl.nao, wl.ngrids
-    # contiguous grid shard of this rank (fixed map rank -> point range)
-    per = (G + world - 1) // world
-    lo, hi = min(G, rank * per), min(G, (rank + 1) * per)
-    Gl = hi - lo
+    batch = wl.extra.get("batch")
     net = workloads.net_spec(wl, args.precision)
-    ctx = XCContext(nao=N, ngrids_max=max(Gl, 1), ncomp=wl.ncomp, nbatch=1, net=net, device=local)
-    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env)
     deriv = 1 if wl.ncomp == 4 else 0
+    if batch:
+        # c4: molecules are sharded round-robin (replicas); only theta_bar crosses ranks
+        from qex_b200.dist import shard_batch
+
+        ids = shard_batch(batch, rank, world)
+        Bl, Gl, lo, hi = len(ids), G, 0, G
+        ctx = XCContext(nao=N, ngrids_max=G, ncomp=wl.ncomp, nbatch=Bl, net=net, device=local)
+        ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.extra["envs"][ids])
+        npts_total = batch * G
+    else:
+        # contiguous grid shard of this rank (fixed map rank -> point range)
+        per = (G + world - 1) // world
+        lo, hi = min(G, rank * per), min(G, (rank + 1) * per)
+        Bl, Gl = 1, hi - lo
+        ctx = XCContext(nao=N, ngrids_max=max(Gl, 1), ncomp=wl.ncomp, nbatch=1, net=net, device=local)
+        ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env)
+        npts_total = G
 
     # pinned host copies of every per-call input, and device-resident copies
     def pin(x):
         return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).pin_memory()
 
-    h_coords, h_w = pin(wl.coords[lo:hi]), pin(wl.weights[lo:hi])
-    h_dm, h_th = pin(wl.dm), pin(wl.theta)
-    h_eb, h_vb = pin(np.array([wl.e_bar])), pin(wl.v_bar)
+    if batch:
+        h_coords, h_w, h_dm = pin(wl.coords[ids]), pin(wl.weights[ids]), pin(wl.dm[ids])
+        h_eb, h_vb = pin(np.full(Bl, wl.e_bar)), pin(np.broadcast_to(wl.v_bar, (Bl, N, N)))
+    else:
+        h_coords, h_w, h_dm = pin(wl.coords[lo:hi]), pin(wl.weights[lo:hi]), pin(wl.dm)
+        h_eb, h_vb = pin(np.array([wl.e_bar])), pin(wl.v_bar)
+    h_th = pin(wl.theta)
     d_coords, d_w, d_dm, d_th, d_eb, d_vb = (t.cuda() for t in (h_coords, h_w, h_dm, h_th, h_eb, h_vb))
-    out = ctx.empty(1, N * N + 2)
-    bar = ctx.empty(N * N + wl.theta.size)
+    out = ctx.empty(Bl, N * N + 2)
+    bar = ctx.empty(Bl * N * N + wl.theta.size)
     resid = ctx.empty(ctx.resid_doubles)
     h_out, h_bar = torch.empty_like(out, device="cpu").pin_memory(), torch.empty_like(bar, device="cpu").pin_memory()
 
@@ -259,11 +288,27 @@ def run_ours(args):
         ctx.set_grid(d_coords, d_w)
         ctx.eval_ao(deriv)
         ctx.nr_rks_fwd(d_dm, d_th, wl.xctype, 0, out=out, resid=resid)
-        if world > 1:
+        if world > 1 and not batch:
             dist.all_reduce(out)
         ctx.nr_rks_vjp(d_th, resid, d_eb, d_vb, wl.xctype, 0, out=bar)
         if world > 1:
-            dist.all_reduce(bar)
+            dist.all_reduce(bar[Bl * N * N:] if batch else bar)
+
+    # Launch-latency-bound sizes (H2, water): capture the ~16 launches of a step into one CUDA graph.
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1 and npts_total <= 200_000)
+    graph = None
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step()  # warm-up: schedules uploaded, attributes set, nothing left to allocate
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+    run_step = graph.replay if graph is not None else step
 
     def step_e2e():
         # host buffers in, host buffers out: what a caller of the drop-in nr_rks pays per call
@@ -273,7 +318,7 @@ def run_ours(args):
         d_th.copy_(h_th, non_blocking=True)
         d_eb.copy_(h_eb, non_blocking=True)
         d_vb.copy_(h_vb, non_blocking=True)
-        step()
+        run_step()
         h_out.copy_(out, non_blocking=True)
         h_bar.copy_(bar, non_blocking=True)
         torch.cuda.synchronize()
@@ -300,22 +345,35 @@ def run_ours(args):
     if rank == 0:
         peak_burst, peak_sus = measure_dgemm_peak(torch)
     for _ in range(max(3, args.warmup)):
-        step()
+        run_step()
     barrier()
 
     # ---- timed region: value ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ctx.profile_enable(True)
-    l0 = ctx.launch_count
-    ms_total = timed(step, args.steps)
-    launches = ctx.launch_count - l0
-    prof = ctx.profile_read()
-    ctx.profile_enable(False)
+    if graph is None:
+        ctx.profile_enable(True)
+        l0 = ctx.launch_count
+        ms_total = timed(step, args.steps)
+        launches = ctx.launch_count - l0
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+        prof_total = ms_total
+    else:
+        ms_total = timed(run_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    if graph is not None:
+        # per-kernel events cannot be recorded inside a replayed graph: take the kernel table (and the
+        # launch count) from a separate un-graphed pass of the same K steps
+        ctx.profile_enable(True)
+        l0 = ctx.launch_count
+        prof_total = timed(step, args.steps)
+        launches = ctx.launch_count - l0
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
     ms_step = ms_total / args.steps
-    value = G / (ms_step * 1e-3)
+    value = npts_total / (ms_step * 1e-3)
 
     # ---- extra: the same step with the MO form of rho (dm tagged with mo_coeff/mo_occ takes pyscf's
     # eval_rho2 branch, numint_legacy.py:527-545).  Reported separately; the headline stays dense-dm. ----
@@ -347,7 +405,7 @@ def run_ours(args):
     if rank == 0:
         # dominant kernel: the FP64 DMMA contractions (2 rowquad + 2 wsyrk launches per step,
         # 2*G*N^2 algorithmic FLOP each -> 8*N^2 FLOP per grid point per step)
-        fl = 2.0 * Gl * N * N
+        fl = 2.0 * Gl * Bl * N * N
         # executed DMMA FLOPs per launch (zero-padded tiles, symmetric operands skipped):
         # (counted by the library with the same predicates the kernels use)
         tri = wl.ncomp == 1
@@ -356,7 +414,7 @@ def run_ours(args):
         for name in ("rowquad", "wsyrk", "xc_fwd", "xc_vjp", "eval_ao"):
             ms, n = prof[name]
             kern[name] = {"launches": n, "avg_ms": (ms / n) if n else None,
-                          "share_of_step": ms / ms_total if ms_total else None}
+                          "share_of_step": ms / prof_total if prof_total else None}
             if name in ex and n:
                 kern[name]["algorithmic_tflops"] = fl / (ms / n * 1e-3) / 1e12
                 kern[name]["executed_tflops"] = ex[name] / (ms / n * 1e-3) / 1e12
@@ -387,14 +445,18 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": wl.describe, "nao": N, "ngrids": G, "ngrids_per_gpu": Gl, "ncomp": wl.ncomp,
-                       "network_precision": args.precision, "parallelism": f"grid-sharded x{world}, NCCL all-reduce of packed V_xc|E_xc|nelec and dm_bar|theta_bar",
+                       "batch": batch, "grid_points_per_step": npts_total,
+                       "network_precision": args.precision, "parallelism": (f"molecules sharded round-robin x{world} (replicas), NCCL all-reduce of theta_bar only" if batch else
+                                       f"grid-sharded x{world}, NCCL all-reduce of packed V_xc|E_xc|nelec and dm_bar|theta_bar"),
                        "l2": "inputs larger than L2 (AO tensor %.1f GB per pass)" % (Gl * ctx_npad(N) * 8 * wl.ncomp / 1e9),
-                       "step": "set_grid + eval_ao (K1) + nr_rks fwd + nr_rks VJP"},
+                       "step": "set_grid + eval_ao (K1) + nr_rks fwd + nr_rks VJP",
+                       "launch": "one CUDA graph replay per step (kernel table from an un-graphed pass)" if graph is not None
+                       else "stream launches"},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": G / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": npts_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "mo_path": None if mo_ms is None else {
-                "value": G / (mo_ms * 1e-3), "unit": UNIT, "ms_per_step": mo_ms,
+                "value": npts_total / (mo_ms * 1e-3), "unit": UNIT, "ms_per_step": mo_ms,
                 "note": "same step with stage 2 in its MO form rho = sum_k occ_k (ao C_k)^2 (150 occupied orbitals), the "
                         "branch the reference takes when dm carries mo_coeff/mo_occ (numint_legacy.py:527-545); not the headline"},
             "gpu_launches": int(launches), "clocks": clocks, "hbm_peak_gbs": hbm,

@@ -31,11 +31,11 @@ class Workload:
 
     @property
     def nao(self):
-        return self.dm.shape[0]
+        return self.dm.shape[-1]
 
     @property
     def ngrids(self):
-        return self.weights.shape[0]
+        return self.weights.shape[-1]
 
 
 def _mlp_theta(sizes, seed=0):
@@ -113,6 +113,27 @@ def make(config: str = "c5", ngrids: int | None = None, seed: int = 0) -> Worklo
             mol=mol, coords=grid.coords, weights=grid.weights, dm=2.0 * c @ c.T, xctype="NN", ncomp=1,
             net=dict(kind="local_qnn", n_features=1, n_hidden=2, width=6, in_scale=1.0),
             theta=rng.uniform(-0.1, 0.1, 36), e_bar=e_bar, v_bar=v_bar)
+    if config == "c4":
+        # batched H2 dissociation curve: 64 bond lengths, LocalMLP, one XC step of every molecule's SCF
+        # iteration in ONE batched launch per stage (configs[3]; the SCF driver itself is out of scope)
+        nb = ngrids or 64  # `ngrids` doubles as the batch-size override for this config
+        bonds = np.linspace(0.4, 3.0, nb)
+        mols = [gto.h2(float(b), "6-31g") for b in bonds]
+        grids = [gen_grid.Grids(m, n_rad=31, n_theta=5, n_phi=4).build() for m in mols]
+        N = 4
+        rng = np.random.default_rng(seed)
+        cs = rng.standard_normal((nb, N)) * 0.4
+        dms = np.stack([2.0 * np.outer(c, c) for c in cs])
+        e_bar, v_bar = _cotangents(N, seed + 3)
+        wl = Workload(
+            name="c4", describe=f"batched H2 dissociation curve: {nb} bond lengths x ({N} AOs x {grids[0].size} grid "
+            "points), LocalMLP rho->64->64->64->1, one XC step (fwd+VJP) of all molecules per launch",
+            mol=mols[0], coords=np.stack([g.coords for g in grids]), weights=np.stack([g.weights for g in grids]),
+            dm=dms, xctype="NN", ncomp=1,
+            net=dict(kind="local_mlp", n_features=1, n_hidden=3, width=64, activation="tanh"),
+            theta=_mlp_theta([1, 64, 64, 64, 1], seed), e_bar=e_bar, v_bar=v_bar,
+            extra=dict(batch=nb, envs=np.stack([m._env for m in mols]), mols=mols))
+        return wl
     raise ValueError(f"unknown workload {config!r}")
 
 
