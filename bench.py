@@ -38,7 +38,7 @@ def _args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c5", choices=["c5", "c5gga", "c3", "c2", "c4"])
+    ap.add_argument("--config", default="c5", choices=["c5", "c5gga", "c3", "c2", "c4", "c1"])
     ap.add_argument("--ngrids", type=int, default=None, help="override the grid size (debugging)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="network precision")
     ap.add_argument("--no-cpu-baseline", action="store_true")

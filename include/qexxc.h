@@ -203,6 +203,24 @@ int qexxc_contraction_flops(qexxc_ctx* ctx, int which, int symmetric, double* ex
  * which = 0 rowquad (rho-type), 1 wsyrk (vmat-type). */
 int qexxc_debug_run_contraction(qexxc_ctx* ctx, int which, void* stream);
 
+/* ---- "next" row N2: incore Coulomb / exchange build on the dense s1 ERI tensor --------
+ * Replaces the two einsums of `_dot_eri_dm_s1` (qedft/train/td/hf_legacy.py:275-286; called from
+ * `SCF.get_jk` :452-470 -> `get_veff` rks_legacy.py:91-117):
+ *     vj[x,k,l] = sum_ij eri[i,j,k,l] dm[x,j,i]      vk[x,i,l] = sum_jk eri[i,j,k,l] dm[x,j,k]
+ * All pointers are DEVICE pointers (the 8*nao^4-byte tensor stays resident in HBM across SCF cycles);
+ * eri is [nao]^4 row-major, dm / vj / vk are [nset][nao][nao].  One pass over the tensor produces J and K.
+ * `work` needs qexxc_jk_workspace_doubles doubles.  These calls are context-free (no grid involved). */
+int qexxc_jk_workspace_doubles(int device, int nao, long* out);
+int qexxc_dot_eri_dm(int device, const double* eri_dev, const double* dm_dev, int nset, int nao, int with_j,
+                     int with_k, double* vj_dev, double* vk_dev, double* work_dev, long work_doubles, void* stream);
+/* Reverse mode of the call above w.r.t. dm (what jax.vjp of the einsums gives; the ERI tensor is not a
+ * parameter): dm_bar[x,j,i] = sum_kl eri[i,j,k,l] vj_bar[x,k,l] + sum_{i',l} eri[i',j,i,l] vk_bar[x,i',l].
+ * Either cotangent may be NULL (= zero). No permutational symmetry of eri is assumed. */
+int qexxc_dot_eri_dm_vjp(int device, const double* eri_dev, const double* vj_bar_dev, const double* vk_bar_dev,
+                         int nset, int nao, double* dm_bar_dev, double* work_dev, long work_doubles, void* stream);
+/* kernels launched by the three J/K calls since the library was loaded */
+long qexxc_jk_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

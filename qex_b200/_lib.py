@@ -28,6 +28,7 @@ EXPORTS = [
     "qexxc_apply_fn_fwd", "qexxc_apply_fn_vjp", "qexxc_vxc_assemble", "qexxc_vxc_assemble_vjp",
     "qexxc_resid_doubles", "qexxc_nr_rks_fwd", "qexxc_nr_rks_vjp", "qexxc_launch_count",
     "qexxc_debug_run_contraction", "qexxc_profile_enable", "qexxc_profile_read", "qexxc_contraction_flops", "qexxc_eval_rho_mo", "qexxc_nr_rks_fwd_mo",
+    "qexxc_jk_workspace_doubles", "qexxc_dot_eri_dm", "qexxc_dot_eri_dm_vjp", "qexxc_jk_launch_count",
 ]
 
 
@@ -95,6 +96,10 @@ def load(build_if_missing: bool = False):
         "qexxc_nr_rks_fwd_mo": (i, [vp, i, p, p, i, p, p, p, vp]),
         "qexxc_contraction_flops": (i, [vp, i, i, C.POINTER(C.c_double)]),
         "qexxc_profile_read": (i, [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
+        "qexxc_jk_workspace_doubles": (i, [i, i, C.POINTER(C.c_long)]),
+        "qexxc_dot_eri_dm": (i, [i, p, p, i, i, i, i, p, p, p, l, vp]),
+        "qexxc_dot_eri_dm_vjp": (i, [i, p, p, p, i, i, p, p, l, vp]),
+        "qexxc_jk_launch_count": (l, []),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -67,7 +67,7 @@ def _cotangents(N, seed):
 
 
 def make(config: str = "c5", ngrids: int | None = None, seed: int = 0) -> Workload:
-    """config in {"c2", "c3", "c5", "c5gga"}; `ngrids` overrides the grid size (tests, CPU samples)."""
+    """config in {"c1", "c2", "c3", "c4", "c5", "c5gga"}; `ngrids` overrides the grid size (tests, CPU samples)."""
     if config == "c5" or config == "c5gga":
         # ~1000 AOs x 1M grid points, LocalMLP (BASELINE.json configs[4])
         mol = gto.synthetic_molecule(50, (4, 2, 2), seed=seed)  # 50 atoms x (4s 2p 2d = 20 AOs) = 1000
@@ -113,6 +113,24 @@ def make(config: str = "c5", ngrids: int | None = None, seed: int = 0) -> Worklo
             mol=mol, coords=grid.coords, weights=grid.weights, dm=2.0 * c @ c.T, xctype="NN", ncomp=1,
             net=dict(kind="local_qnn", n_features=1, n_hidden=2, width=6, in_scale=1.0),
             theta=rng.uniform(-0.1, 0.1, 36), e_bar=e_bar, v_bar=v_bar)
+    if config == "c1":
+        # README 3D H2 example: GlobalMLP (G->64->64->64->1, networks.py:132-138), bond lengths 0.74/0.5/1.5,
+        # batch 3, "NN-AmplitudeEncoding" branch (configs[0])
+        bonds = [0.74, 0.5, 1.5]
+        mols = [gto.h2(b, "6-31g") for b in bonds]
+        grids = [gen_grid.Grids(m, n_rad=31, n_theta=5, n_phi=4).build() for m in mols]
+        N, G = 4, grids[0].size
+        rng = np.random.default_rng(seed)
+        cs = rng.standard_normal((3, N)) * 0.4
+        e_bar, v_bar = _cotangents(N, seed + 3)
+        return Workload(
+            name="c1", describe=f"README 3D H2 example: GlobalMLP {G}->64->64->64->1, {N} AOs x {G} grid points, "
+            "bond lengths 0.74/0.5/1.5, batch 3, NN-AmplitudeEncoding, fwd+VJP",
+            mol=mols[0], coords=np.stack([g.coords for g in grids]), weights=np.stack([g.weights for g in grids]),
+            dm=np.stack([2.0 * np.outer(c, c) for c in cs]), xctype="NN-AmplitudeEncoding", ncomp=1,
+            net=dict(kind="global_mlp", n_hidden=3, width=64, activation="tanh"),
+            theta=_mlp_theta([G, 64, 64, 64, 1], seed), e_bar=e_bar, v_bar=v_bar,
+            extra=dict(batch=3, envs=np.stack([m._env for m in mols]), mols=mols))
     if config == "c4":
         # batched H2 dissociation curve: 64 bond lengths, LocalMLP, one XC step of every molecule's SCF
         # iteration in ONE batched launch per stage (configs[3]; the SCF driver itself is out of scope)

@@ -27,6 +27,8 @@ def test_synthetic_molecules_have_the_named_sizes():
     assert wl.nao == 4 and wl.ngrids == 1240 and wl.theta.size == 36
     wl = workloads.make("c3", ngrids=256)
     assert wl.nao == 120 and wl.ncomp == 4 and wl.xctype == "GGA"
+    wl = workloads.make("c1")
+    assert wl.dm.shape == (3, 4, 4) and wl.xctype == "NN-AmplitudeEncoding" and wl.theta.size == 1240 * 64 + 64 + 2 * (64 * 64 + 64) + 65
 
 
 def test_grid_integrates_a_gaussian():
