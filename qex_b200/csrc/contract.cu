@@ -493,34 +493,53 @@ wsyrk_kernel(const double* __restrict__ ao0, const double* __restrict__ Bsrc,
     }
 }
 
-// out[i][j] = scale * (H[i][j] + (tadd ? H[j][i] : 0)), H = sum over grid chunks (fixed order) of the
-// partial tiles.  With sym != 0 only 8x8 blocks on or above the diagonal were computed (H symmetric).
-__global__ void wsyrk_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, int N, int BN,
-                                    int NT, int nchunk, int ntile, int sym, double scale, int tadd,
-                                    long out_bstride) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// out[i][j] = scale * (H[i][j] + (tadd ? H[j][i] : 0)), H = sum over grid chunks of the partial tiles.
+// With sym != 0 only 8x8 blocks on or above the diagonal were computed (H symmetric).  A block is
+// 32 columns x RK chunk groups: group kg adds chunks kg, kg+RK, ... and the RK sub-sums are combined
+// through shared memory in a fixed order (bit-reproducible, and the dependent-load chain is RK x shorter).
+constexpr int RK = 8;
+__global__ void __launch_bounds__(32 * RK)
+wsyrk_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, int N, int BN, int NT, int nchunk,
+                    int ntile, int sym, double scale, int tadd, long out_bstride) {
+    __shared__ double red[2][RK][32];
+    const int lane = threadIdx.x & 31, kg = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
     const int i = blockIdx.y;
     const int b = blockIdx.z;
-    if (j >= N) return;
     const long tsz = (long)BN * BN;
     auto H = [&](int r, int c) {
         const int tr = r / BN, tc = c / BN;
         const int tile = sym ? tr * NT - tr * (tr - 1) / 2 + (tc - tr) : tr * NT + tc;
         const double* P = part + ((long)(b * ntile + tile) * nchunk) * tsz + (long)(r - tr * BN) * BN + (c - tc * BN);
         double h = 0.0;
-        for (int k = 0; k < nchunk; ++k) h += P[(long)k * tsz];
+        for (int k = kg; k < nchunk; k += RK) h += P[(long)k * tsz];
         return h;
     };
-    double v;
-    if (sym) {
-        const bool up = (j >> 3) >= (i >> 3), lo = (i >> 3) >= (j >> 3);
-        const double hij = up ? H(i, j) : H(j, i);
-        const double hji = lo ? H(j, i) : hij;
-        v = tadd ? hij + hji : hij;
-    } else {
-        v = tadd ? H(i, j) + H(j, i) : H(i, j);
+    double h0 = 0.0, h1 = 0.0;  // sub-sums of H(i,j) [or its mirror] and of the transposed term
+    bool same = false;           // transposed term equals the first one (symmetric, mirrored block)
+    if (j < N) {
+        if (sym) {
+            const bool up = (j >> 3) >= (i >> 3), lo = (i >> 3) >= (j >> 3);
+            h0 = up ? H(i, j) : H(j, i);
+            same = !lo;
+            if (tadd && lo) h1 = H(j, i);
+        } else {
+            h0 = H(i, j);
+            if (tadd) h1 = H(j, i);
+        }
     }
-    out[(long)b * out_bstride + (long)i * N + j] = scale * v;
+    red[0][kg][lane] = h0;
+    red[1][kg][lane] = h1;
+    __syncthreads();
+    if (kg != 0 || j >= N) return;
+    double a = 0.0, t = 0.0;
+#pragma unroll
+    for (int k = 0; k < RK; ++k) {
+        a += red[0][k][lane];
+        t += red[1][k][lane];
+    }
+    if (same) t = a;
+    out[(long)b * out_bstride + (long)i * N + j] = scale * (tadd ? a + t : a);
 }
 
 // S[b][i][j] (Npad x Npad, zero padded) from src[b][N][N]: mode 0 (a+a^T)/2, 1 a, 2 a+a^T.
@@ -874,8 +893,8 @@ int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bs
     }
 #undef QX_WS
     QX_LAUNCH_CHECK(c);
-    dim3 rgrid((c->N + 127) / 128, c->N, c->B);
-    wsyrk_reduce_kernel<<<rgrid, 128, 0, st>>>(c->part, out, c->N, plan.BN, plan.NT, plan.nchunk, plan.ntile,
+    dim3 rgrid((c->N + 31) / 32, c->N, c->B);
+    wsyrk_reduce_kernel<<<rgrid, 32 * RK, 0, st>>>(c->part, out, c->N, plan.BN, plan.NT, plan.nchunk, plan.ntile,
                                               sym ? 1 : 0, scale, tadd, out_bstride);
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;

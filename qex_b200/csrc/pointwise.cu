@@ -57,17 +57,23 @@ stage4_fwd_kernel(int xctype, const double* __restrict__ rho, const double* __re
     }
 }
 
-// sums[b] = (excsum, nelec): serial over the per-block partials (fixed order)
+// sums[b] = (excsum, nelec): one warp per molecule, lane-strided partial sums then a shuffle tree
+// (a fixed order, so the result is bit-reproducible)
 __global__ void stage4_final_kernel(int xctype, const double* __restrict__ part, int nblocks,
                                     const double* __restrict__ exc, long ld, double* __restrict__ sums,
                                     long sums_bstride) {
-    const int b = blockIdx.x;
-    if (threadIdx.x != 0) return;
+    const int b = blockIdx.x, lane = threadIdx.x;
     double te = 0.0, tn = 0.0;
-    for (int k = 0; k < nblocks; ++k) {
+    for (int k = lane; k < nblocks; k += 32) {
         te += part[((long)b * nblocks + k) * 2 + 0];
         tn += part[((long)b * nblocks + k) * 2 + 1];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        te += __shfl_xor_sync(0xffffffffu, te, o);
+        tn += __shfl_xor_sync(0xffffffffu, tn, o);
+    }
+    if (lane != 0) return;
     if (xctype == QEXXC_XC_NN_GLOBAL) te = exc[(long)b * ld];
     sums[(long)b * sums_bstride + 0] = te;
     sums[(long)b * sums_bstride + 1] = tn;
