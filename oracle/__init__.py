@@ -22,6 +22,13 @@ no golden vectors for this path.  What *is* pinned:
   gate matrices are the published horqrux 0.9.2 definitions -> circuit outputs
   "parity unpinned";
 * AO evaluation (``gto_ref``): restates pyscf 2.9 ``GTOval_sph_deriv0/1`` (third-party C,
-  absent from /root/reference); pinned only by orthonormality (numerical overlap
-  integrals = identity for normalised shells) -> "parity unpinned".
+  absent from /root/reference); pinned by orthonormality (numerical overlap integrals =
+  identity for normalised shells) and, for the H2/6-31G s shells, by agreement of the grid
+  overlap with the closed-form overlap of ``ints_ref`` (itself pinned below) -> values of
+  general shells "parity unpinned";
+* J/K contraction, generalised eigensolver, DIIS, SCF loop, 6-31G tables and s-type integrals
+  (``jk_ref``, ``scf_ref``, ``ints_ref``, ``qex_b200/gto.py``): PINNED TOGETHER by six converged RHF
+  energies of H2/6-31G that the reference's own notebook prints
+  (notebooks/04_notebook_td_trainer.ipynb cells 1 and 5: 0.74/0.5/1.5/0.6/0.9/1.2 Angstrom),
+  reproduced to < 1e-12 Ha by the oracle and to < 1e-10 Ha by the CUDA path (tests/test_scf.py).
 """

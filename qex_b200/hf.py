@@ -125,6 +125,26 @@ def dot_eri_dm_autograd(eri, dm, with_j=True, with_k=True):
     return (vj if with_j else None), (vk if with_k else None)
 
 
+class _RowDot(torch.autograd.Function):
+    """J[i,j] = sum_kl eri[i,j,k,l] dm[k,l] (the `einsum("ijkl,kl->ij")` of scf_functions_masked.py:152):
+    forward is the J-bar half of the reverse kernel read back transposed, backward is the forward kernel."""
+
+    @staticmethod
+    def forward(ctx, eri, dm):
+        ctx.eri = eri
+        nao = int(dm.shape[-1])
+        return _dot_eri_dm_s1_vjp(eri, nao, dm.contiguous(), None).transpose(-1, -2).contiguous()
+
+    @staticmethod
+    def backward(ctx, j_bar):
+        vj, _ = _dot_eri_dm_s1(ctx.eri, j_bar.transpose(-1, -2).contiguous(), True, False)
+        return None, vj
+
+
+def dot_eri_dm_rowdot(eri, dm):
+    return _RowDot.apply(eri, dm)
+
+
 def make_rdm1(mo_coeff, mo_occ):
     """hf_legacy.py:331-338: dm = (C_occ * occ) C_occ^T over orbitals with occ > 0."""
     c = torch.as_tensor(mo_coeff, dtype=torch.float64)

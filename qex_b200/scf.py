@@ -1,0 +1,194 @@
+"""GPU-resident fixed-shape SCF iteration around the hot path.
+
+Host mirror (torch, float64, everything stays on the device) of the reference's jit-shaped prototype:
+    scf_functions_masked.py:143-193   get_veff_jax / energy_tot_jax / get_occ / make_rdm1
+    scf_functions_masked.py:856-904   _scf_test_non_padded  (the loop; `scf_loop` here)
+    jax_diis.py:17-132                initialize_diis / update_diis_state / extrapolate_fock / apply_diis
+    generalized_eigensolver.py:264-330  generalized_eigh      (Cholesky + two triangular solves + eigh)
+    generalized_eigensolver.py:143-219  degen_eigh + degen_eigh_bwd (degenerate-safe cotangent)
+    hf_legacy.py get_veff / energy_elec  (`rhf_loop`: vj - vk/2)
+
+What runs where: the two heavy pieces of every cycle are this repo's CUDA kernels --
+V_xc/E_xc through `autograd.nr_rks` (csrc/contract.cu, xc_*.cu) and J/K through `hf`
+(csrc/jk.cu); the N x N linear algebra (Cholesky, triangular solves, eigh, the DIIS solve) is
+library code (torch.linalg -> cuSOLVER/cuBLAS), exactly the role jnp.linalg plays in the reference.
+The loop is differentiable end to end with torch.autograd (d e_tot / d theta through all cycles),
+which is what the reference's trainer does with jax.grad.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import autograd as _ag
+from . import hf
+
+
+# ---------------------------------------------------------------- DIIS (jax_diis.py)
+def initialize_diis(max_vec: int = 6) -> dict:
+    return dict(error_vecs=[], fock_vecs=[], B=None, iteration=0, max_vec=max_vec)
+
+
+def get_diis_error(fock, dm, ovlp):
+    return fock @ (dm @ ovlp) - ovlp @ (dm @ fock)
+
+
+def update_diis_state(state: dict, error_vec, fock, max_vec: int = 6) -> dict:
+    ev = list(state["error_vecs"]) + [error_vec.reshape(-1)]
+    fv = list(state["fock_vecs"]) + [fock.reshape(-1)]
+    if len(ev) > max_vec:
+        ev, fv = ev[-max_vec:], fv[-max_vec:]
+    n = len(ev)
+    E = torch.stack(ev)
+    B = torch.zeros(n + 1, n + 1, dtype=fock.dtype, device=fock.device)
+    B[0, 1:] = -1.0  # "The -1 is critical here" (jax_diis.py:48)
+    B[1:, 0] = -1.0
+    B[1:, 1:] = E @ E.T
+    return dict(error_vecs=ev, fock_vecs=fv, B=B, iteration=state["iteration"] + 1, max_vec=max_vec)
+
+
+def extrapolate_fock(state: dict, fock_shape, min_vecs: int = 2, damping: float = 0.0):
+    n = len(state["fock_vecs"])
+    if n < min_vecs:
+        if n > 0:
+            return state["fock_vecs"][-1].reshape(fock_shape)
+        raise ValueError("no Fock matrix stored yet")
+    B = state["B"]
+    rhs = torch.zeros(n + 1, dtype=B.dtype, device=B.device)
+    rhs[0] = -1.0
+    B_reg = B + 1e-14 * torch.eye(n + 1, dtype=B.dtype, device=B.device)
+    c = torch.linalg.solve(B_reg, rhs)
+    f = (c[1:, None] * torch.stack(state["fock_vecs"])).sum(0)
+    if damping > 0.0:
+        f = (1.0 - damping) * f + damping * state["fock_vecs"][-1]
+    return f.reshape(fock_shape)
+
+
+def apply_diis(state: dict, fock, dm, ovlp, max_vec: int = 6, min_vecs: int = 2, damping: float = 0.0):
+    new = update_diis_state(state, get_diis_error(fock, dm, ovlp), fock, max_vec)
+    return extrapolate_fock(new, fock.shape, min_vecs, damping), new
+
+
+# ---------------------------------------------------------------- eigensolver (row N3)
+class _DegenEigh(torch.autograd.Function):
+    """`degen_eigh` with the reference's custom cotangent: 1/(l_j - l_i) is dropped (set to 0) for
+    |l_j - l_i| < eps**0.6, eigenvalue term V diag(g) V^T, result symmetrised."""
+
+    @staticmethod
+    def forward(ctx, A):
+        w, V = torch.linalg.eigh(A)
+        ctx.save_for_backward(w, V)
+        return w, V
+
+    @staticmethod
+    def backward(ctx, gw, gV):
+        w, V = ctx.saved_tensors
+        Vt = V.transpose(-1, -2)
+        res = torch.zeros_like(V)
+        if gV is not None:
+            thr = torch.finfo(w.dtype).eps ** 0.6
+            F = w.unsqueeze(-2) - w.unsqueeze(-1)
+            near = F.abs() < thr
+            Finv = torch.where(near, torch.zeros_like(F), 1.0 / torch.where(near, torch.ones_like(F), F))
+            res = V @ ((Finv * (Vt @ gV)) @ Vt)
+        if gw is not None:
+            res = res + V @ (gw.unsqueeze(-1) * Vt)
+        return (res + res.transpose(-1, -2)) * 0.5
+
+
+def degen_eigh(A):
+    return _DegenEigh.apply(A)
+
+
+def generalized_eigh(A, B, eps: float = 1.0e-12, scale: bool = False, degenerate_safe: bool = True):
+    """A v = w B v for symmetric A and SPD B (generalized_eigensolver.py:264-330).  `degenerate_safe`
+    routes the inner eigh through `degen_eigh` (the rule the reference's masked solver uses)."""
+    A = (A + A.transpose(-1, -2)) * 0.5
+    B = (B + B.transpose(-1, -2)) * 0.5
+    if scale:
+        s_inv = 1.0 / torch.sqrt(torch.diagonal(B, dim1=-2, dim2=-1))
+        A = (s_inv.unsqueeze(-1) * A) * s_inv.unsqueeze(-2)
+        B = (s_inv.unsqueeze(-1) * B) * s_inv.unsqueeze(-2)
+    lam_min = torch.linalg.eigvalsh(B.detach()).min()
+    shift = torch.clamp(eps - lam_min, min=0.0)
+    B = B + shift * torch.eye(B.shape[-1], dtype=B.dtype, device=B.device)
+    L = torch.linalg.cholesky(B)
+    Y = torch.linalg.solve_triangular(L, A, upper=False)
+    C = torch.linalg.solve_triangular(L, Y.transpose(-1, -2), upper=False).transpose(-1, -2)
+    C = (C + C.transpose(-1, -2)) * 0.5
+    w, U = degen_eigh(C) if degenerate_safe else torch.linalg.eigh(C)
+    V = torch.linalg.solve_triangular(L.transpose(-1, -2), U, upper=True)
+    return w, V
+
+
+# ---------------------------------------------------------------- SCF pieces
+def get_occ(nelectron: int, mo_energy):
+    e_idx = torch.argsort(mo_energy)
+    idx = torch.arange(mo_energy.shape[0], device=mo_energy.device)
+    mo_occ = torch.where(idx < nelectron // 2, 2.0, 0.0).to(mo_energy.dtype)
+    return mo_occ[torch.argsort(e_idx)]
+
+
+def make_rdm1(mo_coeff, mo_occ):
+    return (mo_coeff * mo_occ.unsqueeze(-2)) @ mo_coeff.transpose(-1, -2)
+
+
+def get_j(eri, dm):
+    """J_ij = sum_kl eri[i,j,k,l] dm[k,l]  (`einsum("ijkl,kl->ij")`, scf_functions_masked.py:152) on the
+    streaming kernel: it is the J-bar half of the transposed contraction, read back transposed."""
+    return hf.dot_eri_dm_rowdot(eri, dm)
+
+
+def get_veff(xc, dm, eri, theta, xctype: str = "NN"):
+    """-> (J + V_xc, E_xc, J) of get_veff_jax; the grid, weights and AO values live in the XCContext."""
+    J = get_j(eri, dm)
+    _nelec, excsum, vmat = _ag.nr_rks(xc, dm, theta, xctype, hermi=1)
+    return J + vmat[0], excsum[0], J
+
+
+def energy_tot(dm, h1e, J, exc_energy, energy_nuc):
+    return (dm * h1e.T).sum() + 0.5 * (dm * J).sum() + exc_energy + energy_nuc
+
+
+def scf_loop(xc, theta, dm, eri, s1e, h1e, energy_nuc, nelectron, xctype="NN", max_cycle=15, diis_max_vec=15,
+             diis_min_vec=2, diis_start_cycle=1, diis_damping=0.0):
+    """`_scf_test_non_padded`: returns (e_tot, dm, energies[max_cycle]); differentiable w.r.t. theta."""
+    vhf, exc_e, J = get_veff(xc, dm, eri, theta, xctype)
+    e_tot = energy_tot(dm, h1e, J, exc_e, energy_nuc)
+    st = initialize_diis(diis_max_vec)
+    energies = []
+    for cycle in range(max_cycle):
+        fock = h1e + vhf
+        if cycle >= diis_start_cycle:
+            fock, st = apply_diis(st, fock, dm, s1e, diis_max_vec, diis_min_vec, diis_damping)
+        mo_energy, mo_coeff = generalized_eigh(fock, s1e)
+        dm = make_rdm1(mo_coeff, get_occ(nelectron, mo_energy))
+        vhf, exc_e, J = get_veff(xc, dm, eri, theta, xctype)
+        e_tot = energy_tot(dm, h1e, J, exc_e, energy_nuc)
+        energies.append(e_tot)
+    return e_tot, dm, torch.stack(energies)
+
+
+def rhf_loop(dm, eri, s1e, h1e, energy_nuc, nelectron, max_cycle=30, diis_max_vec=15, diis_min_vec=2,
+             diis_start_cycle=1):
+    """The same loop with the Hartree-Fock potential vj - vk/2 (J and K from one pass over the tensor)."""
+    def veff(d):
+        vj, vk = hf.dot_eri_dm_autograd(eri, d)
+        return vj - 0.5 * vk
+
+    vhf = veff(dm)
+    st = initialize_diis(diis_max_vec)
+    energies = []
+    for cycle in range(max_cycle):
+        fock = h1e + vhf
+        if cycle >= diis_start_cycle:
+            fock, st = apply_diis(st, fock, dm, s1e, diis_max_vec, diis_min_vec)
+        mo_energy, mo_coeff = generalized_eigh(fock, s1e)
+        dm = make_rdm1(mo_coeff, get_occ(nelectron, mo_energy))
+        vhf = veff(dm)
+        energies.append((h1e * dm.T).sum() + 0.5 * (vhf * dm.T).sum() + energy_nuc)
+    return energies[-1], dm, torch.stack(energies)
+
+
+def core_guess(h1e, s1e, nelectron):
+    e, c = generalized_eigh(h1e, s1e)
+    return make_rdm1(c, get_occ(nelectron, e))

@@ -310,6 +310,9 @@ def _nr_rks_oracle(kind, spec, theta, ao, w, dm, e_bar, v_bar, hermi=0):
     ("NN", 4, 1240, 1), ("NN", 120, 2000, 1), ("NN", 40, 700, 3), ("NN", 200, 515, 1), ("NN", 257, 1100, 1),
     ("NN-AmplitudeEncoding", 4, 1240, 3), ("NN-AmplitudeEncoding", 4, 1192, 1),
     ("GGA", 120, 2000, 1), ("GGA", 10, 400, 2),
+    # edges: one AO / one point, tile boundaries (BN = 32/64/128 +- 1), the c5 AO count at a small grid, ragged GGA
+    ("NN", 1, 1, 1), ("NN", 33, 127, 2), ("NN", 64, 128, 1), ("NN", 129, 257, 1), ("NN", 1000, 300, 1),
+    ("GGA", 65, 130, 1), ("GGA", 136, 300, 2), ("NN-AmplitudeEncoding", 7, 33, 2),
 ])
 def test_nr_rks_fwd_and_vjp(kind, N, G, B):
     from qex_b200 import _lib
