@@ -41,6 +41,27 @@ def test_oracle_rhf_reproduces_the_reference_notebook_energies(R):
     assert abs(np.einsum("ij,ji", dm, I["s1e"]) - 2.0) < 1e-12
 
 
+def test_full_eri_tensor_against_the_notebook_ccsd_energy_and_density_matrix():
+    """For two electrons CCSD is exact, so a 16 x 16 full-CI of the oracle integrals must give the notebook's
+    E(CCSD) = -1.151672678339737 and its printed AO density matrix (both carry pyscf's CCSD convergence
+    tolerance of 1e-7): this pins every element class of the ERI tensor, not only its contraction with one dm."""
+    _, I = _h2(0.74)
+    _, C = scf_ref.generalized_eigh(I["h1e"], I["s1e"])
+    h = C.T @ I["h1e"] @ C
+    e = np.einsum("pi,qj,rk,sl,pqrs->ijkl", C, C, C, C, I["eri"], optimize=True)
+    n = 4
+    eye = np.eye(n)
+    H = (np.einsum("ik,jl->ijkl", h, eye) + np.einsum("ik,jl->ijkl", eye, h) + e.transpose(0, 2, 1, 3)).reshape(n * n, n * n)
+    ev, vec = np.linalg.eigh(H)
+    c = vec[:, 0].reshape(n, n)
+    assert np.abs(c - c.T).max() < 1e-12  # singlet ground state
+    assert abs(ev[0] + I["enuc"] - (-1.151672678339737)) < 3e-7
+    dm = C @ (2.0 * c @ c.T) @ C.T
+    printed = np.array([[0.23211218, 0.18285689, 0.20607785, 0.16169728], [0.18285689, 0.1546802, 0.16169728, 0.133479],
+                        [0.20607785, 0.16169728, 0.23211218, 0.18285689], [0.16169728, 0.133479, 0.18285689, 0.1546802]])
+    assert np.abs(dm - printed).max() < 1e-6
+
+
 def test_oracle_eigensolver_and_degenerate_cotangent():
     rng = np.random.default_rng(0)
     n = 6
