@@ -132,6 +132,34 @@ class NumInt:
         rho = ctx.eval_rho(_np(dm), ncomp, hermi)[0].cpu().numpy()
         return rho[0] if ncomp == 1 else rho
 
+    def eval_mat(self, mol, ao, weight, rho, vxc, non0tab=None, xctype="LDA", spin=0, verbose=None):
+        """numint_legacy.py:23-120 (closed-shell LDA / GGA): the V_xc matrix from caller-supplied
+        potentials, `mat + mat.T` with the same 0.5*w*vrho and 2*w*vsigma*grad(rho) scale factors."""
+        xctype = xctype.upper()
+        if spin != 0:
+            raise NotImplementedError("eval_mat: spin-polarised assembly is not on the accelerated path")
+        if xctype not in ("LDA", "HF", "GGA"):
+            raise NotImplementedError("eval_mat: meta-GGA is not on the accelerated path")
+        ao = _np(ao)
+        gga = xctype == "GGA"
+        G, N = ao.shape[-2], ao.shape[-1]
+        if gga:
+            vrho, vsigma = vxc[:2]
+            rho = _np(rho)
+            assert vsigma is not None and rho.ndim == 2
+        else:
+            vrho = vxc[0] if not getattr(vxc, "ndim", None) == 2 else vxc
+            vsigma = None
+            rho = np.zeros(G) if rho is None else _np(rho).reshape(-1)[:G]
+        ncomp = 4 if gga else 1
+        ctx = self._ctx(N, G, ncomp, None)
+        ctx.set_grid(None, _np(weight))
+        ctx.set_ao(ao[:4] if gga else ao, ncomp)
+        self._ao_key.pop(id(ctx), None)
+        out = ctx.vxc_assemble(rho[:4] if gga else rho, np.zeros(G), _np(vrho).reshape(-1),
+                               None if vsigma is None else _np(vsigma).reshape(-1), "GGA" if gga else "NN")
+        return out[0, : N * N].reshape(N, N).cpu().numpy()
+
     # ---- B1 -------------------------------------------------------------------------------
     def nr_rks(self, mol, grids, xc_code, dms, relativity=0, hermi=0, max_memory=2000, verbose=None, params=None,
                return_resid=False):
@@ -229,6 +257,10 @@ def eval_ao(mol, coords, deriv=0, **kwargs):
 def eval_rho(mol, ao, dm, non0tab=None, xctype="LDA", hermi=0, verbose=None):
     """numint_legacy.py:351."""
     return _ni().eval_rho(mol, ao, dm, non0tab, xctype, hermi, verbose)
+
+
+def eval_mat(mol, ao, weight, rho, vxc, non0tab=None, xctype="LDA", spin=0, verbose=None):
+    return _ni().eval_mat(mol, ao, weight, rho, vxc, non0tab, xctype, spin, verbose)
 
 
 def nr_rks(ni, mol, grids, xc_code, dms, relativity=0, hermi=0, max_memory=2000, verbose=None, params=None):

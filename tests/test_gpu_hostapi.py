@@ -262,3 +262,26 @@ def test_batched_h2_dissociation_geometries():
         assert rel_err(bar[b * N * N : (b + 1) * N * N].reshape(N, N), ref["dm_bar"]) <= TOL64
         tsum = tsum + ref["theta_bar"]
     assert rel_err(bar[B * N * N :], tsum) <= TOL64
+
+
+def test_eval_mat_closed_shell_lda_and_gga():
+    """numint_legacy.py:23-120 restated inline (spin = 0): mat + mat.T with 0.5*w*vrho / 2*w*vsigma*grad(rho)."""
+    from qex_b200 import numint
+
+    mol, grids, dm = _h2()
+    w = grids.weights
+    ao1 = gto_ref.eval_ao(mol._atm, mol._bas, mol._env, grids.coords, 1)
+    rho = numint_ref.eval_rho(ao1, dm, "GGA")
+    rng = np.random.default_rng(3)
+    vrho, vsigma = rng.standard_normal(grids.size), rng.standard_normal(grids.size)
+    mat = ao1[0].T @ (ao1[0] * (0.5 * w * vrho)[:, None])
+    got = numint.eval_mat(mol, ao1[0], w, rho[0], (vrho, None, None, None), xctype="LDA")
+    assert rel_err(got, mat + mat.T) <= TOL64
+    wv = np.concatenate(((w * vrho * 0.5)[None], rho[1:4] * (w * vsigma * 2)))
+    mat = ao1[0].T @ np.einsum("npi,np->pi", ao1, wv)
+    got = numint.eval_mat(mol, ao1, w, rho, (vrho, vsigma, None, None), xctype="GGA")
+    assert rel_err(got, mat + mat.T) <= TOL64
+    with pytest.raises(NotImplementedError):
+        numint.eval_mat(mol, ao1, w, rho, (vrho, vsigma, None, None), xctype="MGGA")
+    with pytest.raises(NotImplementedError):
+        numint.eval_mat(mol, ao1[0], w, rho[0], (vrho,), xctype="LDA", spin=1)
