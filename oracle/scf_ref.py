@@ -172,3 +172,34 @@ def core_guess(h1e, s1e, nelectron):
     """dm from the core Hamiltonian (pyscf init_guess='1e'); the converged energy does not depend on it."""
     e, c = generalized_eigh(h1e, s1e)
     return make_rdm1(c, get_occ(nelectron, e))
+
+
+def scf_fixed_point(dm, eri, ao_grid, grid_weights, s1e, h1e, nelectron, exc_vrho, max_cycle=60, conv_tol=1e-11,
+                    diis_max_vec=8):
+    """Self-consistent dm = T(dm) of `_scf_optimality_cond` (hf_legacy.py:40-48), reached with DIIS and
+    polished with three plain applications of T.  -> (dm, last |T(dm) - dm|_max)."""
+    def T(d, fock_hook=None):
+        vhf, _, _ = get_veff(d, eri, ao_grid, grid_weights, exc_vrho)
+        fock = h1e + vhf
+        if fock_hook is not None:
+            fock = fock_hook(fock, d)
+        e, c = generalized_eigh(fock, s1e)
+        return make_rdm1(c, get_occ(nelectron, e))
+
+    st = [initialize_diis(diis_max_vec)]
+
+    def hook(fock, d):
+        f, st[0] = apply_diis(st[0], fock, d, s1e, diis_max_vec, 2)
+        return f
+
+    for it in range(max_cycle):
+        new = T(dm, hook if it >= 1 else None)
+        delta = np.abs(new - dm).max()
+        dm = new
+        if delta < conv_tol:
+            break
+    for _ in range(3):
+        new = T(dm)
+        delta = np.abs(new - dm).max()
+        dm = new
+    return dm, delta

@@ -414,12 +414,25 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
             else
                 WarpGemm<T, MB, NB, false, false>::run(acc, cur + (size_t)row0 * LD, LD,
                                                        s.Wh + (size_t)(l - 1) * HP * LD + col0, LD, HP, g, qd);
+            // tape: tangent rows keep zdot; value rows keep z, or -- tanh build -- h = tanh(z) itself, from
+            // which the reverse sweep gets sigma' = 1 - h^2 and sigma'' = -2 h sigma' without another tanh
             T2* tp = tape + ((size_t)l * NW + warp) * MB * NB * 32 + lane;
 #pragma unroll
-            for (int mi = 0; mi < MB; ++mi)
+            for (int pg = 0; pg < MB / NS; ++pg)
 #pragma unroll
-                for (int nj = 0; nj < NB; ++nj) tp[(mi * NB + nj) * 32] = Vec2<T>::make(acc[mi][nj][0], acc[mi][nj][1]);
-            act_store<T, NS>(acc, nxt, row0, col0, g, qd, act);
+                for (int nj = 0; nj < NB; ++nj) {
+                    T s0[2], s1[2], s2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) act_d012<T>(act, acc[pg * NS][nj][e], s0[e], s1[e], s2[e]);
+                    T* d = nxt + (size_t)(row0 + (pg * NS) * 8 + g) * LD + col0 + nj * 8 + 2 * qd;
+                    d[0] = s0[0];
+                    d[1] = s0[1];
+                    d[8 * LD] = s1[0] * acc[pg * NS + 1][nj][0];
+                    d[8 * LD + 1] = s1[1] * acc[pg * NS + 1][nj][1];
+                    tp[((pg * NS) * NB + nj) * 32] = (ACT == QEXXC_ACT_TANH) ? Vec2<T>::make(s0[0], s0[1])
+                                                                            : Vec2<T>::make(acc[pg * NS][nj][0], acc[pg * NS][nj][1]);
+                    tp[((pg * NS + 1) * NB + nj) * 32] = Vec2<T>::make(acc[pg * NS + 1][nj][0], acc[pg * NS + 1][nj][1]);
+                }
             __syncthreads();
             T* t = cur;
             cur = nxt;
@@ -484,7 +497,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             T s0, s1, s2;
-                            act_d012<T>(act, zz[e], s0, s1, s2);
+                            if (ACT == QEXXC_ACT_TANH) {  // the tape holds h = tanh(z)
+                                s1 = (T)1 - zz[e] * zz[e];
+                                s2 = (T)-2 * zz[e] * s1;
+                            } else {
+                                act_d012<T>(act, zz[e], s0, s1, s2);
+                            }
                             const T hb = acc[pg * NS][nj][e], hdb = acc[pg * NS + 1][nj][e];
                             d[e] = hb * s1 + hdb * s2 * zzd[e];  // z_bar
                             d[8 * LD + e] = hdb * s1;            // zdot_bar
@@ -493,14 +511,26 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_vjp_kernel(const MlpParams
                 if (l > 0) {  // inputs of Dense l: h_{l-1} = sigma(z_{l-1}) from the tape
                     const T2* tq = tape + ((size_t)(l - 1) * NW + warp) * MB * NB * 32 + lane;
 #pragma unroll
-                    for (int mi = 0; mi < MB; ++mi)
+                    for (int pg = 0; pg < MB / NS; ++pg)
 #pragma unroll
                         for (int nj = 0; nj < NB; ++nj) {
-                            const T2 t2 = tq[(mi * NB + nj) * 32];
-                            acc[mi][nj][0] = t2.x;
-                            acc[mi][nj][1] = t2.y;
+                            const T2 a = tq[((pg * NS) * NB + nj) * 32];
+                            const T2 ad = tq[((pg * NS + 1) * NB + nj) * 32];
+                            const T av[2] = {a.x, a.y}, adv[2] = {ad.x, ad.y};
+                            T* d = Bh + (size_t)(row0 + (pg * NS) * 8 + g) * LD + col0 + nj * 8 + 2 * qd;
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                T s0, s1, s2;
+                                if (ACT == QEXXC_ACT_TANH) {
+                                    s0 = av[e];
+                                    s1 = (T)1 - s0 * s0;
+                                } else {
+                                    act_d012<T>(act, av[e], s0, s1, s2);
+                                }
+                                d[e] = s0;
+                                d[8 * LD + e] = s1 * adv[e];
+                            }
                         }
-                    act_store<T, NS>(acc, Bh, row0, col0, g, qd, act);
                 }
                 __syncthreads();
                 // bias gradient: column sums of z_bar over the value rows

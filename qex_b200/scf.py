@@ -192,3 +192,94 @@ def rhf_loop(dm, eri, s1e, h1e, energy_nuc, nelectron, max_cycle=30, diis_max_ve
 def core_guess(h1e, s1e, nelectron):
     e, c = generalized_eigh(h1e, s1e)
     return make_rdm1(c, get_occ(nelectron, e))
+
+
+# ---------------------------------------------------------------- implicit differentiation (row N4)
+def scf_optimality_cond(xc, theta, dm, eri, s1e, h1e, nelectron, xctype="NN"):
+    """One application of the SCF map dm -> dm' without DIIS (`_scf_optimality_cond`, hf_legacy.py:40-48)."""
+    vhf, _, _ = get_veff(xc, dm, eri, theta, xctype)
+    mo_energy, mo_coeff = generalized_eigh(h1e + vhf, s1e)
+    return make_rdm1(mo_coeff, get_occ(nelectron, mo_energy))
+
+
+def _gmres(matvec, b, tol=1e-12, max_iter=50):
+    """Plain (unrestarted) GMRES with modified Gram-Schmidt for the small adjoint system (I - J^T) x = b;
+    vectors live on the device, the (max_iter+1) x max_iter Hessenberg least-squares problem on the host."""
+    import numpy as np
+
+    bnorm = float(b.norm())
+    if bnorm == 0.0:
+        return torch.zeros_like(b)
+    Q = [b / bnorm]
+    Hm = np.zeros((max_iter + 1, max_iter))
+    y = None
+    for k in range(max_iter):
+        w = matvec(Q[k])
+        for i in range(k + 1):
+            Hm[i, k] = float((Q[i] * w).sum())
+            w = w - Hm[i, k] * Q[i]
+        Hm[k + 1, k] = float(w.norm())
+        e1 = np.zeros(k + 2)
+        e1[0] = bnorm
+        y, res, *_ = np.linalg.lstsq(Hm[: k + 2, : k + 1], e1, rcond=None)
+        r = np.linalg.norm(Hm[: k + 2, : k + 1] @ y - e1)
+        if r <= tol * bnorm or Hm[k + 1, k] <= 1e-300:
+            break
+        Q.append(w / Hm[k + 1, k])
+    x = torch.zeros_like(b)
+    for i, yi in enumerate(y):
+        x = x + float(yi) * Q[i]
+    return x
+
+
+class _ImplicitSCF(torch.autograd.Function):
+    """Converged density matrix with the gradient of the FIXED POINT dm* = T(dm*, theta), not of the
+    iteration history (`make_implicit_diff(_scf, ..., optimality_cond=_scf_optimality_cond,
+    solver=gen_gmres())`, hf_legacy.py:202-205): backward solves (I - dT/ddm)^T lam = dm_bar by GMRES,
+    every operator application being one VJP of the XC + J kernels, then theta_bar = (dT/dtheta)^T lam."""
+
+    @staticmethod
+    def forward(ctx, xc, theta, dm0, eri, s1e, h1e, nelectron, xctype, max_cycle, conv_tol, diis_max_vec):
+        with torch.no_grad():
+            dm = dm0
+            st = initialize_diis(diis_max_vec)
+            for cycle in range(max_cycle):
+                vhf, _, _ = get_veff(xc, dm, eri, theta, xctype)
+                fock = h1e + vhf
+                if cycle >= 1:
+                    fock, st = apply_diis(st, fock, dm, s1e, diis_max_vec, 2, 0.0)
+                mo_energy, mo_coeff = generalized_eigh(fock, s1e)
+                new = make_rdm1(mo_coeff, get_occ(nelectron, mo_energy))
+                delta = float((new - dm).norm())
+                dm = new
+                if delta < conv_tol:
+                    break
+            # polish with plain applications of T so that dm is a fixed point of T itself
+            for _ in range(3):
+                dm = scf_optimality_cond(xc, theta, dm, eri, s1e, h1e, nelectron, xctype)
+        ctx.args = (xc, eri, s1e, h1e, nelectron, xctype)
+        ctx.save_for_backward(theta.detach(), dm)
+        return dm.clone()
+
+    @staticmethod
+    def backward(ctx, dm_bar):
+        xc, eri, s1e, h1e, nelectron, xctype = ctx.args
+        theta, dm = ctx.saved_tensors
+        with torch.enable_grad():
+            th = theta.detach().requires_grad_(True)
+            d = dm.detach().requires_grad_(True)
+            out = scf_optimality_cond(xc, th, d, eri, s1e, h1e, nelectron, xctype)
+
+            def jt(v):  # (dT/ddm)^T v
+                (g,) = torch.autograd.grad(out, d, v, retain_graph=True)
+                return g
+
+            lam = _gmres(lambda v: v - jt(v), dm_bar.contiguous())
+            (theta_bar,) = torch.autograd.grad(out, th, lam, retain_graph=False)
+        return None, theta_bar, None, None, None, None, None, None, None, None, None
+
+
+def scf_fixed_point(xc, theta, dm0, eri, s1e, h1e, nelectron, xctype="NN", max_cycle=50, conv_tol=1e-11,
+                    diis_max_vec=8):
+    """Self-consistent density matrix, differentiable w.r.t. theta by implicit differentiation."""
+    return _ImplicitSCF.apply(xc, theta, dm0, eri, s1e, h1e, nelectron, xctype, max_cycle, conv_tol, diis_max_vec)

@@ -187,3 +187,43 @@ def test_cuda_scf_gradient_wrt_theta_matches_finite_differences():
             h = 1e-5
             fd = (e_of(theta + h * d, **kw) - e_of(theta - h * d, **kw)) / (2 * h)
             assert abs(fd - grad @ d) < tol * max(1.0, abs(fd))
+
+
+@pytest.mark.gpu
+def test_cuda_implicit_differentiation_of_the_scf_fixed_point():
+    """`make_implicit_diff(_scf, optimality_cond=_scf_optimality_cond, solver=gen_gmres())` (hf_legacy.py:202-205):
+    gradient of a density-matrix loss at self-consistency from ONE adjoint GMRES solve whose operator is the VJP
+    of the XC + J kernels, against central differences of the oracle's converged fixed point."""
+    import torch
+
+    from qex_b200 import _lib, scf
+    from qex_b200.engine import NetSpec, XCContext
+
+    m, I, g, spec, theta = _ks_problem(0.9)
+    ao = gto_ref.eval_ao(m._atm, m._bas, m._env, g.coords, 0)
+    dm0 = scf_ref.core_guess(I["h1e"], I["s1e"], 2)
+    rng = np.random.default_rng(1)
+    M = rng.standard_normal((4, 4))
+    M = M + M.T
+
+    def loss_ref(th):
+        dm, delta = scf_ref.scf_fixed_point(dm0, I["eri"], ao, g.weights, I["s1e"], I["h1e"], 2,
+                                            lambda rho: mlp_ref.exc_and_vrho_local(spec, th, rho))
+        assert delta < 1e-10
+        return float((dm * M).sum())
+
+    xc = XCContext(nao=4, ngrids_max=g.size, ncomp=1, net=NetSpec(kind=_lib.NET_LOCAL_MLP, n_features=1, n_hidden=3, width=64))
+    xc.set_grid(g.coords, g.weights).set_basis(m._atm, m._bas, m._env).eval_ao(0)
+    t = {k: torch.as_tensor(np.ascontiguousarray(v)).cuda() for k, v in I.items() if k != "enuc"}
+    th = torch.as_tensor(theta).cuda().requires_grad_(True)
+    dm = scf.scf_fixed_point(xc, th, torch.as_tensor(dm0).cuda(), t["eri"], t["s1e"], t["h1e"], 2)
+    loss = (dm * torch.as_tensor(M).cuda()).sum()
+    assert abs(loss.item() - loss_ref(theta)) < 1e-9
+    (grad,) = torch.autograd.grad(loss, th)
+    grad = grad.cpu().numpy()
+    for _ in range(2):
+        d = rng.standard_normal(theta.shape)
+        d /= np.linalg.norm(d)
+        h = 1e-4
+        fd = (loss_ref(theta + h * d) - loss_ref(theta - h * d)) / (2 * h)
+        assert abs(fd - grad @ d) < 1e-8 + 1e-5 * abs(fd)
