@@ -257,9 +257,9 @@ int qexxc_create(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngrids_
     if (C == 4) QX_A(c->aow, B * Gp * Np);
     {
         size_t part_doubles = 0;
-        wsyrk_workspace(c->num_sms, c->Nc, c->GpadMax, c->B, C == 4, &part_doubles, &c->ws_items_bytes);
+        wsyrk_workspace(c->num_sms, c->Nc, c->GpadMax, c->B, C == 4, &part_doubles, &c->ws_items_bytes,
+                        &c->ws_start_cap);
         QX_A(c->part, part_doubles);
-        c->ws_start_cap = (size_t)c->num_sms + 1;
         for (int k = 0; k < 2; ++k) {
             unsigned char* p = nullptr;
             if (rc == QEXXC_OK) rc = dev_alloc(c, &p, c->ws_items_bytes);

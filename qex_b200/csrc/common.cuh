@@ -153,7 +153,7 @@ namespace qexxc {
 // ---- launchers implemented in the .cu files --------------------------------------------------
 // contract.cu
 void wsyrk_workspace(int num_sms, int Nc, int GpadMax, int B, bool general, size_t* part_doubles,
-                     size_t* item_bytes);
+                     size_t* item_bytes, size_t* start_ints);
 double rowquad_executed_flops(const qexxc_ctx* c, int tri);
 double wsyrk_executed_flops(const qexxc_ctx* c, bool sym);
 // mode 0: (a+a^T)/2, 1: a, 2: a+a^T; tri: keep the upper triangle only (diagonal halved)

@@ -493,14 +493,15 @@ wsyrk_kernel(const double* __restrict__ ao0, const double* __restrict__ Bsrc,
     }
 }
 
-// out[i][j] = scale * (H[i][j] + (tadd ? H[j][i] : 0)), H = sum over grid chunks of the partial tiles.
+// out[i][j] = scale * (H[i][j] + (tadd ? H[j][i] : 0)), H = sum of the partial tiles of a tile (slots
+// slot_start[tile] .. slot_start[tile+1], in grid order).
 // With sym != 0 only 8x8 blocks on or above the diagonal were computed (H symmetric).  A block is
 // 32 columns x RK chunk groups: group kg adds chunks kg, kg+RK, ... and the RK sub-sums are combined
 // through shared memory in a fixed order (bit-reproducible, and the dependent-load chain is RK x shorter).
 constexpr int RK = 8;
 __global__ void __launch_bounds__(32 * RK)
-wsyrk_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, int N, int BN, int NT, int nchunk,
-                    int ntile, int sym, double scale, int tadd, long out_bstride) {
+wsyrk_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, int N, int BN, int NT,
+                    const int* __restrict__ slot_start, int ntile, int sym, double scale, int tadd, long out_bstride) {
     __shared__ double red[2][RK][32];
     const int lane = threadIdx.x & 31, kg = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;
@@ -510,9 +511,10 @@ wsyrk_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, i
     auto H = [&](int r, int c) {
         const int tr = r / BN, tc = c / BN;
         const int tile = sym ? tr * NT - tr * (tr - 1) / 2 + (tc - tr) : tr * NT + tc;
-        const double* P = part + ((long)(b * ntile + tile) * nchunk) * tsz + (long)(r - tr * BN) * BN + (c - tc * BN);
+        const int s0 = slot_start[b * ntile + tile], cnt = slot_start[b * ntile + tile + 1] - s0;
+        const double* P = part + (long)s0 * tsz + (long)(r - tr * BN) * BN + (c - tc * BN);
         double h = 0.0;
-        for (int k = kg; k < nchunk; k += RK) h += P[(long)k * tsz];
+        for (int k = kg; k < cnt; k += RK) h += P[(long)k * tsz];
         return h;
     };
     double h0 = 0.0, h1 = 0.0;  // sub-sums of H(i,j) [or its mirror] and of the transposed term
@@ -670,7 +672,8 @@ void ws_shape(int num_sms, int Nc, int Gpad, int B, bool sym, WsPlan& p) {
     p.NT = (Nc + p.BN - 1) / p.BN;
     p.ntile = sym ? p.NT * (p.NT + 1) / 2 : p.NT * p.NT;
     // ~16 items per CTA keeps greedy scheduling within a few percent of perfect balance
-    long rows = ((long)Gpad * p.ntile * B + 16L * num_sms - 1) / (16L * num_sms);
+    static const long per_cta = getenv("QEXXC_WS_ITEMS") ? atol(getenv("QEXXC_WS_ITEMS")) : 16L;
+    long rows = ((long)Gpad * p.ntile * B + per_cta * num_sms - 1) / (per_cta * num_sms);
     rows = ((rows + 255) / 256) * 256;
     if (rows < 256) rows = 256;
     if (rows > Gpad) rows = Gpad;
@@ -697,57 +700,105 @@ int ws_schedule(qexxc_ctx* c, bool sym, WsPlan& plan, cudaStream_t st) {
                 tcost[t] = ws_tile_cost(BN, c->Nc, ti, tj, sym && ti == tj, nullptr);
             }
     }
-    std::vector<WsItem> items;
-    items.reserve(plan.nitems);
-    std::vector<long> load(plan.nctas, 0);
-    std::vector<std::vector<int>> lists(plan.nctas);
-    // chunk-major order, heavier tiles first within a chunk; each item goes to the least-loaded CTA
+    // Chunk-major sequence of (chunk, batch, tile) items, heavier tiles first within a chunk.
+    //  phase 1: each item goes whole to the least-loaded CTA, as long as that CTA stays within the average
+    //           load -- CTAs therefore walk the sequence together and share the chunk's AO rows in L2;
+    //  phase 2: the remaining tail of the sequence is split by grid rows (whole 32-row slabs, pieces of at
+    //           least kMinSlabs): the least-loaded CTA is filled exactly to the average, again and again, so
+    //           all CTAs finish within a fraction of a percent of each other.
+    // Every piece owns one partial-tile slot; the slots of a tile are numbered in grid order.
+    constexpr int kMinSlabs = 8;
+    struct Piece { int b, t, g0, slabs; };
     std::vector<int> order(plan.ntile);
     for (int t = 0; t < plan.ntile; ++t) order[t] = t;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tcost[a] > tcost[b]; });
     const std::vector<int> starts_g = ws_chunk_starts(c->Gpad, plan.chunk_rows);
-    for (int ch = 0; ch < plan.nchunk; ++ch) {
-        const int g0 = starts_g[ch];
-        const int rows = starts_g[ch + 1] - g0;
+    std::vector<Piece> seq;
+    seq.reserve(plan.nitems);
+    double total = 0.0;
+    for (int ch = 0; ch < plan.nchunk; ++ch)
         for (int b = 0; b < c->B; ++b)
             for (int oi = 0; oi < plan.ntile; ++oi) {
-                const int t = order[oi];
-                WsItem im;
-                im.b = b;
-                im.ti = tiles[t].first;
-                im.tj = tiles[t].second;
-                im.g0 = g0;
-                im.kb = rows / BK;
-                im.slot = (b * plan.ntile + t) * plan.nchunk + ch;
-                im.diag = (sym && im.ti == im.tj) ? 1 : 0;
-                im.pad = 0;
-                int best = 0;
-                for (int k = 1; k < plan.nctas; ++k)
-                    if (load[k] < load[best]) best = k;
-                load[best] += (long)tcost[t] * im.kb;
-                lists[best].push_back((int)items.size());
-                items.push_back(im);
+                const int t = order[oi], slabs = (starts_g[ch + 1] - starts_g[ch]) / BK;
+                seq.push_back({b, t, starts_g[ch], slabs});
+                total += (double)tcost[t] * slabs;
             }
+    const double per = total / plan.nctas;
+    std::vector<std::vector<Piece>> lists(plan.nctas);
+    std::vector<double> load(plan.nctas, 0.0);
+    size_t pos = 0;
+    for (; pos < seq.size(); ++pos) {
+        int best = 0;
+        for (int k = 1; k < plan.nctas; ++k)
+            if (load[k] < load[best]) best = k;
+        const double cost = (double)tcost[seq[pos].t] * seq[pos].slabs;
+        if (load[best] + cost > per) break;
+        load[best] += cost;
+        lists[best].push_back(seq[pos]);
     }
-    if (getenv("QEXXC_DEBUG")) {
-        long mx = 0, sum = 0;
-        for (long l : load) {
-            mx = std::max(mx, l);
-            sum += l;
+    for (; pos < seq.size(); ++pos) {
+        Piece rest = seq[pos];
+        while (rest.slabs > 0) {
+            int k = 0;
+            for (int q = 1; q < plan.nctas; ++q)
+                if (load[q] < load[k]) k = q;
+            // fill the least-loaded CTA up to the average; when even it has no room for a minimal piece
+            // (coarse items on a small grid) the rest is dealt out in minimal pieces, least-loaded first
+            long take = (long)std::floor((per - load[k]) / tcost[rest.t] + 0.5);
+            if (take < kMinSlabs) take = kMinSlabs;
+            if (take > rest.slabs || rest.slabs - take < kMinSlabs) take = rest.slabs;
+            lists[k].push_back({rest.b, rest.t, rest.g0, (int)take});
+            load[k] += (double)tcost[rest.t] * take;
+            rest.g0 += (int)take * BK;
+            rest.slabs -= (int)take;
         }
-        fprintf(stderr, "[qexxc] wsyrk schedule: sym=%d BN=%d tiles=%d chunks=%d (rows %d) items=%d ctas=%d imbalance=%.4f\n",
-                (int)sym, BN, plan.ntile, plan.nchunk, plan.chunk_rows, plan.nitems, plan.nctas,
-                (double)mx * plan.nctas / (double)std::max(sum, 1L));
     }
     std::vector<WsItem> flat;
-    flat.reserve(items.size());
+    flat.reserve(plan.nitems + plan.nctas);
+    std::vector<int> piece_tile;
     std::vector<int> start(plan.nctas + 1, 0);
     for (int k = 0; k < plan.nctas; ++k) {
         start[k] = (int)flat.size();
-        for (int id : lists[k]) flat.push_back(items[id]);
+        for (const Piece& pc : lists[k]) {
+            WsItem im;
+            im.b = pc.b;
+            im.ti = tiles[pc.t].first;
+            im.tj = tiles[pc.t].second;
+            im.g0 = pc.g0;
+            im.kb = pc.slabs;
+            im.slot = 0;
+            im.diag = (sym && im.ti == im.tj) ? 1 : 0;
+            im.pad = 0;
+            flat.push_back(im);
+            piece_tile.push_back(pc.b * plan.ntile + pc.t);
+        }
     }
     start[plan.nctas] = (int)flat.size();
-    if (flat.size() * sizeof(WsItem) > c->ws_items_bytes || (size_t)(plan.nctas + 1) > c->ws_start_cap) {
+    // slots: the pieces of one tile, numbered by first grid row (deterministic reduction order)
+    const int ntb = plan.ntile * c->B;
+    std::vector<int> slot_start(ntb + 1, 0);
+    for (int id : piece_tile) slot_start[id + 1]++;
+    for (int q = 0; q < ntb; ++q) slot_start[q + 1] += slot_start[q];
+    {
+        std::vector<int> idx(flat.size());
+        for (size_t q = 0; q < flat.size(); ++q) idx[q] = (int)q;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+            return piece_tile[a] != piece_tile[b] ? piece_tile[a] < piece_tile[b] : flat[a].g0 < flat[b].g0;
+        });
+        for (size_t q = 0; q < idx.size(); ++q) flat[idx[q]].slot = (int)q;  // sorted position == slot id
+    }
+    if (getenv("QEXXC_DEBUG")) {
+        double mx = 0, sum = 0;
+        for (double l : load) {
+            mx = std::max(mx, l);
+            sum += l;
+        }
+        fprintf(stderr, "[qexxc] wsyrk schedule: sym=%d BN=%d tiles=%d chunks=%d (rows %d) pieces=%zu ctas=%d imbalance=%.4f\n",
+                (int)sym, BN, plan.ntile, plan.nchunk, plan.chunk_rows, flat.size(), plan.nctas,
+                mx * plan.nctas / std::max(sum, 1.0));
+    }
+    start.insert(start.end(), slot_start.begin(), slot_start.end());  // device table: [nctas + 1 | ntile * B + 1]
+    if (flat.size() * sizeof(WsItem) > c->ws_items_bytes || start.size() > c->ws_start_cap) {
         set_error("internal: wsyrk schedule exceeds its workspace (%zu items)", flat.size());
         return QEXXC_ERR_STATE;
     }
@@ -762,17 +813,21 @@ int ws_schedule(qexxc_ctx* c, bool sym, WsPlan& plan, cudaStream_t st) {
 }  // namespace
 
 void wsyrk_workspace(int num_sms, int Nc, int GpadMax, int B, bool general, size_t* part_doubles,
-                     size_t* item_bytes) {
+                     size_t* item_bytes, size_t* start_ints) {
     WsPlan a, b;
     ws_shape(num_sms, Nc, GpadMax, B, true, a);
-    size_t n = (size_t)a.nitems * a.BN * a.BN, it = a.nitems;
+    // the schedule may split up to one item per CTA boundary
+    size_t it = (size_t)a.nitems + 2 * num_sms, n = it * a.BN * a.BN, nt = (size_t)a.ntile * B;
     if (general) {
         ws_shape(num_sms, Nc, GpadMax, B, false, b);
-        n = std::max(n, (size_t)b.nitems * b.BN * b.BN);
-        it = std::max(it, (size_t)b.nitems);
+        const size_t itb = (size_t)b.nitems + 2 * num_sms;
+        n = std::max(n, itb * b.BN * b.BN);
+        it = std::max(it, itb);
+        nt = std::max(nt, (size_t)b.ntile * B);
     }
     *part_doubles = n;
     *item_bytes = it * sizeof(WsItem);
+    *start_ints = (size_t)num_sms + 1 + nt + 1;
 }
 
 double rowquad_executed_flops(const qexxc_ctx* c, int tri) {
@@ -894,8 +949,8 @@ int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bs
 #undef QX_WS
     QX_LAUNCH_CHECK(c);
     dim3 rgrid((c->N + 31) / 32, c->N, c->B);
-    wsyrk_reduce_kernel<<<rgrid, 32 * RK, 0, st>>>(c->part, out, c->N, plan.BN, plan.NT, plan.nchunk, plan.ntile,
-                                              sym ? 1 : 0, scale, tadd, out_bstride);
+    wsyrk_reduce_kernel<<<rgrid, 32 * RK, 0, st>>>(c->part, out, c->N, plan.BN, plan.NT, starts + plan.nctas + 1,
+                                                  plan.ntile, sym ? 1 : 0, scale, tadd, out_bstride);
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;
 }
