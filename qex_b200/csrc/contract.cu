@@ -517,14 +517,16 @@ wsyrk_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, i
         for (int k = kg; k < cnt; k += RK) h += P[(long)k * tsz];
         return h;
     };
-    double h0 = 0.0, h1 = 0.0;  // sub-sums of H(i,j) [or its mirror] and of the transposed term
-    bool same = false;           // transposed term equals the first one (symmetric, mirrored block)
+    // Symmetric case: only elements in 8x8 blocks on or above the diagonal are summed (coalesced rows of the
+    // partial tiles); the result is also written to the mirrored position, so no thread ever walks a
+    // partial tile column-wise.  Inside a diagonal block both H(i,j) and H(j,i) exist and are both read.
+    if (sym && blockIdx.x * 32 + 31 < (i & ~7)) return;  // whole block below the diagonal blocks
+    const bool up = (j >> 3) >= (i >> 3), dg = (j >> 3) == (i >> 3);
+    double h0 = 0.0, h1 = 0.0;  // sub-sums of H(i,j) and of the transposed term H(j,i)
     if (j < N) {
         if (sym) {
-            const bool up = (j >> 3) >= (i >> 3), lo = (i >> 3) >= (j >> 3);
-            h0 = up ? H(i, j) : H(j, i);
-            same = !lo;
-            if (tadd && lo) h1 = H(j, i);
+            if (up) h0 = H(i, j);
+            if (tadd && dg) h1 = H(j, i);
         } else {
             h0 = H(i, j);
             if (tadd) h1 = H(j, i);
@@ -533,15 +535,17 @@ wsyrk_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, i
     red[0][kg][lane] = h0;
     red[1][kg][lane] = h1;
     __syncthreads();
-    if (kg != 0 || j >= N) return;
+    if (kg != 0 || j >= N || (sym && !up)) return;
     double a = 0.0, t = 0.0;
 #pragma unroll
     for (int k = 0; k < RK; ++k) {
         a += red[0][k][lane];
         t += red[1][k][lane];
     }
-    if (same) t = a;
-    out[(long)b * out_bstride + (long)i * N + j] = scale * (tadd ? a + t : a);
+    if (sym && !dg) t = a;  // H(j,i) == H(i,j) was not computed separately
+    const double v = scale * (tadd ? a + t : a);
+    out[(long)b * out_bstride + (long)i * N + j] = v;
+    if (sym && !dg) out[(long)b * out_bstride + (long)j * N + i] = v;
 }
 
 // S[b][i][j] (Npad x Npad, zero padded) from src[b][N][N]: mode 0 (a+a^T)/2, 1 a, 2 a+a^T.
