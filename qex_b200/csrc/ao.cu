@@ -144,7 +144,7 @@ __device__ __forceinline__ void fill_harm(double* __restrict__ H, int stride, bo
 }
 
 template <bool DERIV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512, 2)
 eval_ao_tiled_kernel(const double* __restrict__ coords, const ShellDev* __restrict__ shells,
                      const int* __restrict__ shell_atom, const int* __restrict__ atom_coord,
                      const AoMeta* __restrict__ meta, int nshell, int natm, int nrad, int lmax,
@@ -323,14 +323,18 @@ int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
         const size_t smem = ((size_t)(deriv ? 68 : 17) * (((size_t)P * c->natm) | 1) +
                              (size_t)P * c->nrad * (deriv ? 2 : 1)) * 8;
         dim3 tgrid((unsigned)((c->Gpad + P - 1) / P), c->B);
+        // two resident CTAs share the SM's shared memory whatever the block size, so wide blocks double the
+        // resident warps (the kernel is latency-bound, not pipe-bound); small molecules keep 256 threads
+        int nthr = ((long)P * c->natm >= 256 || c->Npad >= 512) ? 512 : 256;
+        if (getenv("QEXXC_AO_THREADS")) nthr = atoi(getenv("QEXXC_AO_THREADS"));
         if (deriv) {
             QX_CUDA(cudaFuncSetAttribute(eval_ao_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            eval_ao_tiled_kernel<true><<<tgrid, 256, smem, st>>>(c->coords, c->shells, c->shell_atom, c->atom_coord,
+            eval_ao_tiled_kernel<true><<<tgrid, nthr, smem, st>>>(c->coords, c->shells, c->shell_atom, c->atom_coord,
                 c->ao_meta, c->nshell, c->natm, c->nrad, c->lmax, c->env, c->nenv, c->ao, c->G, c->Gpad, c->GpadMax,
                 c->N, c->Npad, c->C, P);
         } else {
             QX_CUDA(cudaFuncSetAttribute(eval_ao_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            eval_ao_tiled_kernel<false><<<tgrid, 256, smem, st>>>(c->coords, c->shells, c->shell_atom, c->atom_coord,
+            eval_ao_tiled_kernel<false><<<tgrid, nthr, smem, st>>>(c->coords, c->shells, c->shell_atom, c->atom_coord,
                 c->ao_meta, c->nshell, c->natm, c->nrad, c->lmax, c->env, c->nenv, c->ao, c->G, c->Gpad, c->GpadMax,
                 c->N, c->Npad, c->C, P);
         }
