@@ -242,6 +242,9 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its banner on STDOUT, next to the one JSON line the driver reads
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl = workloads.make(args.config, ngrids=args.ngrids)
