@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libqexxc.so"
+LIB_PATH = Path(os.environ["QEXXC_LIB"]) if os.environ.get("QEXXC_LIB") else HERE / "libqexxc.so"  # override: A/B builds
 
 # mirrors include/qexxc.h
 XC_NN, XC_NN_GLOBAL, XC_GGA = 0, 1, 2

@@ -255,6 +255,7 @@ int qexxc_create(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngrids_
     QX_A(c->vrhob, B * Gp);
     QX_A(c->vgammab, B * Gp);
     if (C == 4) QX_A(c->aow, B * Gp * Np);
+    QX_A(c->rq_part, (size_t)((c->Nc + 31) / 32) * 4 * c->num_sms * 128);
     {
         size_t part_doubles = 0;
         wsyrk_workspace(c->num_sms, c->Nc, c->GpadMax, c->B, C == 4, &part_doubles, &c->ws_items_bytes,

@@ -110,6 +110,7 @@ struct qexxc_ctx {
     double* vrhob = nullptr;    // [B][GpadMax]
     double* vgammab = nullptr;  // [B][GpadMax]
     double* aow = nullptr;      // [B][GpadMax][Npad] (C == 4 only)
+    double* rq_part = nullptr;  // rowquad split-tail partials [NT][4][num_sms][128]
     double* part = nullptr;     // wsyrk partial tiles, one compact [BN][BN] slot per (batch, tile, grid chunk)
     void* ws_items[2] = {nullptr, nullptr};  // wsyrk static schedules (general, symmetric)
     int* ws_start[2] = {nullptr, nullptr};

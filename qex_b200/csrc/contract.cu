@@ -89,6 +89,11 @@ __device__ __forceinline__ int ring_wait(const Ring& r) {
     return s;
 }
 __device__ __forceinline__ void ring_release(Ring& r, int s, int lane) {
+    // The stage was read through the generic proxy (LDS) and will be overwritten through the async proxy
+    // (cp.async.bulk): the mbarrier release/acquire chain alone does not order the two proxies.  Without this
+    // fence a refill could overtake the last fragment loads of a slab -- seen as run-to-run differences of a
+    // few rows of rho in one build variant (scripts/det_probe.py), never as a parity failure.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(r.empty + s);
     ++r.it;
@@ -170,13 +175,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, double* __restrict__ q,
                int Npad, int Nc, long ao_cstride, long ao_bstride, long S_bstride, long q_cstride,
                long q_bstride, int ncomp, int tri, double f0, double f1, double f2, double f3, int ldS, int Sc,
-               const double* __restrict__ sgn) {
+               const double* __restrict__ sgn, int nbulk, int ntail, double* __restrict__ qpart) {
     // tri != 0: S holds only its upper triangle (diagonal halved); the caller folds the factor 2
     // into f0.  Npad = storage pitch (multiple of 32, pad columns are zeros), Nc = compute extent
     // (multiple of 8): slabs are always full, column blocks beyond Nc are never issued.
     // S is [Npad rows][ldS pitch] with Sc compute columns: the square symmetric operand (ldS = Npad,
     // Sc = Nc) or, when sgn != nullptr, the occupation-scaled MO coefficients L = C sqrt|occ| of pyscf's
     // eval_rho2 (numint_legacy.py:527-545): then q[g] = f0 * sum_k sgn_k ((ao L)[g,k])^2.
+    // Grid: blocks [0, nbulk) own one 128-row tile each and sweep all column tiles.  The last `ntail` row
+    // tiles -- the partial wave that would leave SMs idle for a whole tile time -- are cut into one block per
+    // (row tile, column tile), issued heaviest column tile first (list scheduling by the hardware block
+    // dispatcher); their per-column-tile results go to qpart and rowquad_tail_kernel adds them in order.
     using Cfg = RowquadCfg<BN>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
@@ -186,11 +195,19 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    const long g0 = (long)blockIdx.x * BM;
+    const int NT = (Sc + BN - 1) / BN;
+    int tile = blockIdx.x, nt_lo = 0, nt_hi = NT;
+    const bool split = (int)blockIdx.x >= nbulk;
+    if (split) {
+        const int idx = blockIdx.x - nbulk;
+        nt_lo = NT - 1 - idx / ntail;
+        nt_hi = nt_lo + 1;
+        tile = nbulk + idx % ntail;
+    }
+    const long g0 = (long)tile * BM;
     const double* ao_b = ao + (long)b * ao_bstride;
     const double* A0 = ao_b + g0 * Npad;
     const double* S_b = S + (long)b * S_bstride;
-    const int NT = (Sc + BN - 1) / BN;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -209,7 +226,7 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
         // also arms the barrier with the slab's byte count and copies the S rows.
         const int pw = warp - NCONS;
         int it = 0;
-        for (int nt = 0; nt < NT; ++nt) {
+        for (int nt = nt_lo; nt < nt_hi; ++nt) {
             const int nw = imin(BN, ldS - nt * BN);  // copy width: storage columns (zeros beyond Sc)
             const int kend = rq_kend(tri, Nc, BN, nt);
             for (int kb = 0; kb < kend; ++kb, ++it) {
@@ -243,7 +260,7 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
     Ring ring{sm, full, empty, 0};
     const int aoff = (wm * 32 + g) * Cfg::LDA + qd;
     const int boff = qd * Cfg::LDB + wn * 8 + g;  // this warp's blocks are 2*j + wn: 16 doubles apart
-    for (int nt = 0; nt < NT; ++nt) {
+    for (int nt = nt_lo; nt < nt_hi; ++nt) {
         const int nw = imin(BN, Sc - nt * BN);
         const int kend = rq_kend(tri, Nc, BN, nt);
         const int nbv = nw >> 3;                             // valid n8 blocks of this tile
@@ -321,9 +338,23 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
         const double fac[4] = {f0, f1, f2, f3};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            if (c < ncomp)
-                q[(long)b * q_bstride + (long)c * q_cstride + g0 + threadIdx.x] =
-                    fac[c] * (red[(c * 2 + 0) * BM + threadIdx.x] + red[(c * 2 + 1) * BM + threadIdx.x]);
+            if (c < ncomp) {
+                const double v = fac[c] * (red[(c * 2 + 0) * BM + threadIdx.x] + red[(c * 2 + 1) * BM + threadIdx.x]);
+                if (split) qpart[((long)(nt_lo * 4 + c) * ntail + (tile - nbulk)) * BM + threadIdx.x] = v;
+                else q[(long)b * q_bstride + (long)c * q_cstride + g0 + threadIdx.x] = v;
+            }
+    }
+}
+
+// q[c][row] = sum over the column tiles (in order) of the split tail tiles' partial results
+__global__ void rowquad_tail_kernel(const double* __restrict__ qpart, double* __restrict__ q, long q_cstride,
+                                    int ncomp, int NT, int nbulk, int ntail) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ntail * BM) return;
+    for (int c = 0; c < ncomp; ++c) {
+        double s = 0.0;
+        for (int nt = 0; nt < NT; ++nt) s += qpart[((long)(nt * 4 + c) * ntail) * BM + r];
+        q[(long)c * q_cstride + (long)nbulk * BM + r] = s;
     }
 }
 
@@ -896,7 +927,7 @@ int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const doub
         QX_TRY(set_smem(rowquad_kernel<BNV>, RowquadCfg<BNV>::SMEM));                            \
         rowquad_kernel<BNV><<<grid, NTHREADS, RowquadCfg<BNV>::SMEM, st>>>(                      \
             c->ao, L, q, c->Npad, c->Nc, ao_cs, ao_bs, L_bs, 0, q_bstride, 1, 0, 1.0, 0.0, 0.0,  \
-            0.0, ldL, Sc, sgn);                                                                  \
+            0.0, ldL, Sc, sgn, (int)grid.x, 0, nullptr);                                         \
     } while (0)
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
     if (BN == 128) QX_RQM(128);
@@ -907,17 +938,30 @@ int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const doub
     return QEXXC_OK;
 }
 
+// Split the last partial wave of row tiles into per-column-tile blocks?  Unsplit it costs one full tile time;
+// split it costs about (its share of the SMs) + (the heaviest column tile), in units of a tile time.
+int rowquad_tail_tiles(const qexxc_ctx* c, int tri) {
+    if (c->B != 1 || c->rq_part == nullptr || getenv("QEXXC_NO_TAIL_SPLIT")) return 0;
+    const int BN = pick_bn(c->Nc), NT = (c->Nc + BN - 1) / BN, T = c->Gpad / BM;
+    const int rem = T % c->num_sms;
+    if (rem == 0 || NT < 2) return 0;
+    const double heaviest = tri ? 2.0 / (NT + 1) : 1.0 / NT;
+    return ((double)rem / c->num_sms + heaviest < 0.95) ? rem : 0;
+}
+
 int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride,
                    long q_cstride, cudaStream_t st) {
-    const int BN = pick_bn(c->Nc);
-    dim3 grid(c->Gpad / BM, c->B);
+    const int BN = pick_bn(c->Nc), NT = (c->Nc + BN - 1) / BN, T = c->Gpad / BM;
+    const int ntail = rowquad_tail_tiles(c, tri), nbulk = T - ntail;
+    dim3 grid(nbulk + ntail * NT, c->B);
     const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = ao_cs * c->C, S_bs = (long)c->Npad * c->Npad;
 #define QX_RQ(BNV)                                                                               \
     do {                                                                                         \
         QX_TRY(set_smem(rowquad_kernel<BNV>, RowquadCfg<BNV>::SMEM));                            \
         rowquad_kernel<BNV><<<grid, NTHREADS, RowquadCfg<BNV>::SMEM, st>>>(                      \
             c->ao, c->S, q, c->Npad, c->Nc, ao_cs, ao_bs, S_bs, q_cstride, q_bstride, ncomp, tri, \
-            (tri ? 2.0 : 1.0) * fac4[0], fac4[1], fac4[2], fac4[3], c->Npad, c->Nc, nullptr);    \
+            (tri ? 2.0 : 1.0) * fac4[0], fac4[1], fac4[2], fac4[3], c->Npad, c->Nc, nullptr,     \
+            nbulk, ntail, c->rq_part);                                                           \
     } while (0)
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
     if (BN == 128) QX_RQ(128);
@@ -925,6 +969,10 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double*
     else QX_RQ(32);
 #undef QX_RQ
     QX_LAUNCH_CHECK(c);
+    if (ntail > 0) {
+        rowquad_tail_kernel<<<(ntail * BM + 255) / 256, 256, 0, st>>>(c->rq_part, q, q_cstride, ncomp, NT, nbulk, ntail);
+        QX_LAUNCH_CHECK(c);
+    }
     return QEXXC_OK;
 }
 

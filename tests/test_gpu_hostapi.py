@@ -285,3 +285,34 @@ def test_eval_mat_closed_shell_lda_and_gga():
         numint.eval_mat(mol, ao1, w, rho, (vrho, vsigma, None, None), xctype="MGGA")
     with pytest.raises(NotImplementedError):
         numint.eval_mat(mol, ao1[0], w, rho[0], (vrho,), xctype="LDA", spin=1)
+
+
+@pytest.mark.parametrize("G", [61_000, 125_000])
+def test_bitwise_run_to_run_determinism_at_shard_sizes(G):
+    """The per-GPU shard sizes of the 8- and 16-way grid split of c5 (the rowquad tail wave is split there):
+    rho and the full fwd+VJP outputs must be bit-identical between runs.  A missing generic->async proxy
+    fence in the shared-memory ring once showed up exactly here (a few rows of rho differing by 1e-2 between
+    runs in one build variant) while every parity tolerance still passed."""
+    import torch
+
+    from qex_b200 import workloads
+    from qex_b200.engine import XCContext
+
+    wl = workloads.make("c5", ngrids=G)
+    ctx = XCContext(nao=wl.nao, ngrids_max=G, net=workloads.net_spec(wl))
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env).set_grid(wl.coords, wl.weights).eval_ao(0)
+    rho = ctx.eval_rho(wl.dm, 1, 1).clone()
+    ref = None
+    for _ in range(3):
+        assert torch.equal(rho, ctx.eval_rho(wl.dm, 1, 1))
+        out, resid = ctx.nr_rks_fwd(wl.dm, wl.theta, "NN")
+        bar = ctx.nr_rks_vjp(wl.theta, resid, [wl.e_bar], wl.v_bar, "NN")
+        cur = (out.clone(), bar.clone(), resid.clone())
+        if ref is None:
+            ref = cur
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(ref, cur))
+    # and the split tail agrees with the oracle on the last rows of the grid
+    tail = slice(G - 256, G)
+    ao = gto_ref.eval_ao(wl.mol._atm, wl.mol._bas, wl.mol._env, wl.coords[tail], 0)
+    assert rel_err(rho[0, 0, tail].cpu().numpy(), numint_ref.eval_rho(ao, wl.dm, "LDA", hermi=1)) <= TOL64
