@@ -317,7 +317,7 @@ long qexxc_launch_count(const qexxc_ctx* c) { return c ? c->launches : 0; }
 // ---- stage 1 --------------------------------------------------------------------------------
 int qexxc_set_grid(qexxc_ctx* c, const double* coords_dev, const double* weights_dev, int ngrids, void* stream) {
     QX_ARG(c != nullptr, "ctx is null");
-    QX_ARG(weights_dev != nullptr, "weights pointer is null");
+    QX_ARG(weights_dev != nullptr || ngrids == 0, "weights pointer is null");
     QX_ARG(ngrids >= 0 && ngrids <= c->Gmax, "ngrids exceeds the ngrids_max the context was created with");
     QX_CUDA(cudaSetDevice(c->device));
     c->G = ngrids;
@@ -418,7 +418,7 @@ int qexxc_eval_ao(qexxc_ctx* c, int deriv, void* stream) {
 }
 
 int qexxc_set_ao(qexxc_ctx* c, const double* ao_dev, int ncomp, int ngrids, void* stream) {
-    QX_ARG(c != nullptr && ao_dev != nullptr, "null pointer");
+    QX_ARG(c != nullptr && (ao_dev != nullptr || ngrids == 0), "null pointer");
     QX_ARG(ncomp == 1 || ncomp == 4, "ncomp must be 1 or 4");
     QX_ARG(ncomp <= c->C, "ncomp exceeds the context's ncomp");
     if (!c->have_grid || ngrids != c->G) {

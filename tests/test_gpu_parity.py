@@ -451,3 +451,29 @@ def test_errors_are_loud():
     with pytest.raises(NotImplementedError):
         _ctx(nao=4, ngrids_max=128, net=_mlp_net(H=100)).set_grid(None, np.ones(128)).xc_fwd(
             np.ones(128), np.zeros(100 * 1 + 100 + 2 * (100 * 100 + 100) + 101), "NN")
+
+
+def test_empty_grid_and_zero_density_edge_cases():
+    """An empty grid (the reference's block loop simply does not run: nelec = excsum = 0, vmat = 0) and an
+    all-zero density matrix (rho = 0 exactly at every point) go through the same kernels without special cases."""
+    N = 12
+    ctx = _ctx(nao=N, ngrids_max=256, net=_mlp_net())
+    theta = mlp_ref.pack(*mlp_ref.init_params(mlp_ref.MLPSpec([1, 64, 64, 64, 1], "tanh"), 1))
+    rng = np.random.default_rng(0)
+    dm = rng.standard_normal((N, N))
+    ctx.set_grid(None, np.zeros(0)).set_ao(np.zeros((1, 1, 0, N)), 1)
+    out, resid = ctx.nr_rks_fwd(dm, theta, "NN")
+    assert not _to_np(out).any()
+    bar = _to_np(ctx.nr_rks_vjp(theta, resid, [1.0], rng.standard_normal((N, N)), "NN"))
+    assert not bar[: N * N].any() and np.isfinite(bar).all()
+    # zero density on a real grid: exc = f(0) per point, nelec = 0, and the oracle agrees
+    ao, _, w = synth_problem(N, 200, 1, seed=3)
+    ctx.set_grid(None, w).set_ao(ao, 1)
+    out = _to_np(ctx.nr_rks_fwd(np.zeros((N, N)), theta, "NN")[0])[0]
+    spec = mlp_ref.MLPSpec([1, 64, 64, 64, 1], "tanh")
+    nelec, excsum, vmat = numint_ref.nr_rks(ao[0, 0], w[0], np.zeros((N, N)),
+                                            lambda code, rho, **k: (mlp_ref.exc_and_vrho_local(spec, theta, rho)[0],
+                                                                    (mlp_ref.exc_and_vrho_local(spec, theta, rho)[1], None, None, None), None, None),
+                                            "NN")
+    assert out[N * N + 1] == 0.0 and abs(out[N * N] - excsum) <= 1e-12
+    assert rel_err(out[: N * N].reshape(N, N), vmat) <= TOL64
