@@ -313,6 +313,8 @@ def _nr_rks_oracle(kind, spec, theta, ao, w, dm, e_bar, v_bar, hermi=0):
     # edges: one AO / one point, tile boundaries (BN = 32/64/128 +- 1), the c5 AO count at a small grid, ragged GGA
     ("NN", 1, 1, 1), ("NN", 33, 127, 2), ("NN", 64, 128, 1), ("NN", 129, 257, 1), ("NN", 1000, 300, 1),
     ("GGA", 65, 130, 1), ("GGA", 136, 300, 2), ("NN-AmplitudeEncoding", 7, 33, 2),
+    # beyond the c5 AO count (11 column tiles, ragged last one) and a multi-tile GGA case
+    ("NN", 1290, 260, 1), ("GGA", 520, 200, 1),
 ])
 def test_nr_rks_fwd_and_vjp(kind, N, G, B):
     from qex_b200 import _lib
