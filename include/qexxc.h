@@ -218,6 +218,15 @@ int qexxc_dot_eri_dm(int device, const double* eri_dev, const double* dm_dev, in
  * Either cotangent may be NULL (= zero). No permutational symmetry of eri is assumed. */
 int qexxc_dot_eri_dm_vjp(int device, const double* eri_dev, const double* vj_bar_dev, const double* vk_bar_dev,
                          int nset, int nao, double* dm_bar_dev, double* work_dev, long work_doubles, void* stream);
+/* Batched over `nmol` molecules of equal nao, each with its own tensor and ONE density matrix (the c4 pattern:
+ * a dissociation curve of small molecules in one launch): eri [nmol][nao^4], dm / vj / vk / cotangents
+ * [nmol][nao][nao]; `work` needs nmol * qexxc_jk_workspace_doubles doubles. */
+int qexxc_dot_eri_dm_batched(int device, const double* eri_dev, const double* dm_dev, int nmol, int nao, int with_j,
+                             int with_k, double* vj_dev, double* vk_dev, double* work_dev, long work_doubles,
+                             void* stream);
+int qexxc_dot_eri_dm_vjp_batched(int device, const double* eri_dev, const double* vj_bar_dev, const double* vk_bar_dev,
+                                 int nmol, int nao, double* dm_bar_dev, double* work_dev, long work_doubles,
+                                 void* stream);
 /* kernels launched by the three J/K calls since the library was loaded */
 long qexxc_jk_launch_count(void);
 

@@ -103,7 +103,7 @@ struct JkOwn {
 template <bool WJ, bool WK>
 __global__ void __launch_bounds__(JT, 1)
 jk_fwd_kernel(const double* __restrict__ eri, const double* __restrict__ dm, int N, int TL, int rows, int npr,
-              int maxseg, double* __restrict__ Jpart, double* __restrict__ Kpart) {
+              int maxseg, double* __restrict__ Jpart, double* __restrict__ Kpart, long jstride, long kstride) {
     __shared__ double Sk[JT];
     extern __shared__ double Sd[];  // WK: this chunk's dm multipliers, [N][KG][JR], zero beyond the chunk
     const int ce = blockIdx.x, pr = blockIdx.y, nchunk = gridDim.x, tid = threadIdx.x, KG = blockDim.x / TL;
@@ -111,6 +111,11 @@ jk_fwd_kernel(const double* __restrict__ eri, const double* __restrict__ dm, int
     const JkOwn o(N, TL, KG, rows, ce);
     const long long NN = (long long)N * N;
     const long long p0 = jk_split(NN, npr, pr), p1 = jk_split(NN, npr, pr + 1);
+    // blockIdx.z: molecule of a batch (its own tensor, density matrix and partial buffers)
+    eri += (long long)blockIdx.z * NN * NN;
+    dm += (long long)blockIdx.z * NN;
+    Jpart += (long long)blockIdx.z * jstride;
+    Kpart += (long long)blockIdx.z * kstride;
     if (WK) {
         // dm[j][k] for the rows k of this chunk, stored so that a thread's JR multipliers are contiguous:
         // the K loop reads them with broadcast LDS at use time instead of holding JR more loads in registers
@@ -183,7 +188,15 @@ __device__ __forceinline__ int jk_range_of(long long p, long long total, int par
 __global__ void jk_finish_kernel(const double* __restrict__ flat, int nflat, long NN, double* __restrict__ out_flat,
                                  int nblk_flat, const double* __restrict__ rows_part, int N, int nranges, int maxseg,
                                  int nchunk, int owner_rows, const double* __restrict__ add, int nadd,
-                                 double* __restrict__ out_rows) {
+                                 double* __restrict__ out_rows, long jstride, long kstride) {
+    {  // blockIdx.y: molecule of a batch
+        const long long m = blockIdx.y;
+        if (flat) flat += m * jstride;
+        if (out_flat) out_flat += m * NN;
+        if (rows_part) rows_part += m * kstride;
+        if (add) add += m * jstride;
+        if (out_rows) out_rows += m * NN;
+    }
     if ((int)blockIdx.x < nblk_flat) {
         const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
         if (e >= NN) return;
@@ -219,7 +232,8 @@ __global__ void jk_finish_kernel(const double* __restrict__ flat, int nflat, lon
 template <bool WJ, bool WK>
 __global__ void __launch_bounds__(JT, 1)
 jk_vjp_kernel(const double* __restrict__ eri, const double* __restrict__ vjb, const double* __restrict__ vkb, int N,
-              int TL, int rows, int nqr, int maxseg, double* __restrict__ DJpart, double* __restrict__ DKpart) {
+              int TL, int rows, int nqr, int maxseg, double* __restrict__ DJpart, double* __restrict__ DKpart,
+              long jstride, long kstride) {
     __shared__ double Sk[JR * JW];
     __shared__ double Sred[JQ * JW];
     const int ce = blockIdx.x, qr = blockIdx.y, nchunk = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -227,6 +241,11 @@ jk_vjp_kernel(const double* __restrict__ eri, const double* __restrict__ vjb, co
     const JkOwn o(N, TL, KG, rows, ce);
     const long long NN = (long long)N * N;
     const long long q0 = jk_split(NN, nqr, qr), q1 = jk_split(NN, nqr, qr + 1);
+    eri += (long long)blockIdx.z * NN * NN;
+    if (WJ) vjb += (long long)blockIdx.z * NN;
+    if (WK) vkb += (long long)blockIdx.z * NN;
+    DJpart += (long long)blockIdx.z * jstride;
+    DKpart += (long long)blockIdx.z * kstride;
     double jb[JR], ak[JR];
 #pragma unroll
     for (int n = 0; n < JR; ++n) {
@@ -337,82 +356,106 @@ int qexxc_jk_workspace_doubles(int device, int nao, long* out) {
     return QEXXC_OK;
 }
 
-int qexxc_dot_eri_dm(int device, const double* eri_dev, const double* dm_dev, int nset, int nao, int with_j,
-                     int with_k, double* vj_dev, double* vk_dev, double* work_dev, long work_doubles, void* stream) {
+static int jk_forward(int device, const double* eri_dev, const double* dm_dev, int nmol, int nset, int nao,
+                      int with_j, int with_k, double* vj_dev, double* vk_dev, double* work_dev, long work_doubles,
+                      void* stream) {
     QX_ARG(eri_dev && dm_dev && work_dev, "null device pointer");
-    QX_ARG(nset >= 1 && nao >= 1, "nset and nao must be >= 1");
+    QX_ARG(nset >= 1 && nao >= 1 && nmol >= 1, "nmol, nset and nao must be >= 1");
     QX_TRY(jk_check_nao(nao));
     QX_ARG((!with_j || vj_dev) && (!with_k || vk_dev), "output pointer is null for a requested matrix");
     if (!with_j && !with_k) return QEXXC_OK;
     int sms = 0;
     QX_TRY(jk_device(device, &sms));
     const JkPlan p = jk_plan(nao, sms);
-    QX_ARG(work_doubles >= p.jpart + p.kpart, "workspace smaller than qexxc_jk_workspace_doubles");
+    QX_ARG(work_doubles >= (p.jpart + p.kpart) * nmol, "workspace smaller than nmol * qexxc_jk_workspace_doubles");
     cudaStream_t st = (cudaStream_t)stream;
     const long NN = (long)nao * nao;
     double* Jpart = work_dev;
-    double* Kpart = work_dev + p.jpart;
-    const dim3 grid(p.nchunk, p.npr);
+    double* Kpart = work_dev + p.jpart * nmol;
+    const dim3 grid(p.nchunk, p.npr, nmol);
     const size_t smem = with_k ? sizeof(double) * nao * p.KG * JR : 0;  // <= 64 KB
     if (with_k) {
         QX_CUDA(cudaFuncSetAttribute(jk_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         QX_CUDA(cudaFuncSetAttribute(jk_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     }
-    for (int x = 0; x < nset; ++x) {
+    for (int x = 0; x < nset; ++x) {  // nset > 1 only with nmol == 1 (several density matrices, one tensor)
         const double* dm = dm_dev + x * NN;
         if (with_j && with_k) {
-            jk_fwd_kernel<true, true><<<grid, p.KG * p.TL, smem, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr, p.maxseg, Jpart, Kpart);
+            jk_fwd_kernel<true, true><<<grid, p.KG * p.TL, smem, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr, p.maxseg, Jpart, Kpart, p.jpart, p.kpart);
         } else if (with_j) {
-            jk_fwd_kernel<true, false><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr, p.maxseg, Jpart, Kpart);
+            jk_fwd_kernel<true, false><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr, p.maxseg, Jpart, Kpart, p.jpart, p.kpart);
         } else {
-            jk_fwd_kernel<false, true><<<grid, p.KG * p.TL, smem, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr, p.maxseg, Jpart, Kpart);
+            jk_fwd_kernel<false, true><<<grid, p.KG * p.TL, smem, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr, p.maxseg, Jpart, Kpart, p.jpart, p.kpart);
         }
         JK_LAUNCH_CHECK();
         const int nblk_flat = with_j ? (int)((NN + 255) / 256) : 0;
-        jk_finish_kernel<<<nblk_flat + (with_k ? nao : 0), 256, 0, st>>>(Jpart, p.npr, NN, with_j ? vj_dev + x * NN : nullptr,
-                                                                        nblk_flat, Kpart, nao, p.npr, p.maxseg, p.nchunk, 0,
-                                                                        nullptr, 0, with_k ? vk_dev + x * NN : nullptr);
+        jk_finish_kernel<<<dim3(nblk_flat + (with_k ? nao : 0), nmol), 256, 0, st>>>(
+            Jpart, p.npr, NN, with_j ? vj_dev + x * NN : nullptr, nblk_flat, Kpart, nao, p.npr, p.maxseg, p.nchunk, 0,
+            nullptr, 0, with_k ? vk_dev + x * NN : nullptr, p.jpart, p.kpart);
         JK_LAUNCH_CHECK();
     }
     return QEXXC_OK;
 }
 
-int qexxc_dot_eri_dm_vjp(int device, const double* eri_dev, const double* vj_bar_dev, const double* vk_bar_dev,
-                         int nset, int nao, double* dm_bar_dev, double* work_dev, long work_doubles, void* stream) {
+static int jk_reverse(int device, const double* eri_dev, const double* vj_bar_dev, const double* vk_bar_dev, int nmol,
+                      int nset, int nao, double* dm_bar_dev, double* work_dev, long work_doubles, void* stream) {
     QX_ARG(eri_dev && dm_bar_dev && work_dev, "null device pointer");
-    QX_ARG(nset >= 1 && nao >= 1, "nset and nao must be >= 1");
+    QX_ARG(nset >= 1 && nao >= 1 && nmol >= 1, "nmol, nset and nao must be >= 1");
     QX_TRY(jk_check_nao(nao));
     int sms = 0;
     QX_TRY(jk_device(device, &sms));
     const JkPlan p = jk_plan(nao, sms);
-    QX_ARG(work_doubles >= p.jpart + p.kpart, "workspace smaller than qexxc_jk_workspace_doubles");
+    QX_ARG(work_doubles >= (p.jpart + p.kpart) * nmol, "workspace smaller than nmol * qexxc_jk_workspace_doubles");
     cudaStream_t st = (cudaStream_t)stream;
     const long NN = (long)nao * nao;
     const bool wj = vj_bar_dev != nullptr, wk = vk_bar_dev != nullptr;
     if (!wj && !wk) {
-        QX_CUDA(cudaMemsetAsync(dm_bar_dev, 0, sizeof(double) * nset * NN, st));
+        QX_CUDA(cudaMemsetAsync(dm_bar_dev, 0, sizeof(double) * nset * nmol * NN, st));
         return QEXXC_OK;
     }
     double* DJpart = work_dev;
-    double* DKpart = work_dev + p.jpart;
-    const dim3 grid(p.nchunk, p.npr);
+    double* DKpart = work_dev + p.jpart * nmol;
+    const dim3 grid(p.nchunk, p.npr, nmol);
     for (int x = 0; x < nset; ++x) {
         const double* vjb = wj ? vj_bar_dev + x * NN : nullptr;
         const double* vkb = wk ? vk_bar_dev + x * NN : nullptr;
         if (wj && wk) {
-            jk_vjp_kernel<true, true><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, p.maxseg, DJpart, DKpart);
+            jk_vjp_kernel<true, true><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, p.maxseg, DJpart, DKpart, p.jpart, p.kpart);
         } else if (wj) {
-            jk_vjp_kernel<true, false><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, p.maxseg, DJpart, DKpart);
+            jk_vjp_kernel<true, false><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, p.maxseg, DJpart, DKpart, p.jpart, p.kpart);
         } else {
-            jk_vjp_kernel<false, true><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, p.maxseg, DJpart, DKpart);
+            jk_vjp_kernel<false, true><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, p.maxseg, DJpart, DKpart, p.jpart, p.kpart);
         }
         JK_LAUNCH_CHECK();
         double* out = dm_bar_dev + x * NN;
-        jk_finish_kernel<<<nao, 256, 0, st>>>(nullptr, 0, NN, nullptr, 0, wk ? DKpart : nullptr, nao, p.npr, p.maxseg, p.nchunk,
-                                              p.rows, wj ? DJpart : nullptr, wj ? p.nchunk : 0, out);
+        jk_finish_kernel<<<dim3(nao, nmol), 256, 0, st>>>(nullptr, 0, NN, nullptr, 0, wk ? DKpart : nullptr, nao, p.npr,
+                                                         p.maxseg, p.nchunk, p.rows, wj ? DJpart : nullptr,
+                                                         wj ? p.nchunk : 0, out, p.jpart, p.kpart);
         JK_LAUNCH_CHECK();
     }
     return QEXXC_OK;
+}
+
+int qexxc_dot_eri_dm(int device, const double* eri_dev, const double* dm_dev, int nset, int nao, int with_j,
+                     int with_k, double* vj_dev, double* vk_dev, double* work_dev, long work_doubles, void* stream) {
+    return jk_forward(device, eri_dev, dm_dev, 1, nset, nao, with_j, with_k, vj_dev, vk_dev, work_dev, work_doubles, stream);
+}
+
+int qexxc_dot_eri_dm_vjp(int device, const double* eri_dev, const double* vj_bar_dev, const double* vk_bar_dev,
+                         int nset, int nao, double* dm_bar_dev, double* work_dev, long work_doubles, void* stream) {
+    return jk_reverse(device, eri_dev, vj_bar_dev, vk_bar_dev, 1, nset, nao, dm_bar_dev, work_dev, work_doubles, stream);
+}
+
+int qexxc_dot_eri_dm_batched(int device, const double* eri_dev, const double* dm_dev, int nmol, int nao, int with_j,
+                             int with_k, double* vj_dev, double* vk_dev, double* work_dev, long work_doubles,
+                             void* stream) {
+    return jk_forward(device, eri_dev, dm_dev, nmol, 1, nao, with_j, with_k, vj_dev, vk_dev, work_dev, work_doubles, stream);
+}
+
+int qexxc_dot_eri_dm_vjp_batched(int device, const double* eri_dev, const double* vj_bar_dev, const double* vk_bar_dev,
+                                 int nmol, int nao, double* dm_bar_dev, double* work_dev, long work_doubles,
+                                 void* stream) {
+    return jk_reverse(device, eri_dev, vj_bar_dev, vk_bar_dev, nmol, 1, nao, dm_bar_dev, work_dev, work_doubles, stream);
 }
 
 }  // extern "C"

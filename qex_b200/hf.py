@@ -36,12 +36,12 @@ def _device_of(eri) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _workspace(lib, device: torch.device, nao: int) -> torch.Tensor:
-    key = (device.index, nao)
+def _workspace(lib, device: torch.device, nao: int, nmol: int = 1) -> torch.Tensor:
+    key = (device.index, nao, nmol)
     if key not in _work:
         n = C.c_long()
         check(lib.qexxc_jk_workspace_doubles(device.index, nao, C.byref(n)))
-        _work[key] = torch.empty(max(n.value, 1), dtype=torch.float64, device=device)
+        _work[key] = torch.empty(max(n.value * nmol, 1), dtype=torch.float64, device=device)
     return _work[key]
 
 
@@ -143,6 +143,60 @@ class _RowDot(torch.autograd.Function):
 
 def dot_eri_dm_rowdot(eri, dm):
     return _RowDot.apply(eri, dm)
+
+
+# ---- batched over molecules of equal nao (the c4 pattern: one launch for a whole dissociation curve) -------
+def dot_eri_dm_batched(eri, dm, with_j=True, with_k=True):
+    """eri [B, nao^4 ...], dm [B, nao, nao] -> (vj, vk) [B, nao, nao] with the einsums of `_dot_eri_dm_s1`
+    applied per molecule, all molecules in one launch."""
+    lib = _lib.load()
+    device = _device_of(eri)
+    nao, nmol = int(dm.shape[-1]), int(dm.shape[0])
+    e, d = _dev(eri, device), _dev(dm, device)
+    if e.numel() != nmol * nao**4 or d.numel() != nmol * nao * nao:
+        raise ValueError("eri must be [B, nao^4] and dm [B, nao, nao]")
+    vj = torch.empty_like(d) if with_j else None
+    vk = torch.empty_like(d) if with_k else None
+    w = _workspace(lib, device, nao, nmol)
+    with torch.cuda.device(device):
+        check(lib.qexxc_dot_eri_dm_batched(device.index, e.data_ptr(), d.data_ptr(), nmol, nao, int(bool(with_j)),
+                                           int(bool(with_k)), vj.data_ptr() if with_j else None,
+                                           vk.data_ptr() if with_k else None, w.data_ptr(), w.numel(), _stream(device)))
+    return vj, vk
+
+
+def _dot_eri_dm_batched_vjp(eri, nao, nmol, vj_bar=None, vk_bar=None):
+    lib = _lib.load()
+    device = _device_of(eri)
+    e = _dev(eri, device)
+    a = _dev(vj_bar, device) if vj_bar is not None else None
+    b = _dev(vk_bar, device) if vk_bar is not None else None
+    out = torch.empty(nmol, nao, nao, dtype=torch.float64, device=device)
+    w = _workspace(lib, device, nao, nmol)
+    with torch.cuda.device(device):
+        check(lib.qexxc_dot_eri_dm_vjp_batched(device.index, e.data_ptr(), a.data_ptr() if a is not None else None,
+                                               b.data_ptr() if b is not None else None, nmol, nao, out.data_ptr(),
+                                               w.data_ptr(), w.numel(), _stream(device)))
+    return out
+
+
+class _RowDotB(torch.autograd.Function):
+    """Batched `J[b,i,j] = sum_kl eri[b,i,j,k,l] dm[b,k,l]` (see `_RowDot`)."""
+
+    @staticmethod
+    def forward(ctx, eri, dm):
+        ctx.eri = eri
+        B, nao = int(dm.shape[0]), int(dm.shape[-1])
+        return _dot_eri_dm_batched_vjp(eri, nao, B, dm.contiguous(), None).transpose(-1, -2).contiguous()
+
+    @staticmethod
+    def backward(ctx, j_bar):
+        vj, _ = dot_eri_dm_batched(ctx.eri, j_bar.transpose(-1, -2).contiguous(), True, False)
+        return None, vj
+
+
+def dot_eri_dm_rowdot_batched(eri, dm):
+    return _RowDotB.apply(eri, dm)
 
 
 def make_rdm1(mo_coeff, mo_occ):

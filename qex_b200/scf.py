@@ -283,3 +283,71 @@ def scf_fixed_point(xc, theta, dm0, eri, s1e, h1e, nelectron, xctype="NN", max_c
                     diis_max_vec=8):
     """Self-consistent density matrix, differentiable w.r.t. theta by implicit differentiation."""
     return _ImplicitSCF.apply(xc, theta, dm0, eri, s1e, h1e, nelectron, xctype, max_cycle, conv_tol, diis_max_vec)
+
+
+# ---------------------------------------------------------------- batched over molecules (row N1, config c4)
+def _diis_batched(ev, fv, fock_shape, min_vecs):
+    n = len(fv)
+    if n < min_vecs:
+        return fv[-1].reshape(fock_shape)
+    E = torch.stack(ev, dim=1)  # [B, n, N*N]
+    nb = E.shape[0]
+    Bm = torch.zeros(nb, n + 1, n + 1, dtype=E.dtype, device=E.device)
+    Bm[:, 0, 1:] = -1.0
+    Bm[:, 1:, 0] = -1.0
+    Bm[:, 1:, 1:] = E @ E.transpose(-1, -2)
+    rhs = torch.zeros(nb, n + 1, dtype=E.dtype, device=E.device)
+    rhs[:, 0] = -1.0
+    c = torch.linalg.solve(Bm + 1e-14 * torch.eye(n + 1, dtype=E.dtype, device=E.device), rhs)
+    return (c[:, 1:, None] * torch.stack(fv, dim=1)).sum(1).reshape(fock_shape)
+
+
+def get_occ_batched(nelectron: int, mo_energy):
+    ranks = torch.argsort(torch.argsort(mo_energy, dim=-1), dim=-1)
+    return torch.where(ranks < nelectron // 2, 2.0, 0.0).to(mo_energy.dtype)
+
+
+def generalized_eigh_batched(A, Bm, eps: float = 1.0e-12):
+    """`generalized_eigh` for stacks [B, N, N] (per-matrix SPD shift)."""
+    A = (A + A.transpose(-1, -2)) * 0.5
+    Bm = (Bm + Bm.transpose(-1, -2)) * 0.5
+    lam_min = torch.linalg.eigvalsh(Bm.detach()).amin(-1)
+    shift = torch.clamp(eps - lam_min, min=0.0)
+    Bm = Bm + shift[:, None, None] * torch.eye(Bm.shape[-1], dtype=Bm.dtype, device=Bm.device)
+    L = torch.linalg.cholesky(Bm)
+    Y = torch.linalg.solve_triangular(L, A, upper=False)
+    Cm = torch.linalg.solve_triangular(L, Y.transpose(-1, -2), upper=False).transpose(-1, -2)
+    Cm = (Cm + Cm.transpose(-1, -2)) * 0.5
+    w, U = degen_eigh(Cm)
+    return w, torch.linalg.solve_triangular(L.transpose(-1, -2), U, upper=True)
+
+
+def get_veff_batched(xc, dm, eri, theta, xctype: str = "NN"):
+    J = hf.dot_eri_dm_rowdot_batched(eri, dm)
+    _nelec, excsum, vmat = _ag.nr_rks(xc, dm, theta, xctype, hermi=1)
+    return J + vmat, excsum, J
+
+
+def scf_loop_batched(xc, theta, dm, eri, s1e, h1e, energy_nuc, nelectron, xctype="NN", max_cycle=15, diis_max_vec=15,
+                     diis_min_vec=2, diis_start_cycle=1):
+    """`scf_loop` for B molecules of equal nao at once (XCContext with nbatch = B): every cycle is one batched
+    XC launch sequence, one batched J launch and batched N x N linear algebra.  dm, s1e, h1e: [B, N, N];
+    eri: [B, N, N, N, N]; energy_nuc: [B].  -> (e_tot [B], dm [B, N, N], energies [max_cycle, B])."""
+    def energy(d, J, exc_e):
+        return (d * h1e.transpose(-1, -2)).sum((-1, -2)) + 0.5 * (d * J).sum((-1, -2)) + exc_e + energy_nuc
+
+    vhf, exc_e, J = get_veff_batched(xc, dm, eri, theta, xctype)
+    e_tot = energy(dm, J, exc_e)
+    ev, fv, energies = [], [], []
+    for cycle in range(max_cycle):
+        fock = h1e + vhf
+        if cycle >= diis_start_cycle:
+            ev = (ev + [get_diis_error(fock, dm, s1e).reshape(fock.shape[0], -1)])[-diis_max_vec:]
+            fv = (fv + [fock.reshape(fock.shape[0], -1)])[-diis_max_vec:]
+            fock = _diis_batched(ev, fv, fock.shape, diis_min_vec)
+        mo_energy, mo_coeff = generalized_eigh_batched(fock, s1e)
+        dm = make_rdm1(mo_coeff, get_occ_batched(nelectron, mo_energy))
+        vhf, exc_e, J = get_veff_batched(xc, dm, eri, theta, xctype)
+        e_tot = energy(dm, J, exc_e)
+        energies.append(e_tot)
+    return e_tot, dm, torch.stack(energies)
