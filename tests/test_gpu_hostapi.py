@@ -213,6 +213,24 @@ def test_full_size_c5_properties():
     D = bar.cpu().numpy()[: N * N].reshape(N, N)
     assert np.array_equal(V, V.T) and np.abs(D - D.T).max() <= 1e-13 * np.abs(D).max()
     assert np.isfinite(o).all() and np.isfinite(bar.cpu().numpy()).all()
+    # the two contractions at FULL size against library GEMMs (torch.matmul -> cuBLAS DGEMM) on the same AO
+    # tensor: rho = rowdot(ao, ao sym(dm)) and V = ao^T diag(w vrho) ao, in 65536-row chunks
+    ao = ctx.get_ao(1)[0, 0]
+    S = torch.as_tensor(0.5 * (wl.dm + wl.dm.T)).cuda()
+    wt = torch.as_tensor(wl.weights).cuda()
+    _, resid = ctx.nr_rks_fwd(wl.dm, wl.theta, "NN")
+    n = resid.numel() // 4  # [rho | exc | vrho | vgamma], each GpadMax long
+    rho_k, vrho_k = resid[:G], resid[2 * n : 2 * n + G]
+    Vref = torch.zeros(N, N, dtype=torch.float64, device="cuda")
+    worst = 0.0
+    for lo in range(0, G, 65536):
+        a = ao[lo : lo + 65536]
+        r = ((a @ S) * a).sum(1)
+        worst = max(worst, (r - rho_k[lo : lo + 65536]).abs().max().item())
+        Vref += a.T @ (a * (wt[lo : lo + 65536] * vrho_k[lo : lo + 65536])[:, None])
+    assert worst <= 1e-12 * rho_k.abs().max().item()
+    assert rel_err(V, Vref.cpu().numpy()) <= 1e-11
+    del ao, Vref
     # additivity: a local functional's outputs are sums over grid points
     cut = 2048
     oa, ba = run(0, cut)
