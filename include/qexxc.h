@@ -227,6 +227,13 @@ int qexxc_dot_eri_dm_batched(int device, const double* eri_dev, const double* dm
 int qexxc_dot_eri_dm_vjp_batched(int device, const double* eri_dev, const double* vj_bar_dev, const double* vk_bar_dev,
                                  int nmol, int nao, double* dm_bar_dev, double* work_dev, long work_doubles,
                                  void* stream);
+/* ---- "next" row N3 for SMALL matrices: batched generalised symmetric eigensolver A v = w B v, n <= 16 ---------
+ * `generalized_eigh` of qedft/train/td/generalized_eigensolver.py:264-330 (symmetrise, SPD shift of B by
+ * eps - lambda_min(B) when positive, Cholesky, two triangular solves, eigh, back-transform; eigenvalues
+ * ascending, V^T B V = I) for nbatch independent problems, one thread each, no host synchronisation.
+ * a, b, v: [nbatch][n][n]; w: [nbatch][n].  n > 16 returns QEXXC_ERR_UNSUPPORTED (use cuSOLVER). */
+int qexxc_generalized_eigh_batched(int device, const double* a_dev, const double* b_dev, int nbatch, int n,
+                                   double eps, double* w_dev, double* v_dev, void* stream);
 /* kernels launched by the three J/K calls since the library was loaded */
 long qexxc_jk_launch_count(void);
 

@@ -307,8 +307,55 @@ def get_occ_batched(nelectron: int, mo_energy):
     return torch.where(ranks < nelectron // 2, 2.0, 0.0).to(mo_energy.dtype)
 
 
-def generalized_eigh_batched(A, Bm, eps: float = 1.0e-12):
-    """`generalized_eigh` for stacks [B, N, N] (per-matrix SPD shift)."""
+class _GEighSmall(torch.autograd.Function):
+    """`generalized_eigh` for stacks of small matrices (n <= 16) on the one-thread-per-matrix Jacobi kernel
+    (csrc/eigh.cu): no cuSOLVER launch chain and no host synchronisation per SCF cycle.  Backward is the
+    reference's degenerate-safe rule in the B-orthonormal basis, A_bar = sym(V (diag(w_bar) + F o (V^T V_bar)) V^T);
+    B (the overlap matrix) is treated as a constant, as it is in the SCF loop."""
+
+    @staticmethod
+    def forward(ctx, A, Bm, eps):
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        nb, n = int(A.shape[0]), int(A.shape[-1])
+        A = A.contiguous()
+        Bm = Bm.contiguous()
+        w = torch.empty(nb, n, dtype=torch.float64, device=A.device)
+        V = torch.empty(nb, n, n, dtype=torch.float64, device=A.device)
+        with torch.cuda.device(A.device):
+            _lib.check(lib.qexxc_generalized_eigh_batched(A.device.index, A.data_ptr(), Bm.data_ptr(), nb, n, float(eps),
+                                                          w.data_ptr(), V.data_ptr(),
+                                                          C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)))
+        ctx.save_for_backward(w, V)
+        return w, V
+
+    @staticmethod
+    def backward(ctx, gw, gV):
+        w, V = ctx.saved_tensors
+        Vt = V.transpose(-1, -2)
+        inner = torch.zeros_like(V)
+        if gV is not None:
+            thr = torch.finfo(w.dtype).eps ** 0.6
+            F = w.unsqueeze(-2) - w.unsqueeze(-1)
+            near = F.abs() < thr
+            Finv = torch.where(near, torch.zeros_like(F), 1.0 / torch.where(near, torch.ones_like(F), F))
+            inner = Finv * (Vt @ gV)
+        if gw is not None:
+            inner = inner + torch.diag_embed(gw)
+        res = V @ inner @ Vt
+        return (res + res.transpose(-1, -2)) * 0.5, None, None
+
+
+def generalized_eigh_batched(A, Bm, eps: float = 1.0e-12, small_kernel: bool | None = None):
+    """`generalized_eigh` for stacks [B, N, N] (per-matrix SPD shift).  N <= 16 on a CUDA device goes to the
+    batched Jacobi kernel unless `small_kernel=False`; otherwise torch.linalg (cuSOLVER)."""
+    if small_kernel is None:
+        small_kernel = A.is_cuda and A.shape[-1] <= 16 and not Bm.requires_grad
+    if small_kernel:
+        return _GEighSmall.apply(A, Bm, eps)
     A = (A + A.transpose(-1, -2)) * 0.5
     Bm = (Bm + Bm.transpose(-1, -2)) * 0.5
     lam_min = torch.linalg.eigvalsh(Bm.detach()).amin(-1)

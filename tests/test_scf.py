@@ -287,3 +287,45 @@ def test_cuda_batched_scf_matches_per_molecule_loops_and_oracle():
     # with DIIS (reference defaults): same statement as the single-molecule test
     _, _, hist_d = scf.scf_loop_batched(xb, th, torch.as_tensor(dm0).cuda(), st("eri"), st("s1e"), st("h1e"), enuc, 2)
     assert torch.isfinite(hist_d).all() and hist_d.shape == (15, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nb", [(1, 3), (2, 5), (4, 64), (7, 9), (8, 33), (13, 4), (16, 70)])
+def test_cuda_small_generalized_eigh_kernel(n, nb):
+    """csrc/eigh.cu (one thread per matrix, Jacobi) against the oracle's LAPACK route: eigenvalues, the defining
+    relations A V = B V diag(w), V^T B V = I, and the cotangent of a sign-invariant function against torch.linalg."""
+    import torch
+
+    from qex_b200 import scf
+
+    rng = np.random.default_rng(n * 100 + nb)
+    A = rng.standard_normal((nb, n, n))
+    A = A + A.transpose(0, 2, 1)
+    Bm = rng.standard_normal((nb, n, n))
+    Bm = Bm @ Bm.transpose(0, 2, 1) + n * np.eye(n)
+    if n >= 2:
+        A[0] = np.diag(np.arange(n) // 2).astype(float)  # exactly degenerate pairs
+        Bm[0] = np.eye(n)
+    At, Bt = torch.as_tensor(A).cuda().requires_grad_(True), torch.as_tensor(Bm).cuda()
+    w, V = scf.generalized_eigh_batched(At, Bt, small_kernel=True)
+    wn, Vn = w.detach().cpu().numpy(), V.detach().cpu().numpy()
+    for b in range(nb):
+        w_ref, _ = scf_ref.generalized_eigh(A[b], Bm[b])
+        assert np.abs(wn[b] - w_ref).max() <= 1e-12 * max(1.0, np.abs(w_ref).max())
+        assert np.abs(A[b] @ Vn[b] - Bm[b] @ Vn[b] * wn[b]).max() <= 1e-11 * max(1.0, np.abs(A[b]).max())
+        assert np.abs(Vn[b].T @ Bm[b] @ Vn[b] - np.eye(n)).max() <= 1e-12
+    # gradient of a function of the occupied projector and the eigenvalues (invariant to signs / rotations in
+    # non-degenerate subspaces): kernel + custom rule vs torch.linalg route + autograd
+    nocc = max(1, n // 2)
+    M = torch.as_tensor(rng.standard_normal((n, n))).cuda()
+    c = torch.as_tensor(rng.standard_normal(n)).cuda()
+
+    def f(w_, V_):
+        P = V_[..., :nocc] @ V_[..., :nocc].transpose(-1, -2)
+        return (P * (M + M.T)).sum() + (w_ * c).sum()
+
+    (g1,) = torch.autograd.grad(f(w[1:], V[1:]), At)
+    A2 = torch.as_tensor(A).cuda().requires_grad_(True)
+    w2, V2 = scf.generalized_eigh_batched(A2, Bt, small_kernel=False)
+    (g2,) = torch.autograd.grad(f(w2[1:], V2[1:]), A2)
+    assert (g1 - g2).abs().max().item() <= 1e-9 * max(1.0, g2.abs().max().item())
