@@ -298,7 +298,8 @@ def _diis_batched(ev, fv, fock_shape, min_vecs):
     Bm[:, 1:, 1:] = E @ E.transpose(-1, -2)
     rhs = torch.zeros(nb, n + 1, dtype=E.dtype, device=E.device)
     rhs[:, 0] = -1.0
-    c = torch.linalg.solve(Bm + 1e-14 * torch.eye(n + 1, dtype=E.dtype, device=E.device), rhs)
+    # solve_ex without the host-side `info` check: the loop stays asynchronous (and CUDA-graph capturable)
+    c, _ = torch.linalg.solve_ex(Bm + 1e-14 * torch.eye(n + 1, dtype=E.dtype, device=E.device), rhs, check_errors=False)
     return (c[:, 1:, None] * torch.stack(fv, dim=1)).sum(1).reshape(fock_shape)
 
 

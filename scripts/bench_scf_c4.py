@@ -65,6 +65,29 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    # the same loop as ONE CUDA graph (possible because neither the eigensolver kernel nor the DIIS solve
+    # synchronises with the host)
+    ms_graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            eg_, dmg_, histg_ = run()
+        gr.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(histg_, hist)
+        e0.record()
+        for _ in range(args.steps):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_graph = e0.elapsed_time(e1) / args.steps
+    except Exception as ex:  # capture is an optimisation, not a requirement
+        print("graph capture failed:", repr(ex)[:300], file=sys.stderr)
     launches = (int(xc.lib.qexxc_launch_count(xc._h)) + int(xc.lib.qexxc_jk_launch_count()) - n0) // args.steps
     # the same loop differentiated w.r.t. theta (what a training step of the reference does)
     thg = th.clone().requires_grad_(True)
@@ -89,6 +112,7 @@ def main():
     line = {
         "metric": "batched KS-SCF (c4): XC grid-point evaluations per second through the whole SCF loop", "unit": "grid-pts/s",
         "value": pts / (ms * 1e-3), "ms_per_scf_batch": ms, "ms_per_cycle": ms / (args.cycles + 1),
+        "ms_per_scf_batch_cuda_graph": ms_graph,
         "ms_loop_plus_theta_gradient": ms_grad, "gpu_launches_per_batch": int(launches),
         "config": {"workload": f"c4: {B} H2/6-31G geometries (0.4-3.0 A), LocalMLP 1->64->64->64->1, {args.cycles}-cycle "
                                f"KS-SCF with DIIS, {G} grid points x {N} AOs each, one batched loop", "nmol": B, "cycles": args.cycles},
