@@ -38,7 +38,8 @@ def _args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c5", choices=["c5", "c5gga", "c3", "c2", "c4", "c1"])
+    ap.add_argument("--config", default="c5", choices=["c5", "c5gga", "c3", "c2", "c4", "c1", "n2jk", "c4scf"],
+                    help="c5 = the BASELINE headline; n2jk / c4scf = the widening rows (J/K roofline, batched SCF loop)")
     ap.add_argument("--ngrids", type=int, default=None, help="override the grid size (debugging)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="network precision")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -484,9 +485,49 @@ def ctx_npad(N):  # AO row pitch: a multiple of 32 columns (zeros in the pad)
     return ((N + 31) // 32) * 32
 
 
+def run_widening(args):
+    """`--config n2jk` / `--config c4scf`: the measurements of scripts/bench_jk.py and scripts/bench_scf_c4.py
+    with their CPU baselines; bench.py is the one place that may time code under oracle/."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    if args.config == "n2jk":
+        import bench_jk
+        from oracle import jk_ref
+
+        Nc = 64
+        e_c = np.random.default_rng(0).standard_normal((Nc,) * 4)
+        d_c = np.random.default_rng(1).standard_normal((Nc, Nc))
+        t0 = time.perf_counter()
+        jk_ref.dot_eri_dm(e_c, d_c)
+        t_cpu = time.perf_counter() - t0
+        cpu = {"value": 8.0 * Nc**4 / t_cpu / 1e9, "unit": "GB/s", "cores": _cpu_threads(), "kind": "port",
+               "sample": f"numpy einsum oracle (J and K) on a [{Nc}]^4 tensor"}
+        line = bench_jk.measure(bench_jk.parse([]), cpu)
+    else:
+        import bench_scf_c4
+        from oracle import gto_ref, mlp_ref, scf_ref
+
+        def cpu_fn(mols, grids, I, theta, cycles, nc=4):
+            spec = mlp_ref.MLPSpec([1, 64, 64, 64, 1], "tanh")
+            t0 = time.perf_counter()
+            for b in range(nc):
+                ao = gto_ref.eval_ao(mols[b]._atm, mols[b]._bas, mols[b]._env, grids[b].coords, 0)
+                d0 = scf_ref.core_guess(I[b]["h1e"], I[b]["s1e"], 2)
+                scf_ref.scf_loop(d0, I[b]["eri"], ao, grids[b].weights, I[b]["s1e"], I[b]["h1e"], I[b]["enuc"], 2,
+                                 lambda rho: mlp_ref.exc_and_vrho_local(spec, theta, rho), max_cycle=cycles)
+            s_per_mol = (time.perf_counter() - t0) / nc
+            return {"value": grids[0].size * (cycles + 1) / s_per_mol, "unit": "grid-pts/s", "kind": "port",
+                    "cores": _cpu_threads(), "s_per_molecule": s_per_mol,
+                    "sample": f"numpy oracle scf_loop on {nc} of the {len(mols)} molecules"}
+
+        line = bench_scf_c4.measure(bench_scf_c4.parse([]), cpu_fn)
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = _args()
-    if a.impl == "reference":
+    if a.config in ("n2jk", "c4scf"):
+        run_widening(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

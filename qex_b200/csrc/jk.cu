@@ -100,7 +100,10 @@ struct JkOwn {
     }
 };
 
-template <bool WJ, bool WK>
+// BATCHED = false is the single-tensor instantiation: no per-molecule base pointers are kept live (at the
+// 128-register cap two more 64-bit values are enough to make ptxas split the 16 streaming loads of a slab
+// into two batches: 0.27 -> 0.35 ms for the J+K reverse kernel at nao = 120).
+template <bool WJ, bool WK, bool BATCHED>
 __global__ void __launch_bounds__(JT, 1)
 jk_fwd_kernel(const double* __restrict__ eri, const double* __restrict__ dm, int N, int TL, int rows, int npr,
               int maxseg, double* __restrict__ Jpart, double* __restrict__ Kpart, long jstride, long kstride) {
@@ -112,10 +115,12 @@ jk_fwd_kernel(const double* __restrict__ eri, const double* __restrict__ dm, int
     const long long NN = (long long)N * N;
     const long long p0 = jk_split(NN, npr, pr), p1 = jk_split(NN, npr, pr + 1);
     // blockIdx.z: molecule of a batch (its own tensor, density matrix and partial buffers)
-    eri += (long long)blockIdx.z * NN * NN;
-    dm += (long long)blockIdx.z * NN;
-    Jpart += (long long)blockIdx.z * jstride;
-    Kpart += (long long)blockIdx.z * kstride;
+    if (BATCHED) {
+        eri += (long long)blockIdx.z * NN * NN;
+        dm += (long long)blockIdx.z * NN;
+        Jpart += (long long)blockIdx.z * jstride;
+        Kpart += (long long)blockIdx.z * kstride;
+    }
     if (WK) {
         // dm[j][k] for the rows k of this chunk, stored so that a thread's JR multipliers are contiguous:
         // the K loop reads them with broadcast LDS at use time instead of holding JR more loads in registers
@@ -229,7 +234,7 @@ __global__ void jk_finish_kernel(const double* __restrict__ flat, int nflat, lon
     }
 }
 
-template <bool WJ, bool WK>
+template <bool WJ, bool WK, bool BATCHED>
 __global__ void __launch_bounds__(JT, 1)
 jk_vjp_kernel(const double* __restrict__ eri, const double* __restrict__ vjb, const double* __restrict__ vkb, int N,
               int TL, int rows, int nqr, int maxseg, double* __restrict__ DJpart, double* __restrict__ DKpart,
@@ -241,11 +246,13 @@ jk_vjp_kernel(const double* __restrict__ eri, const double* __restrict__ vjb, co
     const JkOwn o(N, TL, KG, rows, ce);
     const long long NN = (long long)N * N;
     const long long q0 = jk_split(NN, nqr, qr), q1 = jk_split(NN, nqr, qr + 1);
-    eri += (long long)blockIdx.z * NN * NN;
-    if (WJ) vjb += (long long)blockIdx.z * NN;
-    if (WK) vkb += (long long)blockIdx.z * NN;
-    DJpart += (long long)blockIdx.z * jstride;
-    DKpart += (long long)blockIdx.z * kstride;
+    if (BATCHED) {
+        eri += (long long)blockIdx.z * NN * NN;
+        if (WJ) vjb += (long long)blockIdx.z * NN;
+        if (WK) vkb += (long long)blockIdx.z * NN;
+        DJpart += (long long)blockIdx.z * jstride;
+        DKpart += (long long)blockIdx.z * kstride;
+    }
     double jb[JR], ak[JR];
 #pragma unroll
     for (int n = 0; n < JR; ++n) {
@@ -375,18 +382,25 @@ static int jk_forward(int device, const double* eri_dev, const double* dm_dev, i
     const dim3 grid(p.nchunk, p.npr, nmol);
     const size_t smem = with_k ? sizeof(double) * nao * p.KG * JR : 0;  // <= 64 KB
     if (with_k) {
-        QX_CUDA(cudaFuncSetAttribute(jk_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        QX_CUDA(cudaFuncSetAttribute(jk_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        QX_CUDA(cudaFuncSetAttribute(jk_fwd_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        QX_CUDA(cudaFuncSetAttribute(jk_fwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        QX_CUDA(cudaFuncSetAttribute(jk_fwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        QX_CUDA(cudaFuncSetAttribute(jk_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     }
+#define JK_FWD(WJV, WKV, SM)                                                                                         \
+    do {                                                                                                             \
+        if (nmol > 1)                                                                                                \
+            jk_fwd_kernel<WJV, WKV, true><<<grid, p.KG * p.TL, SM, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr,       \
+                                                                         p.maxseg, Jpart, Kpart, p.jpart, p.kpart);  \
+        else                                                                                                         \
+            jk_fwd_kernel<WJV, WKV, false><<<grid, p.KG * p.TL, SM, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr,      \
+                                                                          p.maxseg, Jpart, Kpart, p.jpart, p.kpart); \
+    } while (0)
     for (int x = 0; x < nset; ++x) {  // nset > 1 only with nmol == 1 (several density matrices, one tensor)
         const double* dm = dm_dev + x * NN;
-        if (with_j && with_k) {
-            jk_fwd_kernel<true, true><<<grid, p.KG * p.TL, smem, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr, p.maxseg, Jpart, Kpart, p.jpart, p.kpart);
-        } else if (with_j) {
-            jk_fwd_kernel<true, false><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr, p.maxseg, Jpart, Kpart, p.jpart, p.kpart);
-        } else {
-            jk_fwd_kernel<false, true><<<grid, p.KG * p.TL, smem, st>>>(eri_dev, dm, nao, p.TL, p.rows, p.npr, p.maxseg, Jpart, Kpart, p.jpart, p.kpart);
-        }
+        if (with_j && with_k) JK_FWD(true, true, smem);
+        else if (with_j) JK_FWD(true, false, 0);
+        else JK_FWD(false, true, smem);
         JK_LAUNCH_CHECK();
         const int nblk_flat = with_j ? (int)((NN + 255) / 256) : 0;
         jk_finish_kernel<<<dim3(nblk_flat + (with_k ? nao : 0), nmol), 256, 0, st>>>(
@@ -419,13 +433,19 @@ static int jk_reverse(int device, const double* eri_dev, const double* vj_bar_de
     for (int x = 0; x < nset; ++x) {
         const double* vjb = wj ? vj_bar_dev + x * NN : nullptr;
         const double* vkb = wk ? vk_bar_dev + x * NN : nullptr;
-        if (wj && wk) {
-            jk_vjp_kernel<true, true><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, p.maxseg, DJpart, DKpart, p.jpart, p.kpart);
-        } else if (wj) {
-            jk_vjp_kernel<true, false><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, p.maxseg, DJpart, DKpart, p.jpart, p.kpart);
-        } else {
-            jk_vjp_kernel<false, true><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, p.maxseg, DJpart, DKpart, p.jpart, p.kpart);
-        }
+#define JK_VJP(WJV, WKV)                                                                                             \
+    do {                                                                                                             \
+        if (nmol > 1)                                                                                                \
+            jk_vjp_kernel<WJV, WKV, true><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr,  \
+                                                                        p.maxseg, DJpart, DKpart, p.jpart, p.kpart); \
+        else                                                                                                         \
+            jk_vjp_kernel<WJV, WKV, false><<<grid, p.KG * p.TL, 0, st>>>(eri_dev, vjb, vkb, nao, p.TL, p.rows, p.npr, \
+                                                                         p.maxseg, DJpart, DKpart, p.jpart, p.kpart);\
+    } while (0)
+        if (wj && wk) JK_VJP(true, true);
+        else if (wj) JK_VJP(true, false);
+        else JK_VJP(false, true);
+#undef JK_VJP
         JK_LAUNCH_CHECK();
         double* out = dm_bar_dev + x * NN;
         jk_finish_kernel<<<dim3(nao, nmol), 256, 0, st>>>(nullptr, 0, NN, nullptr, 0, wk ? DKpart : nullptr, nao, p.npr,

@@ -4,17 +4,15 @@
 
 Prints ONE JSON line: J+K, J-only and reverse-mode times (CUDA events on the launching stream),
 algorithmic bytes = 8*nao^4 (the tensor is read exactly once per call) against the HBM peak in
-MEASURED_PEAKS.json, the library GEMV (torch.mv -> cuBLAS) on the same tensor for J alone, and
-the numpy-einsum oracle on the host as the CPU baseline.  The tensor (1.66 GB at nao = 120) is
+MEASURED_PEAKS.json, and the library GEMV (torch.mv -> cuBLAS) on the same tensor for J alone.
+`python bench.py --config n2jk` runs the same measurement and adds the CPU baseline (numpy-einsum oracle).  The tensor (1.66 GB at nao = 120) is
 far larger than the 126 MB L2, so every step streams from HBM.
 """
 import argparse
 import json
 import os
 import sys
-import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -36,13 +34,17 @@ def timed(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
-def main():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--nao", type=int, default=120)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--cpu-nao", type=int, default=64, help="size of the CPU oracle sample")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def measure(args, cpu_baseline=None):
+    """-> the JSON line as a dict.  `cpu_baseline` is filled in by `bench.py --config n2jk` (the only place
+    allowed to time the oracle); run directly, this script reports the GPU side only."""
     N = args.nao
     g = torch.Generator("cuda").manual_seed(0)
     naux = 64
@@ -70,15 +72,6 @@ def main():
         pass
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if peak else "B200_PROFILING.md fallback"
     peak = peak or 6500.0
-    # CPU baseline: the numpy-einsum oracle (reference's own subscripts) on a smaller tensor, scaled by bytes
-    from oracle import jk_ref
-
-    Nc = args.cpu_nao
-    e_c = np.random.default_rng(0).standard_normal((Nc,) * 4)
-    d_c = np.random.default_rng(1).standard_normal((Nc, Nc))
-    t0 = time.perf_counter()
-    jk_ref.dot_eri_dm(e_c, d_c)
-    t_cpu = time.perf_counter() - t0
     gbs = lambda ms: nbytes / (ms * 1e-3) / 1e9  # noqa: E731
     line = {
         "metric": "incore J/K build, ERI bytes streamed per second", "unit": "GB/s", "value": gbs(t_jk),
@@ -91,11 +84,10 @@ def main():
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes, "traffic": None,
                      "j_only_frac": gbs(t_j) / peak, "vjp_frac": gbs(t_vjp) / peak,
                      "cublas_gemv_frac": gbs(t_mv) / peak},
-        "cpu_baseline": {"value": 8.0 * Nc**4 / t_cpu / 1e9, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"numpy einsum oracle (J and K) on a [{Nc}]^4 tensor"},
+        "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    return line
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(measure(parse())))

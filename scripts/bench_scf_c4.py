@@ -6,7 +6,8 @@ LocalMLP functional, a 15-cycle KS-SCF of every molecule -- as ONE batched devic
 
 Prints ONE JSON line.  Inputs (integrals, grids, core-Hamiltonian guess) are generated on the host once;
 the timed region is the SCF loop itself with everything resident on the device, CUDA events on the
-launching stream.  CPU baseline: the numpy oracle loop (oracle/scf_ref.py) on a sample of the molecules.
+launching stream.  `python bench.py --config c4scf` runs the same measurement and adds the CPU baseline
+(the numpy oracle loop on a sample of the molecules).
 """
 import argparse
 import json
@@ -24,14 +25,18 @@ from qex_b200 import _lib, gen_grid, gto, ints, scf, workloads  # noqa: E402
 from qex_b200.engine import NetSpec, XCContext  # noqa: E402
 
 
-def main():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--nmol", type=int, default=64)
     ap.add_argument("--cycles", type=int, default=15)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--cpu-mols", type=int, default=4)
-    args = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def measure(args, cpu_baseline_fn=None):
+    """-> the JSON line as a dict.  `cpu_baseline_fn(mols, grids, ints, theta, cycles)` is supplied by
+    `bench.py --config c4scf` (the only place allowed to time the oracle loop)."""
     B = args.nmol
     bonds = np.linspace(0.4, 3.0, B)
     mols = [gto.h2(float(b), "6-31g") for b in bonds]
@@ -96,18 +101,7 @@ def main():
     (g,) = torch.autograd.grad(eg.sum(), thg)
     torch.cuda.synchronize()
     ms_grad = (time.perf_counter() - t0) * 1e3
-    # CPU baseline: oracle loop on a sample
-    from oracle import gto_ref, mlp_ref, scf_ref
-
-    spec = mlp_ref.MLPSpec([1, 64, 64, 64, 1], "tanh")
-    nc = min(args.cpu_mols, B)
-    t0 = time.perf_counter()
-    for b in range(nc):
-        ao = gto_ref.eval_ao(mols[b]._atm, mols[b]._bas, mols[b]._env, grids[b].coords, 0)
-        d0 = scf_ref.core_guess(I[b]["h1e"], I[b]["s1e"], 2)
-        scf_ref.scf_loop(d0, I[b]["eri"], ao, grids[b].weights, I[b]["s1e"], I[b]["h1e"], I[b]["enuc"], 2,
-                         lambda rho: mlp_ref.exc_and_vrho_local(spec, theta, rho), max_cycle=args.cycles)
-    cpu_s_per_mol = (time.perf_counter() - t0) / nc
+    cpu = cpu_baseline_fn(mols, grids, I, theta, args.cycles) if cpu_baseline_fn else None
     pts = B * G * (args.cycles + 1)
     line = {
         "metric": "batched KS-SCF (c4): XC grid-point evaluations per second through the whole SCF loop", "unit": "grid-pts/s",
@@ -117,12 +111,10 @@ def main():
         "config": {"workload": f"c4: {B} H2/6-31G geometries (0.4-3.0 A), LocalMLP 1->64->64->64->1, {args.cycles}-cycle "
                                f"KS-SCF with DIIS, {G} grid points x {N} AOs each, one batched loop", "nmol": B, "cycles": args.cycles},
         "dtype": "f64", "final_energy_min_max": [float(e.min()), float(e.max())],
-        "cpu_baseline": {"value": G * (args.cycles + 1) / cpu_s_per_mol, "unit": "grid-pts/s", "kind": "port",
-                         "cores": os.cpu_count(), "s_per_molecule": cpu_s_per_mol,
-                         "sample": f"numpy oracle scf_loop on {nc} of the {B} molecules"},
+        "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    return line
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(measure(parse())))

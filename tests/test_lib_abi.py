@@ -71,10 +71,11 @@ def test_bad_arguments_return_codes(lib):
 
 
 def test_product_code_does_not_import_the_oracle():
-    """The oracle is test infrastructure: nothing under qex_b200/ may reference it."""
-    pkg = os.path.join(ROOT, "qex_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                txt = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+    """The oracle is test infrastructure: nothing under qex_b200/ or scripts/ may import it (only tests/,
+    __graft_entry__.smoke() and bench.py's CPU-baseline / reference legs do)."""
+    paths = [os.path.join(d, f) for top in ("qex_b200", "scripts") for d, _, fs in os.walk(os.path.join(ROOT, top))
+             for f in fs if f.endswith((".py", ".cu", ".cuh", ".h"))]
+    assert len(paths) > 20
+    for f in paths:
+        txt = open(f).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
