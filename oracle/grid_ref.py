@@ -1,0 +1,156 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): atom-centred integration grids as pyscf builds them.
+
+The reference takes ``coords [G,3]`` / ``weights [G]`` from ``pyscf.dft.gen_grid.Grids`` with
+``level = 0`` and ``becke_scheme = stratmann`` (qedft/train/td/trainer_legacy_no_jit.py:248-251,
+:316-317; qedft/data_io/td/dataset_generation.py:139-142).  pyscf (pin ^2.9.0, pyproject.toml) is a
+third-party dependency absent from /root/reference, so this module restates its published algorithm:
+
+* radial: Treutler-Ahlrichs M4 map of Gauss-Chebyshev (2nd kind) nodes,
+  r = -xi/ln2 (1+x)^0.6 ln((1-x)/2)   [Treutler & Ahlrichs, JCP 102, 346 (1995)], xi per element;
+* angular: Lebedev-Laikov rules (``scipy.integrate.lebedev_rule``: the same octahedral point sets),
+  pruned radially by the NWChem scheme with Bragg-Slater radii;
+* partition: Becke fuzzy cells with Becke's or Stratmann-Scuseria-Frisch's switching function
+  [CPL 257, 213 (1996)], Treutler's atomic-size adjustment for heteronuclear pairs.
+
+PIN STATUS: **pinned against numbers the reference itself prints** (tests/test_zz_pyscf_pin.py):
+
+* ``build(mol H2/6-31G 0.74 A, level=0, stratmann)`` has 1240 points, the count logged by the reference's
+  notebook run (notebooks/04_notebook_td_trainer.ipynb cell 1: "Number of grid points: 1240"), and an
+  LDA-exchange RKS loop on it converges to -1.0371879478690555 against the notebook's
+  "converged SCF energy = -1.03718794786902" (|diff| < 1e-13 Ha): radial nodes AND weights, pruning,
+  Lebedev weights, the Stratmann partition, the AO evaluator, rho, the V_xc assembly and the SCF
+  loop are all inside that number;
+* with ``xi = 1`` for every element (how pyscf releases before the per-element xi table built it) the grid has
+  1192 points, the count of the same notebook's older cells, and rho(r) from the notebook's printed CCSD
+  density matrix reproduces the three tail densities it prints (6.72815113e-13, 3.23056307e-11,
+  1.63724571e-12) to 1e-8 relative (the printed dm carries 8 digits).
+
+Only H at level 0 is pinned that way; the other rows of the level / xi / radius tables are restated from the
+published papers and pyscf's documented defaults and are "parity unpinned".  The order of the points differs
+from pyscf's (which sorts them into spatial boxes and pads to a multiple of 8 with zero-weight points);
+every quantity on the path is a sum over points, so order does not enter.
+"""
+import numpy as np
+from scipy.integrate import lebedev_rule
+
+BOHR = 0.52917721092  # pyscf.data.nist.BOHR
+
+# Bragg-Slater radii (Angstrom), Z = 0..10 (pyscf.dft.radi.BRAGG_RADII, converted to Bohr below)
+_BRAGG_ANG = (0.35, 0.35, 1.40, 1.45, 1.05, 0.85, 0.70, 0.65, 0.60, 0.50, 1.50)
+BRAGG_RADII = np.array(_BRAGG_ANG) / BOHR
+# Treutler-Ahlrichs xi, Z = 0..10 (table 1 of the 1995 paper; ghost atoms take 1)
+TREUTLER_XI = (1.0, 0.8, 0.9, 1.8, 1.4, 1.3, 1.1, 0.9, 0.9, 0.9, 0.9)
+
+# pyscf.dft.gen_grid.RAD_GRIDS / ANG_ORDER: rows = level 0..9, columns = period (H-He, Li-Ne, ...)
+RAD_GRIDS = ((10, 15), (30, 40), (40, 60), (50, 75), (60, 90), (70, 105), (80, 120), (90, 135), (100, 150), (200, 200))
+ANG_ORDER = ((11, 15), (17, 23), (23, 29), (29, 29), (35, 41), (41, 47), (47, 53), (53, 59), (59, 59), (65, 65))
+LEBEDEV_ORDER = {0: 1, 3: 6, 5: 14, 7: 26, 9: 38, 11: 50, 13: 74, 15: 86, 17: 110, 19: 146, 21: 170, 23: 194,
+                 25: 230, 27: 266, 29: 302, 31: 350, 35: 434, 41: 590, 47: 770, 53: 974, 59: 1202, 65: 1454}
+LEBEDEV_NGRID = np.array(sorted(LEBEDEV_ORDER.values()))
+_ORDER_OF_NGRID = {v: k for k, v in LEBEDEV_ORDER.items()}
+
+
+def treutler_ahlrichs(n, chg, xi_table=TREUTLER_XI):
+    """-> (r [n] ascending, dr [n]) with  int f(r) dr ~= sum f(r_i) dr_i."""
+    xi = 1.0 if xi_table is None else xi_table[chg]
+    step = np.pi / (n + 1)
+    ln2 = xi / np.log(2.0)
+    t = (np.arange(n) + 1) * step
+    x = np.cos(t)
+    r = -ln2 * (1 + x) ** 0.6 * np.log((1 - x) / 2)
+    dr = step * np.sin(t) * ln2 * (1 + x) ** 0.6 * (-0.6 / (1 + x) * np.log((1 - x) / 2) + 1 / (1 - x))
+    return r[::-1].copy(), dr[::-1].copy()
+
+
+def nwchem_prune(nuc, rads, n_ang, radii=BRAGG_RADII):
+    """Number of angular points for every radial shell (NWChem's radial pruning regions)."""
+    alphas = np.array(((0.25, 0.5, 1.0, 4.5), (0.1667, 0.5, 0.9, 3.5), (0.1, 0.4, 0.8, 2.5)))
+    leb_ngrid = LEBEDEV_NGRID[4:]  # 38, 50, 74, 86, ...
+    if n_ang < 50:
+        return np.repeat(n_ang, len(rads))
+    if n_ang == 50:
+        leb_l = np.array([1, 2, 2, 2, 1])
+    else:
+        idx = int(np.where(leb_ngrid == n_ang)[0][0])
+        leb_l = np.array([1, 3, idx - 1, idx, idx - 1])
+    r_atom = radii[nuc] + 1e-200
+    row = 0 if nuc <= 2 else (1 if nuc <= 10 else 2)
+    place = ((rads / r_atom).reshape(-1, 1) > alphas[row]).sum(axis=1)
+    return leb_ngrid[leb_l[place]]
+
+
+def original_becke(g):
+    for _ in range(3):
+        g = (3 - g * g) * g * 0.5
+    return g
+
+
+def stratmann(g):
+    a = 0.64
+    ma = g / a
+    ma2 = ma * ma
+    g1 = (1 / 16.0) * (ma * (35 + ma2 * (-35 + ma2 * (21 - 5 * ma2))))
+    g1 = np.where(g <= -a, -1.0, g1)
+    return np.where(g >= a, 1.0, g1)
+
+
+def treutler_atomic_radii_adjust(charges, atomic_radii=BRAGG_RADII):
+    """-> a[i,j] of  nu = mu + a (1 - mu^2)  (zero for equal atoms)."""
+    rad = np.sqrt(atomic_radii[np.asarray(charges)]) + 1e-200
+    rr = rad.reshape(-1, 1) * (1.0 / rad)
+    return np.clip(0.25 * (rr.T - rr), -0.5, 0.5)
+
+
+def gen_atomic_grid(chg, level=0, prune=True, xi_table=TREUTLER_XI):
+    """One atom at the origin -> (coords [n,3], vol [n]); vol = 4 pi r^2 dr x Lebedev weight (sum 1)."""
+    period = 0 if chg <= 2 else 1
+    n_rad = RAD_GRIDS[level][period]
+    n_ang = LEBEDEV_ORDER[ANG_ORDER[level][period]]
+    rad, dr = treutler_ahlrichs(n_rad, chg, xi_table)
+    rad_weight = 4 * np.pi * rad**2 * dr
+    angs = nwchem_prune(chg, rad, n_ang) if prune else np.repeat(n_ang, n_rad)
+    coords, vol = [], []
+    for n in sorted(set(int(a) for a in angs)):
+        x, w = lebedev_rule(_ORDER_OF_NGRID[n])
+        idx = np.where(angs == n)[0]
+        coords.append(np.einsum("i,kj->jik", rad[idx], x).reshape(-1, 3))
+        vol.append(np.einsum("i,j->ji", rad_weight[idx], w / (4 * np.pi)).ravel())
+    return np.vstack(coords), np.hstack(vol)
+
+
+def build(atom_charges, atom_coords, level=0, becke_scheme=stratmann, prune=True, xi_table=TREUTLER_XI):
+    """pyscf ``Grids(mol); .level; .becke_scheme; .build()`` -> (coords [G,3] Bohr, weights [G])."""
+    atom_charges = np.asarray(atom_charges, dtype=int)
+    atom_coords = np.asarray(atom_coords, dtype=np.float64)
+    natm = len(atom_charges)
+    a = treutler_atomic_radii_adjust(atom_charges)
+    dist = np.linalg.norm(atom_coords[:, None] - atom_coords[None], axis=-1)
+    tab = {}
+    coords_all, weights_all = [], []
+    for ia in range(natm):
+        z = int(atom_charges[ia])
+        if z not in tab:
+            tab[z] = gen_atomic_grid(z, level, prune, xi_table)
+        c0, vol = tab[z]
+        c = c0 + atom_coords[ia]
+        gd = np.stack([np.sqrt(((c - atom_coords[j]) ** 2).sum(1)) for j in range(natm)])
+        pbecke = np.ones((natm, c.shape[0]))
+        for i in range(natm):
+            for j in range(i):
+                g = (gd[i] - gd[j]) / dist[i, j]
+                g = g + a[i, j] * (1 - g * g)
+                g = becke_scheme(g)
+                pbecke[i] *= 0.5 * (1 - g)
+                pbecke[j] *= 0.5 * (1 + g)
+        coords_all.append(c)
+        weights_all.append(vol * pbecke[ia] / pbecke.sum(axis=0))
+    return np.vstack(coords_all), np.hstack(weights_all)
+
+
+def lda_exchange(rho):
+    """libxc LDA_X, spin-unpolarised (pyscf ``xc = "lda"`` = Slater exchange alone): energy per particle
+    and potential  d(rho exc)/d rho."""
+    rho = np.maximum(np.asarray(rho, dtype=np.float64), 0.0)
+    cx = -0.75 * (3.0 / np.pi) ** (1.0 / 3.0)
+    exc = cx * np.cbrt(rho)
+    return exc, (4.0 / 3.0) * exc

@@ -1,0 +1,92 @@
+"""Pins of the XC grid-integration path against numbers the REFERENCE ITSELF holds.
+
+notebooks/04_notebook_td_trainer.ipynb (cell 1 / cell 2 outputs) freezes, for H2 / 6-31G at 0.74 A on the pyscf
+grid the trainers use (level 0, Stratmann partition: trainer_legacy_no_jit.py:248-251, dataset_generation.py:139-142):
+
+* "converged SCF energy = -1.03718794786902" of an RKS run with ``xc = "lda"`` (dataset_generation.py:385-389), on a
+  grid of 1240 points ("Number of grid points: 1240");
+* an older run's 1192-point grid with the first/last three densities of the CCSD density matrix it prints.
+
+Everything between the molecule and those numbers is on the path: grid generation, AO values, rho, E_xc, V_xc
+assembly, the SCF loop.  The oracle reproduces the energy to < 1e-12 Ha (CPU tests below), the CUDA kernels
+(AO evaluator, rho contraction, V_xc assembly through the reference-facing ``NumInt.nr_rks``) to < 1e-9 Ha.
+(The file name sorts last on purpose.)"""
+import numpy as np
+import pytest
+
+from oracle import grid_ref, gto_ref, ints_ref, scf_ref
+from qex_b200 import gen_grid, gto
+
+E_LDA_NOTEBOOK = -1.03718794786902
+DM_CCSD_NOTEBOOK = np.array([[0.23211218, 0.18285689, 0.20607785, 0.16169728],
+                             [0.18285689, 0.1546802, 0.16169728, 0.133479],
+                             [0.20607785, 0.16169728, 0.23211218, 0.18285689],
+                             [0.16169728, 0.133479, 0.18285689, 0.1546802]])
+RHO_TAIL_NOTEBOOK = (6.72815113e-13, 3.23056307e-11, 1.63724571e-12)
+
+
+def _h2():
+    m = gto.h2(0.74, "6-31g")
+    return m, ints_ref.integrals(m._atm, m._bas, m._env)
+
+
+def _nearest_rel(values, target):
+    return float(np.abs(values / target - 1.0).min())
+
+
+def test_oracle_grid_has_the_point_counts_the_notebook_logs():
+    m, _ = _h2()
+    c, w = grid_ref.build(m.atom_charges(), m.atom_coords(), level=0)
+    assert c.shape == (1240, 3) and w.shape == (1240,)
+    c, w = grid_ref.build(m.atom_charges(), m.atom_coords(), level=0, xi_table=None)
+    assert c.shape == (1192, 3)
+    # single atom: the partition is the identity and the weights integrate a Gaussian (level 3: 50 x 302 pruned)
+    c, w = grid_ref.build([1], [[0.0, 0.0, 0.0]], level=3)
+    assert abs((np.exp(-(c**2).sum(1)) * w).sum() - np.pi**1.5) < 1e-9
+
+
+def test_oracle_lda_rks_energy_matches_the_notebook():
+    m, I = _h2()
+    c, w = grid_ref.build(m.atom_charges(), m.atom_coords(), level=0, becke_scheme=grid_ref.stratmann)
+    ao = gto_ref.eval_ao(m._atm, m._bas, m._env, c, 0)
+    dm0 = scf_ref.core_guess(I["h1e"], I["s1e"], 2)
+    e, dm, hist = scf_ref.scf_loop(dm0, I["eri"], ao, w, I["s1e"], I["h1e"], I["enuc"], 2, grid_ref.lda_exchange,
+                                   max_cycle=30)
+    assert abs(hist[-1] - hist[-2]) < 1e-13
+    assert abs(e - E_LDA_NOTEBOOK) < 1e-12
+    # the plain-Becke partition or the xi = 1 radial map miss the printed value by 3e-4 / 3e-3 Ha: the pin is sharp
+    c2, w2 = grid_ref.build(m.atom_charges(), m.atom_coords(), level=0, becke_scheme=grid_ref.original_becke)
+    ao2 = gto_ref.eval_ao(m._atm, m._bas, m._env, c2, 0)
+    e2, _, _ = scf_ref.scf_loop(dm0, I["eri"], ao2, w2, I["s1e"], I["h1e"], I["enuc"], 2, grid_ref.lda_exchange, max_cycle=30)
+    assert abs(e2 - E_LDA_NOTEBOOK) > 1e-4
+
+
+def test_oracle_ao_and_rho_reproduce_the_notebook_tail_densities():
+    m, _ = _h2()
+    c, w = grid_ref.build(m.atom_charges(), m.atom_coords(), level=0, xi_table=None)  # the 1192-point run
+    ao = gto_ref.eval_ao(m._atm, m._bas, m._env, c, 0)
+    rho = np.einsum("gi,ij,gj->g", ao, DM_CCSD_NOTEBOOK, ao)
+    for t in RHO_TAIL_NOTEBOOK:
+        assert _nearest_rel(rho, t) < 3e-8  # 8 printed digits of dm, 9 of rho
+
+
+def test_host_grid_generator_matches_the_oracle_grid():
+    m, _ = _h2()
+    for kw in ({}, {"becke_scheme": "becke"}, {"level": 1}):
+        g = gen_grid.Grids(m)
+        g.level = kw.get("level", 0)
+        g.becke_scheme = gen_grid.original_becke if "becke_scheme" in kw else gen_grid.stratmann
+        g.build()
+        c, w = grid_ref.build(m.atom_charges(), m.atom_coords(), level=g.level,
+                              becke_scheme=grid_ref.original_becke if "becke_scheme" in kw else grid_ref.stratmann)
+        assert g.coords.shape == c.shape
+        assert np.abs(g.coords - c).max() < 1e-13 and np.abs(g.weights - w).max() < 1e-13
+    # heteronuclear: the atomic-size adjustment enters
+    mol = gto.Mole([("O", (0.0, 0.0, 0.0)), ("H", (0.0, 0.757, 0.587)), ("H", (0.0, -0.757, 0.587))],
+                   basis=gto.even_tempered_basis([2, 1]))
+    g = gen_grid.Grids(mol)
+    g.level = 0
+    g.build()
+    c, w = grid_ref.build(mol.atom_charges(), mol.atom_coords(), level=0, becke_scheme=grid_ref.original_becke)
+    assert np.abs(g.coords - c).max() < 1e-13 and np.abs(g.weights - w).max() < 1e-13
+    assert abs((np.exp(-((g.coords - mol.atom_coords()[0]) ** 2).sum(1)) * g.weights).sum() - np.pi**1.5) < 1e-3
