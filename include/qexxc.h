@@ -60,6 +60,10 @@ extern "C" {
 #define QEXXC_ACT_GELU 7
 #define QEXXC_ACT_SWISH 8
 
+/* switching function of the Becke partition (pyscf.dft.gen_grid.original_becke / .stratmann) */
+#define QEXXC_BECKE_ORIGINAL 0
+#define QEXXC_BECKE_STRATMANN 1
+
 #define QEXXC_PREC_F64 0
 #define QEXXC_PREC_F32 1
 
@@ -236,6 +240,22 @@ int qexxc_generalized_eigh_batched(int device, const double* a_dev, const double
                                    double eps, double* w_dev, double* v_dev, void* stream);
 /* kernels launched by the three J/K calls since the library was loaded */
 long qexxc_jk_launch_count(void);
+
+/* ---- "next" row N4: grid generation --------------------------------------------------------------------------
+ * qexxc_becke_partition: the O(G natm^2) half of `pyscf.dft.gen_grid.Grids.build()` as the reference calls it
+ * (qedft/train/td/trainer_legacy_no_jit.py:248-251, :316-317; data_io/td/dataset_generation.py:139-142 --
+ * `get_partition` / `gen_grid_partition` in pyscf): Becke fuzzy-cell weights of every grid point,
+ *     weights[g] = vol[g] * P_owner[g](r_g) / sum_i P_i(r_g).
+ * coords [G][3] (Bohr), owner [G] (index of the atom the point was generated around), vol [G] (radial x angular
+ * quadrature weight), atom_coords [natm][3], adjust [natm][natm] = Treutler's a_ij (NULL: no atomic-size
+ * adjustment), scheme = QEXXC_BECKE_ORIGINAL | QEXXC_BECKE_STRATMANN, inv_dist_work: natm*natm doubles of scratch.
+ * All pointers are device pointers.  natm is limited by shared memory (one distance per atom and thread:
+ * ~220 atoms); beyond that QEXXC_ERR_UNSUPPORTED. */
+int qexxc_becke_partition(int device, const double* coords_dev, long ngrids, const int* owner_dev,
+                          const double* vol_dev, const double* atom_coords_dev, const double* adjust_dev, int natm,
+                          int scheme, double* inv_dist_work_dev, double* weights_dev, void* stream);
+/* kernels launched by qexxc_becke_partition since the library was loaded */
+long qexxc_grid_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,16 @@ PARITY PIN STATUS
 -----------------
 The reference cannot be executed in this environment (jax, pyscf, pyscfad, horqrux,
 flax are not installable: no network, not in the wheelhouse), and its own tests hold
-no golden vectors for this path.  What *is* pinned:
+no golden vectors for this path.  Its notebooks, however, freeze
+outputs of the path, and those ARE reproduced.  What is pinned:
+
+* the whole grid -> AO -> rho -> E_xc / V_xc -> SCF chain (``grid_ref``, ``gto_ref`` s shells,
+  ``numint_ref`` conventions, ``scf_ref``): PINNED by the reference notebook's LDA-exchange RKS
+  energy of H2/6-31G on the level-0 Stratmann grid the trainers use
+  (notebooks/04_notebook_td_trainer.ipynb cell 1: "converged SCF energy = -1.03718794786902",
+  1240 grid points) -- the oracle gives -1.0371879478690555 (|diff| < 1e-13 Ha), the CUDA
+  kernels through ``NumInt.nr_rks`` < 1e-9 Ha -- and by the three tail densities the same
+  notebook prints for its CCSD density matrix (1e-8 relative); tests/test_zz_pyscf_pin.py;
 
 * contraction / assembly conventions (``numint_ref``): pinned by the closed-form toy
   functional of ``tests/test_numint.py:96-103`` (exc = 0.01 rho^2, vrho = 0.02 rho), by

@@ -41,6 +41,27 @@ def test_oracle_rhf_reproduces_the_reference_notebook_energies(R):
     assert abs(np.einsum("ij,ji", dm, I["s1e"]) - 2.0) < 1e-12
 
 
+# bond length -> "E(CCSD)" printed by the same notebook (cell 5); exact for two electrons up to pyscf's CCSD tolerance
+GOLDEN_CCSD = {0.74: -1.151672678339737, 0.5: -1.077863888625149, 1.5: -1.054347450987067,
+               0.6: -1.131953433438712, 0.9: -1.140602464558199, 1.2: -1.095595490661586}
+
+
+def _full_ci(I):
+    _, C = scf_ref.generalized_eigh(I["h1e"], I["s1e"])
+    h = C.T @ I["h1e"] @ C
+    e = np.einsum("pi,qj,rk,sl,pqrs->ijkl", C, C, C, C, I["eri"], optimize=True)
+    n = h.shape[0]
+    eye = np.eye(n)
+    H = (np.einsum("ik,jl->ijkl", h, eye) + np.einsum("ik,jl->ijkl", eye, h) + e.transpose(0, 2, 1, 3)).reshape(n * n, n * n)
+    return float(np.linalg.eigvalsh(H)[0] + I["enuc"])
+
+
+@pytest.mark.parametrize("R", list(GOLDEN_CCSD))
+def test_full_ci_of_the_oracle_integrals_reproduces_the_notebook_ccsd_energies(R):
+    _, I = _h2(R)
+    assert abs(_full_ci(I) - GOLDEN_CCSD[R]) < 3e-7
+
+
 def test_full_eri_tensor_against_the_notebook_ccsd_energy_and_density_matrix():
     """For two electrons CCSD is exact, so a 16 x 16 full-CI of the oracle integrals must give the notebook's
     E(CCSD) = -1.151672678339737 and its printed AO density matrix (both carry pyscf's CCSD convergence
