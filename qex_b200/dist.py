@@ -36,6 +36,13 @@ def shard_batch(nbatch: int, rank: int, world: int):
     return list(range(rank, nbatch, world))
 
 
+def rank_world(group=None):
+    """(rank, world) of the initialised process group, (0, 1) without one."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
 def all_reduce_packed(buf: torch.Tensor, group=None) -> torch.Tensor:
     """In-place sum over ranks of a packed output buffer; no-op without an initialised group."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

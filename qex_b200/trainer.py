@@ -26,6 +26,7 @@ import numpy as np
 import torch
 
 from . import autograd as _ag
+from . import dist as _dist
 from . import gen_grid, gto, ints, scf
 from .engine import XCContext
 from .networks import GlobalMLP, LocalMLP
@@ -145,7 +146,8 @@ class TDKSDFTTrainer:
             self._problems[key] = _BatchProblem(batch_data, self._spec(), self.device, int(self.config.get("grid_density", 0)))
         return self._problems[key]
 
-    def _loss(self, theta, batch_data, energy_weight, density_weight):
+    def _loss_sum(self, theta, batch_data, energy_weight, density_weight):
+        """Sum over the given molecules of the two per-molecule loss terms (a differentiable 0-d tensor)."""
         p = self._problem(batch_data)
         xctype = "NN-AmplitudeEncoding" if self.is_global_xc else "NN"
         e, dm, _ = scf.scf_loop_batched(p.xc, theta, p.dm0, p.eri, p.s1e, p.h1e, p.enuc, p.nelectron, xctype=xctype,
@@ -154,7 +156,24 @@ class TDKSDFTTrainer:
         loss_e = energy_weight * (e - p.e_goal) ** 2
         rho = _ag.eval_rho(p.xc, dm, 1, 1)[:, 0, :]  # [B, G]
         loss_n = density_weight * ((rho - p.rho_goal) ** 2).mean(dim=1)
-        return loss_e.mean() + loss_n.mean()
+        return loss_e.sum() + loss_n.sum()
+
+    def _loss_and_grad_flat(self, theta, batch_data, energy_weight, density_weight, want_grad=True):
+        """mean_E + mean_n of the batch (:277-281) and its theta gradient.  Under torch.distributed the molecules of
+        the batch are dealt round-robin to the ranks (`dist.shard_batch`: replicas, no data-path collective) and the
+        packed `[grad | loss]` is all-reduced once, so every rank steps the same replicated theta."""
+        rank, world = _dist.rank_world()
+        mine = [batch_data[i] for i in _dist.shard_batch(len(batch_data), rank, world)]
+        theta = theta.detach().requires_grad_(want_grad)
+        packed = torch.zeros(theta.numel() + 1, dtype=torch.float64, device=theta.device)
+        if mine:
+            with torch.set_grad_enabled(want_grad):
+                loss = self._loss_sum(theta, mine, energy_weight, density_weight) / len(batch_data)
+            if want_grad:
+                (packed[:-1],) = torch.autograd.grad(loss, theta)
+            packed[-1] = loss.detach()
+        _dist.all_reduce_packed(packed)
+        return float(packed[-1]), packed[:-1]
 
     def _theta(self, params):
         fn = _native_apply(self.network)
@@ -164,22 +183,20 @@ class TDKSDFTTrainer:
 
     def _compute_loss_and_grad(self, params, batch_data, energy_weight, density_weight):
         """-> (loss float, grads): grads is flat when ``params`` is a flat tensor, else in the stax structure."""
-        theta = self._theta(params).detach().requires_grad_(True)
-        loss = self._loss(theta, batch_data, energy_weight, density_weight)
-        (g,) = torch.autograd.grad(loss, theta)
+        loss, g = self._loss_and_grad_flat(self._theta(params), batch_data, energy_weight, density_weight)
         if isinstance(params, torch.Tensor):
-            return float(loss), g
-        return float(loss), _native_apply(self.network).unflatten(g.cpu().numpy())
+            return loss, g
+        return loss, _native_apply(self.network).unflatten(g.cpu().numpy())
 
     def _compute_validation_loss(self, params, validation_data, energy_weight, density_weight, batch_size):
         if len(validation_data) == 0:
             return 0.0
-        theta = self._theta(params).detach()
+        theta = self._theta(params)
         total, nb = 0.0, 0
-        with torch.no_grad():
-            for lo in range(0, len(validation_data), batch_size):
-                total += float(self._loss(theta, validation_data[lo : lo + batch_size], energy_weight, density_weight))
-                nb += 1
+        for lo in range(0, len(validation_data), batch_size):
+            total += self._loss_and_grad_flat(theta, validation_data[lo : lo + batch_size], energy_weight, density_weight,
+                                              want_grad=False)[0]
+            nb += 1
         return total / nb
 
     # ---- train (:395-560) ----------------------------------------------------------------------------------
