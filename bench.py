@@ -38,7 +38,7 @@ def _args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c5", choices=["c5", "c5gga", "c3", "c2", "c4", "c1", "n2jk", "c4scf"],
+    ap.add_argument("--config", default="c5", choices=["c5", "c5gga", "c3", "c2", "c4", "c1", "n2jk", "c4scf", "c1train"],
                     help="c5 = the BASELINE headline; n2jk / c4scf = the widening rows (J/K roofline, batched SCF loop)")
     ap.add_argument("--ngrids", type=int, default=None, help="override the grid size (debugging)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="network precision")
@@ -502,6 +502,24 @@ def run_widening(args):
         cpu = {"value": 8.0 * Nc**4 / t_cpu / 1e9, "unit": "GB/s", "cores": _cpu_threads(), "kind": "port",
                "sample": f"numpy einsum oracle (J and K) on a [{Nc}]^4 tensor"}
         line = bench_jk.measure(bench_jk.parse([]), cpu)
+    elif args.config == "c1train":
+        import bench_train
+        from oracle import mlp_ref, train_ref
+        from qex_b200 import gto
+
+        def cpu_train(bonds, cycles, is_global):
+            data = train_ref.make_dataset([gto.h2(b, "6-31g") for b in bonds], level=0)
+            G = data[0][1].shape[0]
+            spec = mlp_ref.MLPSpec([G if is_global else 1, 64, 64, 64, 1], "tanh")
+            theta = mlp_ref.pack(*mlp_ref.init_params(spec, 0))
+            t0 = time.perf_counter()
+            train_ref.batch_loss(theta, spec, data, 1.0, 1.0, is_global=is_global, max_cycle=cycles)
+            t = time.perf_counter() - t0
+            return {"value": 1.0 / t, "unit": "it/s", "cores": _cpu_threads(), "kind": "port",
+                    "sample": "ONE forward evaluation of the batch loss by the numpy restatement (no gradient: the "
+                              "reference's step adds a reverse pass, so this over-states its rate)"}
+
+        line = bench_train.measure(bench_train.parse([]), cpu_train)
     else:
         import bench_scf_c4
         from oracle import gto_ref, mlp_ref, scf_ref
@@ -525,7 +543,7 @@ def run_widening(args):
 
 if __name__ == "__main__":
     a = _args()
-    if a.config in ("n2jk", "c4scf"):
+    if a.config in ("n2jk", "c4scf", "c1train"):
         run_widening(a)
     elif a.impl == "reference":
         run_reference(a)

@@ -1,0 +1,77 @@
+"""README 3D example as a device-resident training step (BASELINE.json configs[0]): H2 at 0.74 / 0.5 / 1.5 A, 6-31G,
+level-0 Stratmann grids (1240 points), batch 3, `max_cycle`-cycle KS-SCF per molecule, energy + density loss,
+theta gradient, Adam update -- `qex_b200.trainer.TDKSDFTTrainer._compute_loss_and_grad` + `adam_update`.
+CUDA events around `steps` iterations after `warmup`; prints one JSON line.  `bench.py --config c1train` adds the
+CPU baseline (the numpy restatement of the loss; bench.py is the only place allowed to time oracle code)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qex_b200 import gen_grid, gto, trainer  # noqa: E402
+from qex_b200.networks import GlobalMLP, LocalMLP  # noqa: E402
+
+
+def parse(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cycles", type=int, default=20)
+    ap.add_argument("--global-xc", action="store_true", help="GlobalMLP / NN-AmplitudeEncoding (README default)")
+    return ap.parse_args(argv)
+
+
+def measure(args, cpu_baseline_fn=None):
+    bonds = [0.74, 0.5, 1.5]
+    g = gen_grid.Grids(gto.h2(0.74, "6-31g"))
+    g.level = 0
+    g.becke_scheme = gen_grid.stratmann
+    g.build()
+    net = (GlobalMLP if args.global_xc else LocalMLP)().build_network(g.coords)
+    tr = trainer.TDKSDFTTrainer(dict(train_bond_lengths=bonds, val_bond_lengths=[], batch_size=3, max_cycle=args.cycles,
+                                     is_global_xc=args.global_xc), network=net, seed=0)
+    train, _ = tr.prepare_dataset()
+    theta = tr._theta(net[0](0, None)[1])
+    state = trainer.adam_init(theta)
+
+    def step(theta, state):
+        loss, grad = tr._compute_loss_and_grad(theta, train, 1.0, 1.0)
+        theta, state = trainer.adam_update(grad, state, theta, 1e-3)
+        return loss, theta, state
+
+    losses = []
+    for _ in range(max(3, args.warmup)):
+        loss, theta, state = step(theta, state)
+        losses.append(loss)
+    torch.cuda.synchronize()
+    xc = tr._problem(train).xc
+    n0 = int(xc.lib.qexxc_launch_count(xc._h)) + int(xc.lib.qexxc_jk_launch_count())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, theta, state = step(theta, state)
+        losses.append(loss)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (int(xc.lib.qexxc_launch_count(xc._h)) + int(xc.lib.qexxc_jk_launch_count()) - n0) // args.steps
+    G = g.size
+    cpu = cpu_baseline_fn(bonds, args.cycles, args.global_xc) if cpu_baseline_fn else None
+    return {
+        "metric": "training iterations per second (README 3D H2 example: batch 3, KS-SCF + energy/density loss + grad + Adam)",
+        "unit": "it/s", "value": 1e3 / ms, "ms_per_iteration": ms, "gpu_launches_per_iteration": int(launches),
+        "grid_pts_per_s": 3 * G * (args.cycles + 1) / (ms * 1e-3),
+        "losses_first_last": [losses[0], losses[-1]], "loss_decreased": bool(losses[-1] < losses[0]),
+        "config": {"workload": f"c1 as a training step: 3 H2/6-31G geometries, {G} grid points x 4 AOs, "
+                               f"{'GlobalMLP' if args.global_xc else 'LocalMLP'} 64x3 tanh, {args.cycles}-cycle KS-SCF with DIIS",
+                   "steps": args.steps, "warmup": max(3, args.warmup)},
+        "dtype": "f64", "cpu_baseline": cpu,
+    }
+
+
+if __name__ == "__main__":
+    print(json.dumps(measure(parse())))
