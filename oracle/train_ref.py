@@ -56,14 +56,18 @@ def _veff(dm, eri, ao, w, exc_vrho, is_global):
     return J + Vxc, exc_e, J
 
 
-def ks_scf(theta, spec, I, ao, w, nelectron=2, is_global=False, max_cycle=15, diis=True):
-    """-> (e_tot, dm) of the fixed-cycle KS loop with the MLP functional."""
+def mlp_functional(spec, is_global=False):
+    """-> functional(theta, rho) = (exc, vrho) of trainer_legacy_no_jit.py:46-63 for an MLP spec."""
     if is_global:
-        def exc_vrho(rho):
-            return mlp_ref.exc_and_vrho_global(spec, theta, rho)
-    else:
-        def exc_vrho(rho):
-            return mlp_ref.exc_and_vrho_local(spec, theta, rho)
+        return lambda theta, rho: mlp_ref.exc_and_vrho_global(spec, theta, rho)
+    return lambda theta, rho: mlp_ref.exc_and_vrho_local(spec, theta, rho)
+
+
+def ks_scf(theta, functional, I, ao, w, nelectron=2, is_global=False, max_cycle=15, diis=True):
+    """-> (e_tot, dm) of the fixed-cycle KS loop; ``functional(theta, rho) -> (exc, vrho)``."""
+    def exc_vrho(rho):
+        return functional(theta, rho)
+
     dm = scf_ref.core_guess(I["h1e"], I["s1e"], nelectron)
     vhf, exc_e, J = _veff(dm, I["eri"], ao, w, exc_vrho, is_global)
     st = scf_ref.initialize_diis(15)
@@ -79,11 +83,14 @@ def ks_scf(theta, spec, I, ao, w, nelectron=2, is_global=False, max_cycle=15, di
     return e_tot, dm
 
 
-def batch_loss(theta, spec, batch, energy_weight=1.0, density_weight=1.0, is_global=False, max_cycle=15, diis=True):
-    """trainer_legacy_no_jit.py:240-283 -> scalar loss of one batch of ``make_dataset`` entries."""
+def batch_loss(theta, functional, batch, energy_weight=1.0, density_weight=1.0, is_global=False, max_cycle=15, diis=True):
+    """trainer_legacy_no_jit.py:240-283 -> scalar loss of one batch of ``make_dataset`` entries.
+    ``functional``: ``mlp_functional(spec, is_global)`` or any ``(theta, rho) -> (exc, vrho)``; an ``MLPSpec`` is accepted."""
+    if isinstance(functional, mlp_ref.MLPSpec):
+        functional = mlp_functional(functional, is_global)
     le, ln = [], []
     for e_goal, density_goal, _mol, x in batch:
-        e, dm = ks_scf(theta, spec, x["I"], x["ao"], x["weights"], 2, is_global, max_cycle, diis)
+        e, dm = ks_scf(theta, functional, x["I"], x["ao"], x["weights"], 2, is_global, max_cycle, diis)
         le.append(energy_weight * (e - e_goal) ** 2)
         rho = np.einsum("gi,ij,gj->g", x["ao"], dm, x["ao"])
         ln.append(density_weight * np.mean((rho - density_goal[:, 3]) ** 2))

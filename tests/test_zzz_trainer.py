@@ -72,15 +72,18 @@ def test_trainer_rejects_unknown_methods():
         t._generate(0.74)
 
 
-def _trainer(cfg, is_global):
+def _trainer(cfg, is_global, qnn=False):
     from qex_b200 import gen_grid, trainer
-    from qex_b200.networks import GlobalMLP, LocalMLP
+    from qex_b200.networks import GlobalMLP, LocalMLP, LocalQNN
 
     g = gen_grid.Grids(gto.h2(0.74, "6-31g"))
     g.level = 0
     g.becke_scheme = gen_grid.stratmann
     g.build()
-    net = (GlobalMLP if is_global else LocalMLP)().build_network(g.coords)
+    if qnn:
+        net = LocalQNN({"n_qubits": 6, "n_layers": 2}).build_network(g.coords)
+    else:
+        net = (GlobalMLP if is_global else LocalMLP)().build_network(g.coords)
     return trainer.TDKSDFTTrainer(dict(cfg, is_global_xc=is_global), network=net, seed=0)
 
 
@@ -134,3 +137,34 @@ def test_cuda_trainer_trains_end_to_end(lib):
     assert len(tl) == 8 and len(vl) == 2 and opt_state["count"] == 8
     assert all(np.isfinite(tl)) and tl[-1] < tl[0]
     assert len(params) == 7 and params[0][0].shape == (1, 64)
+
+
+@pytest.mark.gpu
+def test_cuda_training_step_with_the_local_qnn_functional(lib, dataset):
+    """BASELINE.json configs[1] as a training step: H2 KS-SCF with the LocalQNN functional (6 qubits, 2 hea layers, 36
+    parameters) at every grid point; loss against the numpy statevector restatement, gradient against its central
+    differences along two directions and, with only 36 parameters, a few single coordinates."""
+    import torch
+
+    from oracle import qnn_ref
+
+    tr = _trainer(dict(max_cycle=4, diis_start_cycle=10**6), is_global=False, qnn=True)
+    qspec = qnn_ref.QNNSpec(6, 2)
+    theta = np.random.default_rng(2).uniform(-0.1, 0.1, 36)
+    batch = [(e, d, m, dict(I=x["I"])) for e, d, m, x in dataset]
+
+    def ref(th):
+        return train_ref.batch_loss(th, lambda t, rho: qnn_ref.exc_and_vrho_local(qspec, t, rho), dataset, 1.0, 1.0,
+                                    max_cycle=4, diis=False)
+
+    loss, grad = tr._compute_loss_and_grad(torch.as_tensor(theta), batch, 1.0, 1.0)
+    l0 = ref(theta)
+    assert abs(loss - l0) < 1e-10 * max(1.0, abs(l0))
+    grad = grad.cpu().numpy()
+    rng = np.random.default_rng(8)
+    dirs = [rng.standard_normal(36) for _ in range(2)] + [np.eye(36)[k] for k in (0, 17, 35)]
+    for d in dirs:
+        d = d / np.linalg.norm(d)
+        h = 1e-5
+        fd = (ref(theta + h * d) - ref(theta - h * d)) / (2 * h)
+        assert abs(fd - grad @ d) < 1e-6 * max(1.0, abs(fd))
