@@ -8,7 +8,6 @@ import json
 import os
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -59,46 +58,21 @@ def measure(args, cpu_baseline_fn=None):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (int(xc.lib.qexxc_launch_count(xc._h)) + int(xc.lib.qexxc_jk_launch_count()) - n0) // args.steps
-    # the same iteration (forward, reverse, Adam) as ONE CUDA graph: nothing in it synchronises with the host once the
-    # step counter of Adam's bias correction lives on the device
+    # the same iteration (forward, reverse, Adam) as ONE CUDA graph (`config["cuda_graph"]` of the trainer)
     ms_graph, graph_note = None, None
     try:
-        s_theta = theta.detach().clone()
-        s_mu, s_nu = state["mu"].clone(), state["nu"].clone()
-        s_count = torch.full((), float(state["count"]), dtype=torch.float64, device=theta.device)
-        s_loss = torch.zeros((), dtype=torch.float64, device=theta.device)
-
-        def graph_step():
-            th = s_theta.detach().requires_grad_(True)
-            loss = tr._loss_sum(th, train, 1.0, 1.0) / len(train)
-            (gr,) = torch.autograd.grad(loss, th)
-            s_count.add_(1.0)
-            s_mu.mul_(0.9).add_(gr, alpha=0.1)
-            s_nu.mul_(0.999).addcmul_(gr, gr, value=0.001)
-            mhat = s_mu / (1.0 - torch.pow(torch.full_like(s_count, 0.9), s_count))
-            vhat = s_nu / (1.0 - torch.pow(torch.full_like(s_count, 0.999), s_count))
-            s_theta.sub_(1e-3 * mhat / (torch.sqrt(vhat) + 1e-8))
-            s_loss.copy_(loss.detach())
-
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                graph_step()
-        torch.cuda.current_stream().wait_stream(side)
-        gr_ = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr_):
-            graph_step()
-        gr_.replay()
+        shared = dict(theta=theta.detach().clone(), mu=state["mu"].clone(), nu=state["nu"].clone(),
+                      count=torch.full((), float(state["count"]), dtype=torch.float64, device=theta.device))
+        gi = trainer._GraphedIteration(tr, train, 1.0, 1.0, 1e-3, shared)
+        l_a = float(gi.replay())
         torch.cuda.synchronize()
-        l_a = float(s_loss)
         e0.record()
         for _ in range(args.steps):
-            gr_.replay()
+            l_b = gi.replay()
         e1.record()
         torch.cuda.synchronize()
         ms_graph = e0.elapsed_time(e1) / args.steps
-        graph_note = {"loss_after_capture": l_a, "loss_after_replays": float(s_loss)}
+        graph_note = {"loss_first_replay": l_a, "loss_last_replay": float(l_b)}
     except Exception as ex:  # capture is an optimisation, not a requirement
         graph_note = "graph capture failed: " + repr(ex)[:300]
     G = g.size

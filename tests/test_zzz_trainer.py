@@ -140,6 +140,24 @@ def test_cuda_trainer_trains_end_to_end(lib):
 
 
 @pytest.mark.gpu
+def test_cuda_graph_training_equals_stream_training(lib, dataset):
+    """`cuda_graph=True` replays forward + reverse + Adam of an iteration as one CUDA graph: same losses, same
+    parameters, same optimiser state as the stream-launched loop (two batches, so two graphs share one optimiser)."""
+    cfg = dict(n_iterations=4, batch_size=2, learning_rate=1e-3, max_cycle=6, validation_interval=2)
+    data = [(e, d, m, dict(I=x["I"])) for e, d, m, x in dataset]
+    out = []
+    for graph in (False, True):
+        tr = _trainer(dict(cfg, cuda_graph=graph), is_global=False)
+        params, st, tl, vl = tr.train(data, data[:1])
+        out.append((tr.network[1].flatten(params), st, tl, vl))
+    (p0, s0, t0, v0), (p1, s1, t1, v1) = out
+    assert s0["count"] == s1["count"] == 8
+    assert np.abs(np.array(t0) - np.array(t1)).max() < 1e-11 and np.abs(np.array(v0) - np.array(v1)).max() < 1e-11
+    assert np.abs(p0 - p1).max() < 1e-10
+    assert np.abs((s0["mu"] - s1["mu"]).cpu().numpy()).max() < 1e-10
+
+
+@pytest.mark.gpu
 def test_cuda_training_step_with_the_local_qnn_functional(lib, dataset):
     """BASELINE.json configs[1] as a training step: H2 KS-SCF with the LocalQNN functional (6 qubits, 2 hea layers, 36
     parameters) at every grid point; loss against the numpy statevector restatement, gradient against its central
