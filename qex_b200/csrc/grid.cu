@@ -60,18 +60,38 @@ becke_partition_kernel(const double* __restrict__ coords, long ngrids, const int
             dcol[j * kTpb + threadIdx.x] = sqrt(dx * dx + dy * dy + dz * dz);
         }
         const int own = owner[g];
+        if (SCHEME == 1 && adjust == nullptr) {
+            // Stratmann's screening (CPL 257, 213, eq. 15): within 1/2 (1 - a) of the nearest neighbour every mu_own,j
+            // is below -a, so P_own = 1 and all other cells vanish -- exactly what the loops below would compute
+            double inv_nn = 0.0;
+            for (int j = 0; j < natm; ++j) inv_nn = fmax(inv_nn, ir[own * natm + j]);
+            if (dcol[own * kTpb + threadIdx.x] * inv_nn < 0.5 * (1.0 - 0.64)) {
+                weights[g] = vol[g];
+                continue;
+            }
+        }
+        auto cell = [&](int i, int j, double di) -> double {
+            double mu = (di - dcol[j * kTpb + threadIdx.x]) * ir[i * natm + j];
+            if (adjust != nullptr) mu += adjust[i * natm + j] * (1.0 - mu * mu);
+            const double s = SCHEME == 0 ? switch_becke(mu) : switch_stratmann(mu);
+            return 0.5 * (1.0 - s);
+        };
         double psum = 0.0, pown = 0.0;
         for (int i = 0; i < natm; ++i) {
             const double di = dcol[i * kTpb + threadIdx.x];
-            double p = 1.0;
-            for (int j = 0; j < natm; ++j) {
-                if (j == i) continue;
-                double mu = (di - dcol[j * kTpb + threadIdx.x]) * ir[i * natm + j];
-                if (adjust != nullptr) mu += adjust[i * natm + j] * (1.0 - mu * mu);
-                const double s = SCHEME == 0 ? switch_becke(mu) : switch_stratmann(mu);
-                p *= 0.5 * (1.0 - s);
-                if (p == 0.0) break;  // Stratmann's switch is exactly 1 beyond a = 0.64
+            // the factor against the owner first: with Stratmann's switch it is exactly zero for most atoms, which
+            // ends their product after one pair term; two interleaved partial products shorten the FP64 chain
+            double p0 = i == own ? 1.0 : cell(i, own, di), p1 = 1.0;
+            if (p0 != 0.0) {
+                for (int j = 0; j < natm; ++j) {
+                    if (j == i || j == own) continue;
+                    const double c = cell(i, j, di);
+                    if (j & 1) p1 *= c;
+                    else p0 *= c;
+                    if (c == 0.0) break;
+                }
             }
+            const double p = p0 * p1;
             psum += p;
             if (i == own) pown = p;
         }

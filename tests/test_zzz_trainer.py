@@ -143,18 +143,24 @@ def test_cuda_trainer_trains_end_to_end(lib):
 def test_cuda_graph_training_equals_stream_training(lib, dataset):
     """`cuda_graph=True` replays forward + reverse + Adam of an iteration as one CUDA graph: same losses, same
     parameters, same optimiser state as the stream-launched loop (two batches, so two graphs share one optimiser)."""
-    cfg = dict(n_iterations=4, batch_size=2, learning_rate=1e-3, max_cycle=6, validation_interval=2)
     data = [(e, d, m, dict(I=x["I"])) for e, d, m, x in dataset]
-    out = []
-    for graph in (False, True):
-        tr = _trainer(dict(cfg, cuda_graph=graph), is_global=False)
-        params, st, tl, vl = tr.train(data, data[:1])
-        out.append((tr.network[1].flatten(params), st, tl, vl))
-    (p0, s0, t0, v0), (p1, s1, t1, v1) = out
-    assert s0["count"] == s1["count"] == 8
-    assert np.abs(np.array(t0) - np.array(t1)).max() < 1e-11 and np.abs(np.array(v0) - np.array(v1)).max() < 1e-11
-    assert np.abs(p0 - p1).max() < 1e-10
-    assert np.abs((s0["mu"] - s1["mu"]).cpu().numpy()).max() < 1e-10
+    # plain SCF iteration: strict.  With DIIS the extrapolation solve is ill-conditioned and amplifies last-bit differences
+    # (torch.pow on the device vs Python's pow in Adam's bias correction, library algorithm choices under capture) to
+    # ~1e-7 in the loss -- the same scatter tests/test_scf.py documents for LAPACK vs cuSOLVER
+    for diis_start, tol in ((10**6, 1e-10), (1, 1e-5)):
+        cfg = dict(n_iterations=4, batch_size=2, learning_rate=1e-3, max_cycle=6, validation_interval=2,
+                   diis_start_cycle=diis_start)
+        out = []
+        for graph in (False, True):
+            tr = _trainer(dict(cfg, cuda_graph=graph), is_global=False)
+            params, st, tl, vl = tr.train(data, data[:1])
+            out.append((tr.network[1].flatten(params), st, tl, vl))
+        (p0, s0, t0, v0), (p1, s1, t1, v1) = out
+        assert s0["count"] == s1["count"] == 8
+        assert np.abs(np.array(t0) - np.array(t1)).max() < tol and np.abs(np.array(v0) - np.array(v1)).max() < tol
+        assert np.abs(p0 - p1).max() < 10 * tol
+        assert np.abs((s0["mu"] - s1["mu"]).cpu().numpy()).max() < 10 * tol * max(1.0, float(s0["mu"].abs().max()))
+        assert t0[-1] < t0[0]
 
 
 @pytest.mark.gpu
