@@ -34,6 +34,13 @@ _LEB_NGRID = np.array((1, 6, 14, 26, 38, 50, 74, 86, 110, 146, 170, 194, 230, 26
 _LEB_ORDER = np.array((0, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23, 25, 27, 29, 31, 35, 41, 47, 53, 59, 65))
 
 
+_SYMBOLS = ("X", "H", "He", "Li", "Be", "B", "C", "N", "O", "F", "Ne")
+
+
+def _charge_of(key) -> int:
+    return _SYMBOLS.index(key) if isinstance(key, str) else int(key)
+
+
 # ---------------------------------------------------------------- switching functions (pyscf names)
 def original_becke(g):
     """Becke's three-fold iterated p(x) = (3x - x^3)/2."""
@@ -223,13 +230,19 @@ class Grids:
         self.coords = None if coords is None else np.asarray(coords, dtype=np.float64)
         self.weights = None if weights is None else np.asarray(weights, dtype=np.float64)
 
-    def build(self, device=None, **kwargs):
-        """``device=None``: partition on the host (NumPy); ``device=k``: on GPU k (csrc/grid.cu)."""
+    def build(self, mol=None, with_non0tab=False, sort_grids=True, device=None, **kwargs):
+        """pyscf's ``Grids.build(mol=None, with_non0tab=False, sort_grids=True)`` plus ``device``:
+        ``device=None`` partitions on the host (NumPy), ``device=k`` on GPU k (csrc/grid.cu).  ``with_non0tab`` /
+        ``sort_grids`` are accepted and ignored: no screening table is built and the points keep generation order."""
+        del with_non0tab, sort_grids, kwargs
+        if mol is not None:
+            self.mol = mol
         if self.n_rad is not None:
             return self._build_product()
         charges = np.asarray(self.mol.atom_charges(), dtype=int)
         centers = np.asarray(self.mol.atom_coords(), dtype=np.float64)
-        tab = gen_atomic_grids(charges, self.level, self.prune, self.atom_grid)
+        atom_grid = {_charge_of(k): tuple(v) for k, v in (self.atom_grid or {}).items()}  # pyscf keys by symbol
+        tab = gen_atomic_grids(charges, self.level, self.prune, atom_grid)
         coords = np.concatenate([tab[int(z)][0] + centers[ia] for ia, z in enumerate(charges)])
         vol = np.concatenate([tab[int(z)][1] for z in charges])
         owner = np.concatenate([np.full(tab[int(z)][1].shape[0], ia, dtype=np.int32) for ia, z in enumerate(charges)])

@@ -90,6 +90,13 @@ def test_host_grid_generator_matches_the_oracle_grid():
     c, w = grid_ref.build(mol.atom_charges(), mol.atom_coords(), level=0, becke_scheme=grid_ref.original_becke)
     assert np.abs(g.coords - c).max() < 1e-13 and np.abs(g.weights - w).max() < 1e-13
     assert abs((np.exp(-((g.coords - mol.atom_coords()[0]) ** 2).sum(1)) * g.weights).sum() - np.pi**1.5) < 1e-2
+    # pyscf's calling conventions: build(mol) positionally, atom_grid keyed by element symbol, prune switched off
+    g2 = gen_grid.Grids(None)
+    g2.atom_grid = {"H": (12, 26), "O": (15, 50)}
+    g2.prune = None
+    g2.build(mol, with_non0tab=True)
+    assert g2.size == 2 * 12 * 26 + 15 * 50
+    assert abs((np.exp(-((g2.coords - mol.atom_coords()[1]) ** 2).sum(1)) * g2.weights).sum() - np.pi**1.5) < 5e-2
 
 
 # ---------------------------------------------------------------------------------------------- CUDA path
