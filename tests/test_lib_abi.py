@@ -68,6 +68,26 @@ def test_bad_arguments_return_codes(lib):
     assert lib.qexxc_create(C.byref(h), 0, 1, 3, 128, 4, None) == _lib.ERR_ARG
     assert lib.qexxc_nr_rks_fwd(None, 0, 0, None, None, None, None, None) == _lib.ERR_ARG
     assert lib.qexxc_destroy(None) == 0
+    # grid partition: argument checks come before any device work; an empty grid is a no-op
+    assert lib.qexxc_becke_partition(0, None, 10, None, None, None, None, 0, 0, None, None, None) == _lib.ERR_ARG
+    assert lib.qexxc_becke_partition(0, None, 10, None, None, None, None, 2, 7, None, None, None) == _lib.ERR_ARG
+    assert lib.qexxc_becke_partition(0, None, 10, None, None, None, None, 2, 1, None, None, None) == _lib.ERR_ARG
+    assert b"null device pointer" in lib.qexxc_last_error()
+    assert lib.qexxc_becke_partition(0, None, 0, None, None, None, None, 2, 1, None, None, None) == 0
+
+
+def test_grid_build_on_a_device_is_loud_without_one():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from qex_b200 import gen_grid, gto
+
+    g = gen_grid.Grids(gto.h2(0.74, "6-31g"))
+    g.level = 0
+    with pytest.raises(RuntimeError):
+        g.build(device=0)
+    assert g.build().size == 1240  # the host partition is set-up code and needs no device
 
 
 def test_product_code_does_not_import_the_oracle():
