@@ -257,6 +257,14 @@ int qexxc_becke_partition(int device, const double* coords_dev, long ngrids, con
 /* kernels launched by qexxc_becke_partition since the library was loaded */
 long qexxc_grid_launch_count(void);
 
+/* ---- analytic LDA exchange (libxc LDA_X, unpolarised): the functional of pyscf's `xc = "lda"` -------------------
+ * What `ni.eval_xc("lda", rho, ...)` returns inside the reference's nr_rks (numint_legacy.py LDA branch; run by
+ * dataset_generation.py:385-389): exc[g] = -3/4 (3/pi)^(1/3) rho^(1/3) (energy per particle),
+ * vrho[g] = d(rho exc)/d rho = 4/3 exc.  rho, exc, vrho: npts doubles on the device (any batch layout, flat).
+ * Feed the result to qexxc_vxc_assemble with xctype QEXXC_XC_NN (the same assembly as the LDA branch). */
+int qexxc_lda_exchange(int device, const double* rho_dev, long npts, double* exc_dev, double* vrho_dev, void* stream);
+long qexxc_lda_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

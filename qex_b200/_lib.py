@@ -30,7 +30,7 @@ EXPORTS = [
     "qexxc_debug_run_contraction", "qexxc_profile_enable", "qexxc_profile_read", "qexxc_contraction_flops", "qexxc_eval_rho_mo", "qexxc_nr_rks_fwd_mo",
     "qexxc_jk_workspace_doubles", "qexxc_dot_eri_dm", "qexxc_dot_eri_dm_vjp", "qexxc_jk_launch_count",
     "qexxc_dot_eri_dm_batched", "qexxc_dot_eri_dm_vjp_batched", "qexxc_generalized_eigh_batched",
-    "qexxc_becke_partition", "qexxc_grid_launch_count",
+    "qexxc_becke_partition", "qexxc_grid_launch_count", "qexxc_lda_exchange", "qexxc_lda_launch_count",
 ]
 
 
@@ -107,6 +107,8 @@ def load(build_if_missing: bool = False):
         "qexxc_generalized_eigh_batched": (i, [i, p, p, i, i, d, p, p, vp]),
         "qexxc_becke_partition": (i, [i, p, l, p, p, p, p, i, i, p, p, vp]),
         "qexxc_grid_launch_count": (l, []),
+        "qexxc_lda_exchange": (i, [i, p, l, p, p, vp]),
+        "qexxc_lda_launch_count": (l, []),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

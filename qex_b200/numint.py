@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from .engine import NetSpec, XCContext
-from .xc import _native_apply, _theta
+from .xc import LDA_EXCHANGE_CODES, _native_apply, _theta, lda_exchange
 from .xc import eval_xc as _native_eval_xc
 
 
@@ -51,6 +51,8 @@ def _xctype(ni, xc_code):
         return xc_code
     if isinstance(xc_code, str) and xc_code.upper() in ("LDA", "GGA"):
         return xc_code.upper()
+    if isinstance(xc_code, str) and xc_code.lower().replace(" ", "") in LDA_EXCHANGE_CODES:
+        return "LDA"  # pyscf's _xc_type of Slater exchange
     t = getattr(ni, "_xc_type_override", None)
     if t is not None:
         return t
@@ -200,12 +202,22 @@ class NumInt:
                 nelec.append(float(o[N * N + 1]))
                 resids.append(resid)
         else:
-            if not callable(self.eval_xc):
+            builtin_lda = not callable(self.eval_xc) and xctype == "LDA"
+            if not callable(self.eval_xc) and not builtin_lda:
                 raise ValueError("NumInt.eval_xc is not set: install a functional first (define_xc_)")
             ctx = self._ctx(N, G, ncomp, None)
             self._load(ctx, mol, grids, 1 if gga else 0)
             for dm in dm_list:
                 rho = ctx.eval_rho_mo(mo_coeff, mo_occ) if use_mo else ctx.eval_rho(dm, ncomp, hermi)
+                if builtin_lda:
+                    # the reference's libxc route for xc_code "lda" (Slater exchange), all on the device
+                    exc_d, vrho_d = lda_exchange(rho[:, 0, :])
+                    o = ctx.vxc_assemble(rho, exc_d, vrho_d, None, "NN")[0].cpu().numpy()
+                    vmat.append(o[: N * N].reshape(N, N).copy())
+                    excsum.append(float(o[N * N]))
+                    nelec.append(float(o[N * N + 1]))
+                    resids.append(None)
+                    continue
                 r = rho[0].cpu().numpy()
                 exc, vxc = self.eval_xc(xc_code, r[0] if ncomp == 1 else r, spin=0, relativity=relativity, deriv=1,
                                         verbose=verbose, params=params)[:2]

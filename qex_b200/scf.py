@@ -138,10 +138,27 @@ def get_j(eri, dm):
     return hf.dot_eri_dm_rowdot(eri, dm)
 
 
+def _nr_rks_lda(xc, dm):
+    """`nr_rks(mol, grids, "lda", dm)` on the device without a network: rho (K2) -> Slater exchange (csrc/xc_lda.cu)
+    -> E_xc / V_xc assembly (K5).  Not differentiable (there is nothing to train)."""
+    from .xc import lda_exchange
+
+    with torch.no_grad():
+        B, N = xc.nbatch, xc.nao
+        rho = xc.eval_rho(dm.detach().reshape(B, N, N), 1, 1)
+        exc, vrho = lda_exchange(rho[:, 0, :])
+        out = xc.vxc_assemble(rho, exc, vrho, None, "NN")
+    return out[:, N * N + 1], out[:, N * N], out[:, : N * N].reshape(B, N, N)
+
+
 def get_veff(xc, dm, eri, theta, xctype: str = "NN"):
-    """-> (J + V_xc, E_xc, J) of get_veff_jax; the grid, weights and AO values live in the XCContext."""
+    """-> (J + V_xc, E_xc, J) of get_veff_jax; the grid, weights and AO values live in the XCContext.
+    ``theta=None`` with ``xctype="LDA"`` selects the analytic Slater-exchange functional (pyscf's ``xc = "lda"``)."""
     J = get_j(eri, dm)
-    _nelec, excsum, vmat = _ag.nr_rks(xc, dm, theta, xctype, hermi=1)
+    if theta is None and xctype == "LDA":
+        _nelec, excsum, vmat = _nr_rks_lda(xc, dm)
+    else:
+        _nelec, excsum, vmat = _ag.nr_rks(xc, dm, theta, xctype, hermi=1)
     return J + vmat[0], excsum[0], J
 
 
@@ -372,7 +389,10 @@ def generalized_eigh_batched(A, Bm, eps: float = 1.0e-12, small_kernel: bool | N
 
 def get_veff_batched(xc, dm, eri, theta, xctype: str = "NN"):
     J = hf.dot_eri_dm_rowdot_batched(eri, dm)
-    _nelec, excsum, vmat = _ag.nr_rks(xc, dm, theta, xctype, hermi=1)
+    if theta is None and xctype == "LDA":
+        _nelec, excsum, vmat = _nr_rks_lda(xc, dm)
+    else:
+        _nelec, excsum, vmat = _ag.nr_rks(xc, dm, theta, xctype, hermi=1)
     return J + vmat, excsum, J
 
 

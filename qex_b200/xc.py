@@ -79,6 +79,42 @@ def eval_xc(xc_code, rho, spin=0, relativity=0, deriv=2, verbose=None, params=No
     return exc, (vrho, None, None, None), None, None
 
 
+LDA_EXCHANGE_CODES = ("lda", "lda,", "slater", "slater,", "lda_x", "lda_x,")  # pyscf aliases of libxc LDA_X alone
+
+
+def lda_exchange(rho):
+    """libxc LDA_X, unpolarised, on the device (csrc/xc_lda.cu): rho (CUDA tensor or array, any shape) ->
+    (exc per particle, vrho = d(rho exc)/d rho), returned in the type that came in."""
+    import ctypes as C
+
+    import torch
+
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.QexxcError(_lib.ERR_NODEVICE, "no CUDA device: qex_b200 has no CPU fallback")
+    if isinstance(rho, torch.Tensor) and rho.is_cuda:
+        r = rho.to(torch.float64).contiguous()
+    else:
+        r = torch.as_tensor(np.ascontiguousarray(rho, dtype=np.float64)).cuda()
+    exc, vrho = torch.empty_like(r), torch.empty_like(r)
+    with torch.cuda.device(r.device):
+        _lib.check(lib.qexxc_lda_exchange(r.device.index, r.data_ptr(), r.numel(), exc.data_ptr(), vrho.data_ptr(),
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return _out(exc, rho), _out(vrho, rho)
+
+
+def lda_eval_xc(xc_code, rho, spin=0, relativity=0, deriv=1, verbose=None, params=None, **kwargs):
+    """``ni.eval_xc("lda", rho, ...)`` of the reference's LDA branch (pyscfad libxc) for Slater exchange:
+    -> (exc, (vrho, None, None, None), None, None).  Other libxc functionals stay with pyscf."""
+    if not (isinstance(xc_code, str) and xc_code.lower().replace(" ", "") in LDA_EXCHANGE_CODES):
+        raise NotImplementedError(f"xc_code {xc_code!r}: only Slater exchange ('lda') has a kernel; other libxc "
+                                  "functionals stay with pyscf")
+    if spin != 0:
+        raise NotImplementedError("spin-polarised LDA is not on the accelerated path")
+    exc, vrho = lda_exchange(rho)
+    return exc, (vrho, None, None, None), None, None
+
+
 def make_eval_xc(network, is_global_xc=False):
     """What the trainer installs with ``mf.define_xc_(description=...)``
     (trainer_legacy_no_jit.py:256-261): ``eval_xc`` with the network bound."""

@@ -74,6 +74,9 @@ def test_bad_arguments_return_codes(lib):
     assert lib.qexxc_becke_partition(0, None, 10, None, None, None, None, 2, 1, None, None, None) == _lib.ERR_ARG
     assert b"null device pointer" in lib.qexxc_last_error()
     assert lib.qexxc_becke_partition(0, None, 0, None, None, None, None, 2, 1, None, None, None) == 0
+    assert lib.qexxc_lda_exchange(0, None, 5, None, None, None) == _lib.ERR_ARG
+    assert lib.qexxc_lda_exchange(0, None, -1, None, None, None) == _lib.ERR_ARG
+    assert lib.qexxc_lda_exchange(0, None, 0, None, None, None) == 0
 
 
 def test_grid_build_on_a_device_is_loud_without_one():

@@ -194,3 +194,83 @@ def test_cuda_becke_partition_matches_the_host_partition(lib, case):
                               becke_scheme=grid_ref.stratmann if "stratmann" in case else grid_ref.original_becke)
         assert np.abs(dev.weights - w).max() <= 1e-13 * scale
     assert lib.qexxc_grid_launch_count() > 0
+
+
+def test_lda_code_handling_on_the_host():
+    from qex_b200 import numint, xc
+
+    assert numint._xctype(numint.NumInt(), "lda") == "LDA" and numint._xctype(numint.NumInt(), "LDA,") == "LDA"
+    with pytest.raises(NotImplementedError):
+        numint._xctype(numint.NumInt(), "b3lyp")
+    with pytest.raises(NotImplementedError):
+        xc.lda_eval_xc("lda,vwn", np.ones(4))
+    with pytest.raises(NotImplementedError):
+        xc.lda_eval_xc("lda", np.ones(4), spin=1)
+
+
+@pytest.mark.gpu
+def test_cuda_lda_exchange_kernel_matches_the_closed_form(lib):
+    import torch
+
+    from qex_b200 import xc
+
+    rng = np.random.default_rng(0)
+    rho = np.concatenate([10.0 ** rng.uniform(-14, 1, 5000), [0.0, -1e-18, 1e-300]])
+    e_ref, v_ref = grid_ref.lda_exchange(rho)
+    e, (v, a, b, c), f, k = xc.lda_eval_xc("lda", rho)
+    assert (a, b, c, f, k) == (None,) * 5 and isinstance(e, np.ndarray)
+    assert np.abs(e - e_ref).max() <= 4e-16 * np.abs(e_ref).max() and np.abs(v - v_ref).max() <= 4e-16 * np.abs(v_ref).max()
+    et, vt = xc.lda_exchange(torch.tensor(rho, device="cuda").reshape(3, -1))  # tensors stay on the device
+    assert et.is_cuda and et.shape == (3, rho.size // 3) and np.array_equal(et.cpu().numpy().ravel(), e)
+    assert lib.qexxc_lda_launch_count() >= 2
+
+
+@pytest.mark.gpu
+def test_cuda_device_resident_lda_scf_matches_the_notebook(lib):
+    """The same pin with NOTHING on the host: `scf.scf_loop` (J kernel, batched-Jacobi / cuSOLVER eigensolver, DIIS) around
+    rho (K2) -> Slater exchange (csrc/xc_lda.cu) -> V_xc assembly (K5), grid from the CUDA partition.  Then the built-in
+    `nr_rks(mol, grids, "lda", dm)` against the host-callback route, and three bond lengths in ONE batched loop."""
+    import torch
+
+    from qex_b200 import scf
+    from qex_b200.engine import XCContext
+    from qex_b200.numint import NumInt
+
+    def problem(R):
+        m = gto.h2(R, "6-31g")
+        g = gen_grid.Grids(m)
+        g.level = 0
+        g.becke_scheme = gen_grid.stratmann
+        return m, ints_ref.integrals(m._atm, m._bas, m._env), g.build(device=0)
+
+    m, I, g = problem(0.74)
+    ctx = XCContext(nao=4, ngrids_max=g.size, ncomp=1)
+    ctx.set_grid(g.coords, g.weights).set_basis(m._atm, m._bas, m._env).eval_ao(0)
+    t = {k: torch.as_tensor(np.ascontiguousarray(v)).cuda() for k, v in I.items() if k != "enuc"}
+    dm0 = torch.as_tensor(scf_ref.core_guess(I["h1e"], I["s1e"], 2)).cuda()
+    e, dm, hist = scf.scf_loop(ctx, None, dm0, t["eri"], t["s1e"], t["h1e"], I["enuc"], 2, xctype="LDA", max_cycle=25)
+    assert abs(float(hist[-1] - hist[-2])) < 1e-11
+    assert abs(float(e) - E_LDA_NOTEBOOK) < 1e-9
+    # built-in functional of nr_rks == the host-callback route of the first pin test
+    ni, nj = NumInt(), NumInt()
+    nj.eval_xc = _slater_eval_xc
+    d = dm.cpu().numpy()
+    n1, e1, v1 = ni.nr_rks(m, g, "lda", d, hermi=1)
+    n2, e2, v2 = nj.nr_rks(m, g, "LDA", d, hermi=1)
+    assert abs(n1 - n2) < 1e-13 and abs(e1 - e2) < 1e-13 and np.abs(v1 - v2).max() < 1e-13
+    # batched: three geometries in one loop against the oracle loop on the oracle grid
+    bonds = [0.74, 0.5, 1.5]
+    P = [problem(R) for R in bonds]
+    xb = XCContext(nao=4, ngrids_max=P[0][2].size, ncomp=1, nbatch=3)
+    xb.set_grid(np.stack([p[2].coords for p in P]), np.stack([p[2].weights for p in P]))
+    xb.set_basis(P[0][0]._atm, P[0][0]._bas, np.stack([p[0]._env for p in P])).eval_ao(0)
+    st = lambda k: torch.as_tensor(np.stack([p[1][k] for p in P])).cuda()  # noqa: E731
+    dmb = torch.as_tensor(np.stack([scf_ref.core_guess(p[1]["h1e"], p[1]["s1e"], 2) for p in P])).cuda()
+    enuc = torch.as_tensor(np.array([p[1]["enuc"] for p in P])).cuda()
+    eb, _, _ = scf.scf_loop_batched(xb, None, dmb, st("eri"), st("s1e"), st("h1e"), enuc, 2, xctype="LDA", max_cycle=25)
+    for b, (mm, II, gg) in enumerate(P):
+        ao = gto_ref.eval_ao(mm._atm, mm._bas, mm._env, gg.coords, 0)
+        e_ref, _, _ = scf_ref.scf_loop(scf_ref.core_guess(II["h1e"], II["s1e"], 2), II["eri"], ao, gg.weights, II["s1e"],
+                                       II["h1e"], II["enuc"], 2, grid_ref.lda_exchange, max_cycle=25)
+        assert abs(float(eb[b]) - e_ref) < 1e-9
+    assert abs(float(eb[0]) - E_LDA_NOTEBOOK) < 1e-9
