@@ -215,7 +215,7 @@ def test_cuda_lda_exchange_kernel_matches_the_closed_form(lib):
     from qex_b200 import xc
 
     rng = np.random.default_rng(0)
-    rho = np.concatenate([10.0 ** rng.uniform(-14, 1, 5000), [0.0, -1e-18, 1e-300]])
+    rho = np.concatenate([10.0 ** rng.uniform(-14, 1, 5001), [0.0, -1e-18, 1e-300]])  # 5004 = 3 x 1668
     e_ref, v_ref = grid_ref.lda_exchange(rho)
     e, (v, a, b, c), f, k = xc.lda_eval_xc("lda", rho)
     assert (a, b, c, f, k) == (None,) * 5 and isinstance(e, np.ndarray)
