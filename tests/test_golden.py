@@ -65,3 +65,23 @@ def test_cuda_path_matches_fixtures(gold, case):
     assert abs(out[N * N + 1] - gold[case + "_nelec"]) <= 1e-9
     assert rel_err(bar[: N * N].reshape(N, N), gold[case + "_dm_bar"]) <= 1e-10
     assert rel_err(bar[N * N :], gold[case + "_theta_bar"]) <= 1e-10
+
+
+def test_reference_notebook_fixture_is_what_the_pin_tests_use():
+    """tests/golden/reference_notebook.json holds the numbers extracted from the reference's stored notebook outputs
+    (tests/golden/extract_reference_notebook.py); the constants in the pin tests must be exactly those."""
+    import json
+    import os
+
+    from tests import test_scf, test_zz_pyscf_pin, test_zzz_trainer
+
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_notebook.json")))
+    scf_all = ref["converged_scf_energies_all"]
+    assert all(v in scf_all for v in test_scf.GOLDEN_RHF.values()) and len(scf_all) == 7
+    assert test_zz_pyscf_pin.E_LDA_NOTEBOOK == ref["lda_rks_energy_0.74"] and ref["lda_rks_energy_0.74"] in scf_all
+    assert sorted(round(v, 12) for v in test_scf.GOLDEN_CCSD.values()) == ref["ccsd_energies_all"]
+    assert all(abs(test_scf.GOLDEN_CCSD[b] - v) < 1e-15 for b, v in test_zzz_trainer.E_CCSD_NOTEBOOK.items())
+    assert np.array_equal(test_zz_pyscf_pin.DM_CCSD_NOTEBOOK, np.array(ref["cell2_dm_ao"]))
+    assert list(test_zz_pyscf_pin.RHO_TAIL_NOTEBOOK) == ref["cell2_density_head_tail"][:3]
+    assert ref["cell2_density_head_tail"][3:] == ref["cell2_density_head_tail"][:3][::-1]
+    assert ref["ngrids_logged"] == [1192, 1240] and ref["cell2_grid_points"] == 1192 and ref["lda_rks_ngrids"] == 1240
