@@ -274,3 +274,41 @@ def test_cuda_device_resident_lda_scf_matches_the_notebook(lib):
                                        II["h1e"], II["enuc"], 2, grid_ref.lda_exchange, max_cycle=25)
         assert abs(float(eb[b]) - e_ref) < 1e-9
     assert abs(float(eb[0]) - E_LDA_NOTEBOOK) < 1e-9
+
+
+@pytest.mark.gpu
+def test_nr_rks_lda_like_the_reference_pyscf_consistency_test(lib):
+    """tests/test_numint.py:208-258 of the reference (`test_pyscf_pyscfad_consistency`): H2 at 1.0 A, STO-3G, xc "LDA",
+    grids.level = 1 (pyscf's default Becke scheme), `ni.nr_rks(mol, grids, "LDA", dm)` compared between two
+    implementations at rtol 1e-6 / 1e-5.  Here: the CUDA path against the oracle (pyscf itself is absent), same calls,
+    tolerances five orders tighter; then the converged RKS energies of both."""
+    import torch
+
+    from qex_b200 import scf
+    from qex_b200.engine import XCContext
+    from qex_b200.numint import NumInt
+    from oracle import numint_ref
+
+    mol = gto.h2(1.0, "sto-3g")
+    grids = gen_grid.Grids(mol)
+    grids.level = 1
+    grids.build(device=0)
+    c, w = grid_ref.build(mol.atom_charges(), mol.atom_coords(), level=1, becke_scheme=grid_ref.original_becke)
+    assert grids.coords.shape == c.shape and np.abs(grids.weights - w).max() < 1e-13 * np.abs(w).max()
+    I = ints_ref.integrals(mol._atm, mol._bas, mol._env)
+    dm = scf_ref.core_guess(I["h1e"], I["s1e"], 2)  # stands in for get_init_guess()
+    ni = NumInt()
+    nelec, exc, vxc = ni.nr_rks(mol, grids, "LDA", dm)
+    ao = gto_ref.eval_ao(mol._atm, mol._bas, mol._env, c, 0)
+    n0, e0, v0 = numint_ref.nr_rks(ao, w, dm, _slater_eval_xc, "NN")  # the LDA branch shares the NN branch's assembly
+    np.testing.assert_allclose(nelec, n0, rtol=1e-11)
+    np.testing.assert_allclose(exc, e0, rtol=1e-11)
+    np.testing.assert_allclose(vxc, v0, rtol=1e-10, atol=1e-13)
+    assert abs(nelec - 2.0) < 1e-4  # a level-1 grid integrates the density to 1e-5
+    ctx = XCContext(nao=2, ngrids_max=grids.size, ncomp=1)
+    ctx.set_grid(grids.coords, grids.weights).set_basis(mol._atm, mol._bas, mol._env).eval_ao(0)
+    t = {k: torch.as_tensor(np.ascontiguousarray(v)).cuda() for k, v in I.items() if k != "enuc"}
+    e_gpu, _, _ = scf.scf_loop(ctx, None, torch.as_tensor(dm).cuda(), t["eri"], t["s1e"], t["h1e"], I["enuc"], 2,
+                               xctype="LDA", max_cycle=20)
+    e_ref, _, _ = scf_ref.scf_loop(dm, I["eri"], ao, w, I["s1e"], I["h1e"], I["enuc"], 2, grid_ref.lda_exchange, max_cycle=20)
+    np.testing.assert_allclose(float(e_gpu), e_ref, rtol=1e-10)
