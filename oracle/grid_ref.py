@@ -26,9 +26,10 @@ PIN STATUS: **pinned against numbers the reference itself prints** (tests/test_z
   1.63724571e-12) to 1e-8 relative (the printed dm carries 8 digits).
 
 Only H at level 0 is pinned that way; the other rows of the level / xi / radius tables are restated from the
-published papers and pyscf's documented defaults and are "parity unpinned".  The order of the points differs
-from pyscf's (which sorts them into spatial boxes and pads to a multiple of 8 with zero-weight points);
-every quantity on the path is a sum over points, so order does not enter.
+published papers and pyscf's documented defaults and are "parity unpinned".  Point ORDER: pyscf sorts the points into spatial boxes (``arg_group_grids``) and pads to a multiple
+of 8 with zero-weight points; ``build(sort_grids=True)`` restates the box sort, and with it rho[:3] and rho[-3:] equal the
+head and tail the notebook prints IN ORDER (order inside a box follows scipy's Lebedev point order, which may differ from
+pyscf's; padding is not reproduced -- 1240 and 1192 need none).  Every quantity on the path is a sum over points.
 """
 import numpy as np
 from scipy.integrate import lebedev_rule
@@ -118,8 +119,9 @@ def gen_atomic_grid(chg, level=0, prune=True, xi_table=TREUTLER_XI):
     return np.vstack(coords), np.hstack(vol)
 
 
-def build(atom_charges, atom_coords, level=0, becke_scheme=stratmann, prune=True, xi_table=TREUTLER_XI):
-    """pyscf ``Grids(mol); .level; .becke_scheme; .build()`` -> (coords [G,3] Bohr, weights [G])."""
+def build(atom_charges, atom_coords, level=0, becke_scheme=stratmann, prune=True, xi_table=TREUTLER_XI, sort_grids=False):
+    """pyscf ``Grids(mol); .level; .becke_scheme; .build()`` -> (coords [G,3] Bohr, weights [G]).
+    ``sort_grids=True`` applies pyscf's box ordering (``arg_group_grids``); the default keeps generation order."""
     atom_charges = np.asarray(atom_charges, dtype=int)
     atom_coords = np.asarray(atom_coords, dtype=np.float64)
     natm = len(atom_charges)
@@ -144,7 +146,27 @@ def build(atom_charges, atom_coords, level=0, becke_scheme=stratmann, prune=True
                 pbecke[j] *= 0.5 * (1 + g)
         coords_all.append(c)
         weights_all.append(vol * pbecke[ia] / pbecke.sum(axis=0))
-    return np.vstack(coords_all), np.hstack(weights_all)
+    coords_all, weights_all = np.vstack(coords_all), np.hstack(weights_all)
+    if sort_grids:
+        idx = arg_group_grids(atom_coords, coords_all)
+        coords_all, weights_all = coords_all[idx], weights_all[idx]
+    return coords_all, weights_all
+
+
+def arg_group_grids(atom_coords, coords, box_size=1.2, boundary_penalty=4.2):
+    """pyscf's point order: space is cut into boxes of ~1.2 Bohr inside [min(atoms) - 4.2, max(atoms) + 4.2], points
+    are grouped by box (boxes in lexicographic order, one overflow layer on each side), generation order kept inside a
+    box.  -> index array.  Pinned only through the first / last three densities the reference notebook prints."""
+    atom_coords = np.asarray(atom_coords, dtype=np.float64)
+    lo, hi = atom_coords.min(axis=0) - boundary_penalty, atom_coords.max(axis=0) + boundary_penalty
+    boxes = ((hi - lo) * (1.0 / box_size)).round().astype(int)
+    size = (hi - lo) / boxes
+    ids = np.floor((coords - lo) * (1.0 / size)).astype(int)
+    ids[ids < -1] = -1
+    for k in range(3):
+        ids[ids[:, k] > boxes[k], k] = boxes[k]
+    inverse = np.unique(ids, axis=0, return_inverse=True)[1]
+    return np.argsort(np.ravel(inverse), kind="stable")
 
 
 def lda_exchange(rho):

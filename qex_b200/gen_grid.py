@@ -126,6 +126,19 @@ def treutler_atomic_radii_adjust(charges, atomic_radii=BRAGG_RADII):
     return np.clip(0.25 * (1.0 / chi - chi), -0.5, 0.5)
 
 
+def group_grids_by_boxes(centers, coords, box_size=1.2, margin=4.2):
+    """Index array of pyscf's point order (``arg_group_grids``): boxes of about ``box_size`` Bohr over the molecule's
+    bounding box grown by ``margin``, one overflow layer per side, boxes visited in lexicographic (x, y, z) order, points
+    of a box in generation order."""
+    lo = centers.min(axis=0) - margin
+    span = centers.max(axis=0) + margin - lo
+    nbox = np.rint(span / box_size).astype(np.int64)
+    cell = np.floor((coords - lo) / (span / nbox)).astype(np.int64)
+    cell = np.minimum(np.maximum(cell, -1), nbox)             # overflow layers -1 and nbox
+    key = ((cell[:, 0] + 1) * (nbox[1] + 2) + (cell[:, 1] + 1)) * (nbox[2] + 2) + (cell[:, 2] + 1)
+    return np.argsort(key, kind="stable")
+
+
 # ---------------------------------------------------------------- partition
 def _partition_host(coords, owner, vol, centers, adjust, scheme):
     na = centers.shape[0]
@@ -230,11 +243,13 @@ class Grids:
         self.coords = None if coords is None else np.asarray(coords, dtype=np.float64)
         self.weights = None if weights is None else np.asarray(weights, dtype=np.float64)
 
-    def build(self, mol=None, with_non0tab=False, sort_grids=True, device=None, **kwargs):
+    def build(self, mol=None, with_non0tab=False, sort_grids=None, device=None, **kwargs):
         """pyscf's ``Grids.build(mol=None, with_non0tab=False, sort_grids=True)`` plus ``device``:
-        ``device=None`` partitions on the host (NumPy), ``device=k`` on GPU k (csrc/grid.cu).  ``with_non0tab`` /
-        ``sort_grids`` are accepted and ignored: no screening table is built and the points keep generation order."""
-        del with_non0tab, sort_grids, kwargs
+        ``device=None`` partitions on the host (NumPy), ``device=k`` on GPU k (csrc/grid.cu).  ``sort_grids=True`` gives
+        pyscf's box ordering of the points; left unset the points keep generation order (atom by atom), which is what
+        the fixtures are frozen on -- every consumer on the path sums over points.  ``with_non0tab`` is accepted and
+        ignored (no screening table is built, no zero-weight padding points are appended)."""
+        del with_non0tab, kwargs
         if mol is not None:
             self.mol = mol
         if self.n_rad is not None:
@@ -253,6 +268,9 @@ class Grids:
             weights = _partition_host(coords, owner, vol, centers, adjust, self.becke_scheme)
         else:
             weights = _partition_cuda(coords, owner, vol, centers, adjust, self.becke_scheme, device)
+        if sort_grids:
+            idx = group_grids_by_boxes(centers, coords)
+            coords, weights = coords[idx], weights[idx]
         self.coords, self.weights = coords, weights
         return self
 

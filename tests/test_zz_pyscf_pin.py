@@ -70,6 +70,28 @@ def test_oracle_ao_and_rho_reproduce_the_notebook_tail_densities():
         assert _nearest_rel(rho, t) < 3e-8  # 8 printed digits of dm, 9 of rho
 
 
+def test_box_ordering_reproduces_the_head_and_tail_the_notebook_prints():
+    """pyscf hands the points out sorted into spatial boxes; cell 2 of the notebook prints `Density: [a b c ... c b a]`.
+    With the box sort restated, rho[:3] and rho[-3:] come out as printed, in order (oracle and host generator)."""
+    m, _ = _h2()
+    c, w = grid_ref.build(m.atom_charges(), m.atom_coords(), level=0, xi_table=None, sort_grids=True)
+    ao = gto_ref.eval_ao(m._atm, m._bas, m._env, c, 0)
+    rho = np.einsum("gi,ij,gj->g", ao, DM_CCSD_NOTEBOOK, ao)
+    printed = np.array(RHO_TAIL_NOTEBOOK)
+    assert np.abs(rho[:3] / printed - 1).max() < 3e-8 and np.abs(rho[-3:] / printed[::-1] - 1).max() < 3e-8
+    # the unsorted grid starts at the nucleus instead
+    c0, _ = grid_ref.build(m.atom_charges(), m.atom_coords(), level=0, xi_table=None)
+    assert np.linalg.norm(c0[0]) < 0.01 and np.linalg.norm(c[0]) > 8.0
+    # host generator: same permutation (independent implementation of the box key), same weights
+    g = gen_grid.Grids(m)
+    g.level = 0
+    g.becke_scheme = gen_grid.stratmann
+    g.build(sort_grids=True)
+    c1, w1 = grid_ref.build(m.atom_charges(), m.atom_coords(), level=0, sort_grids=True)
+    assert np.abs(g.coords - c1).max() < 1e-13 and np.abs(g.weights - w1).max() < 1e-13
+    assert abs(g.weights.sum() - g.build().weights.sum()) < 1e-12
+
+
 def test_host_grid_generator_matches_the_oracle_grid():
     m, _ = _h2()
     for kw in ({}, {"becke_scheme": "becke"}, {"level": 1}):
