@@ -334,3 +334,22 @@ def test_nr_rks_lda_like_the_reference_pyscf_consistency_test(lib):
                                xctype="LDA", max_cycle=20)
     e_ref, _, _ = scf_ref.scf_loop(dm, I["eri"], ao, w, I["s1e"], I["h1e"], I["enuc"], 2, grid_ref.lda_exchange, max_cycle=20)
     np.testing.assert_allclose(float(e_gpu), e_ref, rtol=1e-10)
+
+
+@pytest.mark.parametrize("z", [1, 8])
+def test_level_tables_give_converging_atomic_quadratures(z):
+    """Rows of the level / xi / pruning tables that no reference number pins (only H at level 0 is): every level must at
+    least be a quadrature that converges -- a Gaussian, a 1s Slater density and an l = 4 moment on one atom."""
+    errs = []
+    for level in (0, 1, 3, 5):
+        c, w = grid_ref.build([z], [[0.0, 0.0, 0.0]], level=level)
+        r2 = (c**2).sum(1)
+        errs.append((abs((np.exp(-r2) * w).sum() - np.pi**1.5),
+                     abs((np.exp(-2.0 * np.sqrt(r2)) / np.pi * w).sum() - 1.0),
+                     abs((c[:, 0] ** 2 * c[:, 2] ** 2 * np.exp(-r2) * w).sum() - np.pi**1.5 / 4.0)))
+        g = gen_grid.Grids(gto.Mole([(z, (0.0, 0.0, 0.0))], basis=gto.even_tempered_basis([1]), unit="Bohr"))
+        g.level = level
+        g.build()
+        assert g.size == w.size and np.abs(g.weights - w).max() < 1e-13 * np.abs(w).max()
+    errs = np.array(errs)
+    assert (errs[0] < 1e-2).all() and (errs[1] < 1e-8).all() and (errs[2] < 1e-9).all() and (errs[3] < 1e-10).all()
