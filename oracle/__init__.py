@@ -19,7 +19,9 @@ outputs of the path, and those ARE reproduced.  What is pinned:
   (notebooks/04_notebook_td_trainer.ipynb cell 1: "converged SCF energy = -1.03718794786902",
   1240 grid points) -- the oracle gives -1.0371879478690555 (|diff| < 1e-13 Ha), the CUDA
   kernels through ``NumInt.nr_rks`` < 1e-9 Ha -- and by the three tail densities the same
-  notebook prints for its CCSD density matrix (1e-8 relative); tests/test_zz_pyscf_pin.py;
+  notebook prints for its CCSD density matrix (1e-8 relative, and in pyscf's point order with
+  ``grid_ref.build(sort_grids=True)``); tests/test_zz_pyscf_pin.py; the extracted numbers live in
+  tests/golden/reference_notebook.json; ``train_ref`` restates the trainer's loss on top of this chain;
 
 * contraction / assembly conventions (``numint_ref``): pinned by the closed-form toy
   functional of ``tests/test_numint.py:96-103`` (exc = 0.01 rho^2, vrho = 0.02 rho), by
