@@ -34,7 +34,15 @@ def main():
     w = torch.empty_like(v)
     G = c.shape[0]
     out = {"natm": natoms, "level": level, "ngrids": G, "host_tables_s": round(t_host, 3)}
-    for name, sid in (("becke", 0), ("stratmann", 1)):
+    variants = [("becke", 0, c, v, o), ("stratmann", 1, c, v, o)]
+    if "--sorted" in sys.argv:
+        # experiment for DESIGN 6d's open item: points ordered by (owner, distance to owner) make the lanes of a warp
+        # break out of the pair loops at similar places (NOT yet run on hardware)
+        d_own = np.linalg.norm(coords - centers[owner], axis=1)
+        perm = torch.tensor(np.lexsort((d_own, owner)), device=dev)
+        variants += [("becke_sorted", 0, c[perm].contiguous(), v[perm].contiguous(), o[perm].contiguous()),
+                     ("stratmann_sorted", 1, c[perm].contiguous(), v[perm].contiguous(), o[perm].contiguous())]
+    for name, sid, c, v, o in variants:
         def run():
             _lib.check(lib.qexxc_becke_partition(0, c.data_ptr(), C.c_long(G), o.data_ptr(), v.data_ptr(), ac.data_ptr(), None,
                                                  natoms, sid, work.data_ptr(), w.data_ptr(),

@@ -25,7 +25,20 @@ def parse(argv=None):
     return ap.parse_args(argv)
 
 
+def _dist_setup():
+    """Under torchrun: one rank per GPU, NCCL; the trainer deals the molecules of a batch to the ranks and all-reduces
+    the packed [grad | loss] (this mode has a gloo test but no hardware run yet)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    return int(os.environ.get("RANK", "0")), world
+
+
 def measure(args, cpu_baseline_fn=None):
+    rank, world = _dist_setup()
     bonds = [0.74, 0.5, 1.5] if args.nmol == 3 else [float(b) for b in torch.linspace(0.4, 3.0, args.nmol)]
     g = gen_grid.Grids(gto.h2(0.74, "6-31g"))
     g.level = 0
@@ -48,7 +61,16 @@ def measure(args, cpu_baseline_fn=None):
         loss, theta, state = step(theta, state)
         losses.append(loss)
     torch.cuda.synchronize()
-    xc = tr._problem(train).xc
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        from qex_b200 import dist as qdist
+
+        mine = [train[i] for i in qdist.shard_batch(len(train), rank, world)]
+    else:
+        mine = train
+    xc = tr._problem(mine).xc
     n0 = int(xc.lib.qexxc_launch_count(xc._h)) + int(xc.lib.qexxc_jk_launch_count())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -58,10 +80,16 @@ def measure(args, cpu_baseline_fn=None):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:  # max over ranks, on the device clock
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
     launches = (int(xc.lib.qexxc_launch_count(xc._h)) + int(xc.lib.qexxc_jk_launch_count()) - n0) // args.steps
     # the same iteration (forward, reverse, Adam) as ONE CUDA graph (`config["cuda_graph"]` of the trainer)
     ms_graph, graph_note = None, None
     try:
+        if world > 1:
+            raise RuntimeError("one-graph replay is a single-GPU mode")
         shared = dict(theta=theta.detach().clone(), mu=state["mu"].clone(), nu=state["nu"].clone(),
                       count=torch.full((), float(state["count"]), dtype=torch.float64, device=theta.device))
         gi = trainer._GraphedIteration(tr, train, 1.0, 1.0, 1e-3, shared)
@@ -93,9 +121,11 @@ def measure(args, cpu_baseline_fn=None):
         "config": {"workload": f"c1 as a training step: {len(bonds)} H2/6-31G geometries, {G} grid points x 4 AOs, "
                                f"{'GlobalMLP' if args.global_xc else 'LocalMLP'} 64x3 tanh, {args.cycles}-cycle KS-SCF with DIIS",
                    "steps": args.steps, "warmup": max(3, args.warmup)},
-        "dtype": "f64", "cpu_baseline": cpu,
+        "dtype": "f64", "cpu_baseline": cpu, "n_gpus": world, "rank": rank,
     }
 
 
 if __name__ == "__main__":
-    print(json.dumps(measure(parse())))
+    line = measure(parse())
+    if line["rank"] == 0:
+        print(json.dumps(line))
