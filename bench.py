@@ -7,19 +7,32 @@
 One "step" = one pass of the hot path over the whole synthetic workload (default c5:
 1000 AOs x 1,000,000 grid points, LocalMLP XC, float64): K1 AO values on the grid, stage 2 rho,
 stage 3 network exc/vrho, stage 4 E_xc / V_xc, then the reverse pass (dm_bar, theta_bar).  For
-N > 1 the grid is sharded in contiguous point ranges (strong scaling: the global grid is fixed)
-and the packed outputs are all-reduced with NCCL (one collective per direction).
+N > 1 the grid is sharded in contiguous 128-aligned point ranges (`qex_b200.dist.shard_range`; strong
+scaling: the global grid is fixed) and the packed outputs are all-reduced over NCCL through the C ABI
+(`qexxc_allreduce`), one collective per direction, the forward one overlapped with the VJP.
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events around exactly K steps, barrier +
 synchronize on both sides, max over ranks; inputs (8 GB AO tensor per pass) exceed L2.
+The line also carries, all timed in the same run: `roofline` (executed DMMA-pipe fraction of the dominant
+contraction + the streaming kernels against the HBM peak), `configs` (the other BASELINE configs: c1, c2, c3,
+c4, c5gga and c5 with the float32 network, each with value / ms / dominant kernel / CPU baseline), `e2e`
+(host buffers in and out) and, for N > 1, `parity_vs_n1` and the collective times.
 """
 from __future__ import annotations
 
+import os
+import sys
+
+# `--impl reference` times NumPy/BLAS on ALL host cores; torchrun exports OMP_NUM_THREADS=1 to its children,
+# which would silently shrink the BLAS pool, so the thread count is pinned before numpy is imported
+if "reference" in sys.argv or os.environ.get("QEX_BENCH_CPU_THREADS"):
+    _n = os.environ.get("QEX_BENCH_CPU_THREADS") or str(os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = _n
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -30,6 +43,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "XC grid-integration grid-pts/s (fwd+VJP)"
 UNIT = "grid-pts/s"
+SUB_CONFIGS = ("c1", "c2", "c3", "c4", "c5gga", "c5_f32")
 
 
 def _args():
@@ -43,6 +57,7 @@ def _args():
     ap.add_argument("--ngrids", type=int, default=None, help="override the grid size (debugging)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="network precision")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE configs)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the whole step as one CUDA graph (auto: single GPU and <= 200k grid points, where the "
                          "step is launch-latency bound)")
@@ -109,16 +124,19 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU side: the oracle restatement of the reference math on the host cores
 # ------------------------------------------------------------------------------------------------
-def _cpu_threads():
+def _set_cpu_threads():
+    """All host cores for BLAS, whatever OMP_NUM_THREADS the launcher exported.  Returns the count in use."""
+    want = int(os.environ.get("QEX_BENCH_CPU_THREADS") or os.cpu_count() or 1)
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
 
+        threadpool_limits(limits=want)  # stays in force for the process (not used as a context manager)
         n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
         if n:
             return int(max(n))
     except Exception:
         pass
-    return os.cpu_count() or 1
+    return want
 
 
 def cpu_step_time(wl, sample, repeats=1):
@@ -127,7 +145,7 @@ def cpu_step_time(wl, sample, repeats=1):
 
     m = wl.mol
     best = float("inf")
-    if "batch" in wl.extra:  # c4: `sample` counts grid points over whole molecules
+    if "batch" in wl.extra:  # c1 / c4: `sample` counts grid points over whole molecules
         nmol = max(1, min(wl.extra["batch"], sample // wl.ngrids))
         for _ in range(repeats):
             t0 = time.perf_counter()
@@ -145,15 +163,23 @@ def cpu_step_time(wl, sample, repeats=1):
     return best
 
 
+def _cpu_sample(wl, target_s, t0, s0):
+    G = wl.ngrids * (wl.extra.get("batch") or 1)
+    sample = int(min(G, max(s0, s0 * target_s / max(t0, 1e-6) / 2)))
+    if "batch" in wl.extra:
+        return max(wl.ngrids, (sample // wl.ngrids) * wl.ngrids)
+    return max(256, (sample // 256) * 256) if G >= 256 else G
+
+
 def cpu_baseline(wl, target_s):
     """Bounded sample of the same workload (about `target_s` seconds of CPU work)."""
+    cores = _set_cpu_threads()
     G = wl.ngrids * (wl.extra.get("batch") or 1)
-    s0 = min(G, 2048)
+    s0 = min(G, 2048) if "batch" not in wl.extra else wl.ngrids
     t0 = cpu_step_time(wl, s0)  # calibration (also warms BLAS threads)
-    sample = int(min(G, max(s0, s0 * target_s / max(t0, 1e-6) / 2)))
-    sample = max(256, (sample // 256) * 256) if G >= 256 else G
+    sample = _cpu_sample(wl, target_s, t0, s0)
     t = cpu_step_time(wl, sample)
-    return {"value": sample / t, "unit": UNIT, "cores": _cpu_threads(), "kind": "port",
+    return {"value": sample / t, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {sample} of {G} grid points of the same workload, 1 step (AO eval + nr_rks fwd + VJP), "
                       f"NumPy/BLAS float64 oracle restatement of the reference math (real JAX/pyscfad not installable); "
                       f"{t:.2f} s", "host_cpus": os.cpu_count()}
@@ -161,19 +187,20 @@ def cpu_baseline(wl, target_s):
 
 def run_reference(args):
     """`--impl reference`: the reference's own math on the host cores (the oracle port; the
-    reference itself -- JAX + pyscfad -- cannot be installed in this image)."""
+    reference itself -- JAX + pyscfad -- cannot be installed in this image).  BLAS runs on every host core even
+    under torchrun (which exports OMP_NUM_THREADS=1): pinned at the top of this file and again here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = _set_cpu_threads()
     from qex_b200 import workloads
 
     wl = workloads.make(args.config, ngrids=args.ngrids)
     G = wl.ngrids * (wl.extra.get("batch") or 1)
-    s0 = min(G, 2048)
+    s0 = min(G, 2048) if "batch" not in wl.extra else wl.ngrids
     t0 = cpu_step_time(wl, s0)
     budget = 120.0 / max(1, args.steps + args.warmup)  # whole run within a few minutes
-    sample = int(min(G, max(s0, s0 * min(budget, args.cpu_seconds) / max(t0, 1e-6) / 2)))
-    sample = max(256, (sample // 256) * 256) if G >= 256 else G
+    sample = _cpu_sample(wl, min(budget, args.cpu_seconds), t0, s0)
     for _ in range(args.warmup):
         cpu_step_time(wl, sample)
     t = time.perf_counter()
@@ -186,10 +213,10 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl.describe, "nao": wl.nao, "ngrids": G, "sample_ngrids": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": _cpu_threads(), "kind": "port",
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"each step = first {sample} of {G} grid points (AO eval + nr_rks fwd + VJP), "
                                    "NumPy/BLAS float64 oracle port; the reference's JAX/pyscfad stack is not installable here",
-                         "host_cpus": os.cpu_count()},
+                         "host_cpus": os.cpu_count(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -229,74 +256,110 @@ def measure_dgemm_peak(torch, seconds=1.5):
     return best, sustained
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+def ctx_npad(N):  # AO row pitch: a multiple of 32 columns (zeros in the pad)
+    return ((N + 31) // 32) * 32
 
+
+def _hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        return None
+
+
+def _err_pair(a, b, floor_frac=1e-6):
+    """(max-norm relative error, element-wise relative error with the denominator floored at
+    floor_frac * max|b|)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    mx = max(float(np.abs(b).max()), 1e-300)
+    d = np.abs(a - b)
+    return float(d.max() / mx), float((d / np.maximum(np.abs(b), floor_frac * mx)).max())
+
+
+class Env:
+    """Process-level state shared by the measurements of one bench run."""
+
+    def __init__(self, torch, tdist, world, rank, local, comm):
+        self.torch, self.tdist, self.world, self.rank, self.local, self.comm = torch, tdist, world, rank, local, comm
+
+    def barrier(self):
+        if self.world > 1:
+            self.tdist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, k):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.tdist.all_reduce(ms, op=self.tdist.ReduceOp.MAX)
+        return float(ms.item())
+
+
+def measure(env: Env, args, cfg: str, precision: str, steps: int, warmup: int, headline: bool, peak_sus=None,
+            cpu_seconds: float = 0.0):
+    """Times one workload on this process group.  Returns (summary dict for rank 0, extras)."""
+    torch = env.torch
     from qex_b200 import workloads
+    from qex_b200.dist import ShardedXC, shard_batch, shard_range
     from qex_b200.engine import XCContext
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the product path)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print its banner on STDOUT, next to the one JSON line the driver reads
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    wl = workloads.make(args.config, ngrids=args.ngrids)
+    world, rank, local = env.world, env.rank, env.local
+    wl = workloads.make(cfg, ngrids=args.ngrids if headline else None)
     N, G = wl.nao, wl.ngrids
     batch = wl.extra.get("batch")
-    net = workloads.net_spec(wl, args.precision)
+    net = workloads.net_spec(wl, precision)
     deriv = 1 if wl.ncomp == 4 else 0
     if batch:
-        # c4: molecules are sharded round-robin (replicas); only theta_bar crosses ranks
-        from qex_b200.dist import shard_batch
-
+        # c1 / c4: molecules are sharded round-robin (replicas); only theta_bar crosses ranks
         ids = shard_batch(batch, rank, world)
         Bl, Gl, lo, hi = len(ids), G, 0, G
-        ctx = XCContext(nao=N, ngrids_max=G, ncomp=wl.ncomp, nbatch=Bl, net=net, device=local)
-        ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.extra["envs"][ids])
+        ctx = XCContext(nao=N, ngrids_max=G, ncomp=wl.ncomp, nbatch=max(Bl, 1), net=net, device=local)
+        ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.extra["envs"][ids] if Bl else wl.extra["envs"][:1])
         npts_total = batch * G
     else:
-        # contiguous grid shard of this rank (fixed map rank -> point range)
-        per = (G + world - 1) // world
-        lo, hi = min(G, rank * per), min(G, (rank + 1) * per)
+        lo, hi = shard_range(G, rank, world)  # fixed 128-aligned rank -> point-range map
         Bl, Gl = 1, hi - lo
         ctx = XCContext(nao=N, ngrids_max=max(Gl, 1), ncomp=wl.ncomp, nbatch=1, net=net, device=local)
         ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env)
         npts_total = G
+    sx = ShardedXC(ctx, comm=env.comm)
+    nth = wl.theta.size
 
-    # pinned host copies of every per-call input, and device-resident copies
     def pin(x):
         return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).pin_memory()
 
     if batch:
-        h_coords, h_w, h_dm = pin(wl.coords[ids]), pin(wl.weights[ids]), pin(wl.dm[ids])
-        h_eb, h_vb = pin(np.full(Bl, wl.e_bar)), pin(np.broadcast_to(wl.v_bar, (Bl, N, N)))
+        sel = ids if Bl else [0]
+        h_coords, h_w, h_dm = pin(wl.coords[sel]), pin(wl.weights[sel]), pin(wl.dm[sel])
+        h_eb, h_vb = pin(np.full(len(sel), wl.e_bar)), pin(np.broadcast_to(wl.v_bar, (len(sel), N, N)))
     else:
         h_coords, h_w, h_dm = pin(wl.coords[lo:hi]), pin(wl.weights[lo:hi]), pin(wl.dm)
         h_eb, h_vb = pin(np.array([wl.e_bar])), pin(wl.v_bar)
     h_th = pin(wl.theta)
     d_coords, d_w, d_dm, d_th, d_eb, d_vb = (t.cuda() for t in (h_coords, h_w, h_dm, h_th, h_eb, h_vb))
-    out = ctx.empty(Bl, N * N + 2)
-    bar = ctx.empty(Bl * N * N + wl.theta.size)
+    Bc = ctx.nbatch
+    out = ctx.empty(Bc, N * N + 2)
+    bar = ctx.empty(Bc * N * N + nth)
     resid = ctx.empty(ctx.resid_doubles)
     h_out, h_bar = torch.empty_like(out, device="cpu").pin_memory(), torch.empty_like(bar, device="cpu").pin_memory()
 
-    def step():
+    def step(record=False):
         ctx.set_grid(d_coords, d_w)
         ctx.eval_ao(deriv)
-        ctx.nr_rks_fwd(d_dm, d_th, wl.xctype, 0, out=out, resid=resid)
-        if world > 1 and not batch:
-            dist.all_reduce(out)
-        ctx.nr_rks_vjp(d_th, resid, d_eb, d_vb, wl.xctype, 0, out=bar)
-        if world > 1:
-            dist.all_reduce(bar[Bl * N * N:] if batch else bar)
+        if batch:
+            ctx.nr_rks_fwd(d_dm, d_th, wl.xctype, 0, out=out, resid=resid)
+            ctx.nr_rks_vjp(d_th, resid, d_eb, d_vb, wl.xctype, 0, out=bar)
+            if world > 1:
+                sx._all_reduce(bar[Bc * N * N:])
+        else:
+            sx.step(d_dm, d_th, d_eb, d_vb, wl.xctype, out, bar, resid, record=record)
 
     # Launch-latency-bound sizes (H2, water): capture the ~16 launches of a step into one CUDA graph.
     use_graph = args.graph == "on" or (args.graph == "auto" and world == 1 and npts_total <= 200_000)
@@ -314,108 +377,119 @@ def run_ours(args):
             step()
     run_step = graph.replay if graph is not None else step
 
-    def step_e2e():
-        # host buffers in, host buffers out: what a caller of the drop-in nr_rks pays per call
-        d_coords.copy_(h_coords, non_blocking=True)
-        d_w.copy_(h_w, non_blocking=True)
-        d_dm.copy_(h_dm, non_blocking=True)
-        d_th.copy_(h_th, non_blocking=True)
-        d_eb.copy_(h_eb, non_blocking=True)
-        d_vb.copy_(h_vb, non_blocking=True)
+    for _ in range(max(3, warmup)):
         run_step()
-        h_out.copy_(out, non_blocking=True)
-        h_bar.copy_(bar, non_blocking=True)
-        torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, k):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    peak_burst = peak_sus = None
-    if rank == 0:
-        peak_burst, peak_sus = measure_dgemm_peak(torch)
-    for _ in range(max(3, args.warmup)):
-        run_step()
-    barrier()
+    env.barrier()
 
     # ---- timed region: value ----
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if headline else None
+    if rank == 0 and sampler:
         sampler.start()
     if graph is None:
         ctx.profile_enable(True)
-        l0 = ctx.launch_count
-        ms_total = timed(step, args.steps)
+        l0, c0 = ctx.launch_count, (env.comm.calls if env.comm else 0)
+        ms_total = env.timed(step, steps)
         launches = ctx.launch_count - l0
+        ncoll = (env.comm.calls if env.comm else 0) - c0
         prof = ctx.profile_read()
         ctx.profile_enable(False)
         prof_total = ms_total
     else:
-        ms_total = timed(run_step, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+        ms_total = env.timed(run_step, steps)
+    clocks = sampler.stop() if (rank == 0 and sampler) else None
     if graph is not None:
         # per-kernel events cannot be recorded inside a replayed graph: take the kernel table (and the
         # launch count) from a separate un-graphed pass of the same K steps
         ctx.profile_enable(True)
         l0 = ctx.launch_count
-        prof_total = timed(step, args.steps)
+        prof_total = env.timed(step, steps)
         launches = ctx.launch_count - l0
+        ncoll = 0
         prof = ctx.profile_read()
         ctx.profile_enable(False)
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     value = npts_total / (ms_step * 1e-3)
 
-    # ---- extra: the same step with the MO form of rho (dm tagged with mo_coeff/mo_occ takes pyscf's
-    # eval_rho2 branch, numint_legacy.py:527-545).  Reported separately; the headline stays dense-dm. ----
+    # collective times of one step (events on the streams the collectives run on), max over ranks
+    coll = None
+    if world > 1 and not batch:
+        step(record=True)
+        f_ms, v_ms = sx.collective_ms()
+        t = torch.tensor([f_ms, v_ms], dtype=torch.float64, device="cuda")
+        env.tdist.all_reduce(t, op=env.tdist.ReduceOp.MAX)
+        coll = {"fwd_allreduce_ms": float(t[0]), "vjp_allreduce_ms": float(t[1]),
+                "bytes_each": int(out.numel() * 8), "calls_in_timed_region": int(ncoll),
+                "note": "NCCL all-reduce of the packed fp64 buffers through qexxc_allreduce; the forward one runs on a "
+                        "side stream under the VJP's first contraction, the VJP one closes the step (exposed)"}
+
+    # ---- the same step with the MO form of rho (headline only) ----
     mo_ms = None
-    if "mo_coeff" in wl.extra and wl.xctype != "GGA":
+    if headline and "mo_coeff" in wl.extra and wl.xctype != "GGA":
         d_C, d_occ = ctx.dev(wl.extra["mo_coeff"]), ctx.dev(wl.extra["mo_occ"])
 
         def step_mo():
             ctx.set_grid(d_coords, d_w)
             ctx.eval_ao(deriv)
             ctx.nr_rks_fwd_mo(d_C, d_occ, d_th, wl.xctype, out=out, resid=resid)
-            if world > 1:
-                dist.all_reduce(out)
+            sx._all_reduce(out)
             ctx.nr_rks_vjp(d_th, resid, d_eb, d_vb, wl.xctype, 0, out=bar)
-            if world > 1:
-                dist.all_reduce(bar)
+            sx._all_reduce(bar)
 
         for _ in range(2):
             step_mo()
-        mo_ms = timed(step_mo, args.steps) / args.steps
+        mo_ms = env.timed(step_mo, steps) / steps
 
-    # ---- e2e: host buffers, copies inside the timed region ----
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region ----
+    if batch or graph is not None:
+        # (batched molecules, or a launch-latency-bound single-GPU step replayed as one graph)
+        def step_e2e():
+            d_coords.copy_(h_coords, non_blocking=True)
+            d_w.copy_(h_w, non_blocking=True)
+            d_dm.copy_(h_dm, non_blocking=True)
+            d_th.copy_(h_th, non_blocking=True)
+            d_eb.copy_(h_eb, non_blocking=True)
+            d_vb.copy_(h_vb, non_blocking=True)
+            run_step()
+            h_out.copy_(out, non_blocking=True)
+            h_bar.copy_(bar, non_blocking=True)
+            torch.cuda.synchronize()
+
+        h2d = sum(t.numel() * 8 for t in (h_coords, h_w, h_dm, h_th, h_eb, h_vb))
+        d2h = (h_out.numel() + h_bar.numel()) * 8
+        e2e_note = "every rank copies its own inputs in and its outputs out around the step"
+        io = None
+    else:
+        io = sx.make_host_io(1, nth)
+        if rank == 0:
+            sx.pack_host_inputs(io, wl.dm, wl.theta, wl.e_bar, wl.v_bar)
+
+        def step_e2e():
+            sx.step_host(io, h_coords, h_w, d_coords, d_w, wl.xctype, deriv)
+
+        # rank 0 moves the replicated inputs/outputs; every rank moves its own grid shard (bytes of rank 0)
+        h2d = (io["n1"] + io["n2"]) * 8 + (h_coords.numel() + h_w.numel()) * 8
+        d2h = (out.numel() + bar.numel()) * 8
+        e2e_note = ("rank 0 uploads dm|theta|e_bar|v_bar once (NCCL broadcast to the peers over NVLink) and downloads "
+                    "out|bar; every rank uploads its own coords/weights shard; cotangent upload and the forward "
+                    "result's reduce + download overlap compute")
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
-    h2d = sum(t.numel() * 8 for t in (h_coords, h_w, h_dm, h_th, h_eb, h_vb))
-    d2h = (h_out.numel() + h_bar.numel()) * 8
+    ms_e2e = env.timed(step_e2e, steps) / steps
+    e2e_same = None
+    if io is not None:
+        # the pipelined host path must return what the device-resident path returns (bit for bit)
+        run_step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            e2e_same = bool(torch.equal(io["h_out"], out.cpu()) and torch.equal(io["h_bar"], bar.cpu()))
 
+    res = None
     if rank == 0:
-        # dominant kernel: the FP64 DMMA contractions (2 rowquad + 2 wsyrk launches per step,
-        # 2*G*N^2 algorithmic FLOP each -> 8*N^2 FLOP per grid point per step)
-        fl = 2.0 * Gl * Bl * N * N
-        # executed DMMA FLOPs per launch (zero-padded tiles, symmetric operands skipped):
-        # (counted by the library with the same predicates the kernels use)
+        fl = 2.0 * Gl * Bc * N * N
         tri = wl.ncomp == 1
         ex = {"rowquad": ctx.contraction_flops(0, tri), "wsyrk": ctx.contraction_flops(1, tri)}
         kern = {}
-        for name in ("rowquad", "wsyrk", "xc_fwd", "xc_vjp", "eval_ao"):
+        for name in ("rowquad", "wsyrk", "xc_fwd", "xc_vjp", "eval_ao", "stage4"):
             ms, n = prof[name]
             kern[name] = {"launches": n, "avg_ms": (ms / n) if n else None,
                           "share_of_step": ms / prof_total if prof_total else None}
@@ -423,72 +497,206 @@ def run_ours(args):
                 kern[name]["algorithmic_tflops"] = fl / (ms / n * 1e-3) / 1e12
                 kern[name]["executed_tflops"] = ex[name] / (ms / n * 1e-3) / 1e12
                 kern[name]["executed_frac_of_peak"] = kern[name]["executed_tflops"] / peak_sus if peak_sus else None
-        dom = max(("rowquad", "wsyrk"), key=lambda k: prof[k][0])
+        dom_all = max(kern, key=lambda k: prof[k][0])
+        cpu = None
+        if cpu_seconds > 0 and world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(wl, cpu_seconds)
+        res = {
+            "wl": wl, "value": value, "ms_per_step": ms_step, "kern": kern, "ex": ex, "fl": fl, "dominant": dom_all,
+            "e2e": {"value": npts_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "note": e2e_note,
+                    "bitwise_equal_to_device_path": e2e_same},
+            "launches": int(launches), "clocks": clocks, "cpu": cpu, "mo_ms": mo_ms, "coll": coll,
+            "graph": graph is not None, "Gl": Gl, "Bl": Bc, "npts_total": npts_total, "batch": batch,
+            "workspace_gb": ctx.workspace_bytes / 1e9, "npad": ctx_npad(N),
+        }
+    extras = {"ctx": ctx, "out": out, "bar": bar, "wl": wl, "step": step}
+    return res, extras
+
+
+def parity_vs_single_rank(env: Env, extras):
+    """N > 1: rank 0 recomputes the step on the WHOLE grid by itself and compares it with the sharded,
+    all-reduced result every rank holds (|dE_xc|, V_xc / dm_bar / theta_bar: max-norm and element-wise)."""
+    torch = env.torch
+    from qex_b200 import workloads
+    from qex_b200.engine import XCContext
+
+    wl = extras["wl"]
+    extras["step"]()
+    torch.cuda.synchronize()
+    o_n, b_n = extras["out"].cpu().numpy()[0], extras["bar"].cpu().numpy()
+    res = None
+    if env.rank == 0:
+        N, G = wl.nao, wl.ngrids
+        c1 = XCContext(nao=N, ngrids_max=G, ncomp=wl.ncomp, nbatch=1, net=extras["ctx"].net, device=env.local)
+        c1.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env).set_grid(wl.coords, wl.weights).eval_ao(1 if wl.ncomp == 4 else 0)
+        o1, r1 = c1.nr_rks_fwd(wl.dm, wl.theta, wl.xctype)
+        b1 = c1.nr_rks_vjp(wl.theta, r1, [wl.e_bar], wl.v_bar, wl.xctype).cpu().numpy()
+        o1 = o1.cpu().numpy()[0]
+        nn = N * N
+        v = _err_pair(o_n[:nn], o1[:nn])
+        d = _err_pair(b_n[:nn], b1[:nn])
+        t = _err_pair(b_n[nn:], b1[nn:])
+        res = {"dE_xc_abs": abs(float(o_n[nn] - o1[nn])), "nelec_abs": abs(float(o_n[nn + 1] - o1[nn + 1])),
+               "vxc_maxnorm_rel": v[0], "vxc_elementwise_rel": v[1], "dm_bar_maxnorm_rel": d[0],
+               "dm_bar_elementwise_rel": d[1], "theta_bar_maxnorm_rel": t[0], "theta_bar_elementwise_rel": t[1],
+               "elementwise_floor": "denominator max(|ref|, 1e-6 max|ref|)",
+               "tolerance": "|dE_xc| <= 1e-9 Ha, elements <= 1e-10 relative (north_star)",
+               "ok": bool(abs(o_n[nn] - o1[nn]) <= 1e-9 and max(v[0], d[0], t[0]) <= 1e-10)}
+        c1.close()
+    env.barrier()
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as tdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its banner on STDOUT, next to the one JSON line the driver reads
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from qex_b200.dist import Comm
+
+        comm = Comm(rank, world, local)  # the data-path collectives go through the C ABI (qexxc_allreduce)
+    env = Env(torch, tdist, world, rank, local, comm)
+
+    peak_burst = peak_sus = None
+    if rank == 0:
+        peak_burst, peak_sus = measure_dgemm_peak(torch)
+    res, extras = measure(env, args, args.config, args.precision, args.steps, args.warmup, True, peak_sus,
+                          args.cpu_seconds)
+    parity = parity_vs_single_rank(env, extras) if (world > 1 and not extras["wl"].extra.get("batch")) else None
+    ctx_ws = res["workspace_gb"] if res else None
+    extras["ctx"].close()
+    del extras
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, timed in the same run (single GPU; c4 also when sharded by molecule) ----
+    subs = {}
+    if not args.no_configs and args.ngrids is None and args.config == "c5":
+        todo = SUB_CONFIGS if world == 1 else ("c4",)
+        for name in todo:
+            cfg, prec = ("c5", "f32") if name == "c5_f32" else (name, "f64")
+            try:
+                r, ex2 = measure(env, args, cfg, prec, args.steps, args.warmup, False, peak_sus,
+                                 0.0 if name == "c5_f32" else min(4.0, args.cpu_seconds))
+                ex2["ctx"].close()
+                del ex2
+                torch.cuda.empty_cache()
+                if rank == 0:
+                    k = r["kern"][r["dominant"]]
+                    subs[name] = {
+                        "workload": r["wl"].describe, "network_precision": prec, "value": r["value"], "unit": UNIT,
+                        "ms_per_step": r["ms_per_step"], "grid_points_per_step": r["npts_total"],
+                        "e2e_value": r["e2e"]["value"], "e2e_ms_per_step": r["e2e"]["ms_per_step"],
+                        "dominant_kernel": r["dominant"], "dominant_share_of_step": k["share_of_step"],
+                        "dominant_avg_ms": k["avg_ms"],
+                        "kernel_shares": {n: v["share_of_step"] for n, v in r["kern"].items() if v["launches"]},
+                        "contraction_executed_frac_of_dgemm": {n: r["kern"][n].get("executed_frac_of_peak")
+                                                               for n in ("rowquad", "wsyrk")},
+                        "gpu_launches": r["launches"], "cpu_baseline": r["cpu"],
+                        "launch": "one CUDA graph replay per step" if r["graph"] else "stream launches",
+                    }
+            except Exception as e:  # a failing side config must not lose the headline line
+                if rank == 0:
+                    subs[name] = {"error": f"{type(e).__name__}: {e}"}
+
+    if rank == 0:
+        wl, kern, ex, fl = res["wl"], res["kern"], res["ex"], res["fl"]
+        N, G = wl.nao, wl.ngrids
+        hbm = _hbm_peak()
+        dom = max(("rowquad", "wsyrk"), key=lambda k: (kern[k]["avg_ms"] or 0) * (kern[k]["launches"] or 0))
         avg_ms = kern[dom]["avg_ms"] or float("nan")
-        achieved = fl / (avg_ms * 1e-3) / 1e12
-        # DRAM bytes per launch from the committed `ncu --set full` capture (only valid for the captured shape)
+        achieved_alg = fl / (avg_ms * 1e-3) / 1e12
         traffic = None
         if wl.name == "c5" and world == 1 and G == 1_000_000:
             try:
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["c5"].get(dom + "_kernel")
             except Exception:
                 traffic = None
+        # streaming kernels against the HBM copy peak (algorithmic bytes, SURVEY 8d / DESIGN section 4)
+        C_ = wl.ncomp
+        stream_bytes = {
+            # K1 writes the AO tensor once: 8 B x Npad x C per point (coords in: 24 B)
+            "eval_ao": (8.0 * res["npad"] * C_ + 24.0) * res["Gl"] * res["Bl"],
+            # stage 4 fwd: rho(C) exc vrho (vgamma) w in, wv(C) out; adjoint: the same in + wvb(C), rho_bar(C) exc_bar
+            # vrho_bar (vgamma_bar) out -- summed over the two launches per step and divided by two below
+            "stage4": 0.5 * 8.0 * ((C_ + 3 + (C_ == 4) + C_) + (2 * C_ + 3 + (C_ == 4) + C_ + 2 + (C_ == 4))) * res["Gl"] * res["Bl"],
+        }
+        streaming = {}
+        for name, nbytes in stream_bytes.items():
+            k = kern[name]
+            if k["launches"]:
+                gbs = nbytes / (k["avg_ms"] * 1e-3) / 1e9
+                streaming[name] = {"kernel": {"eval_ao": "eval_ao_kernel (K1)", "stage4": "stage4_fwd/vjp kernels"}[name],
+                                   "bytes_per_launch": nbytes, "avg_ms": k["avg_ms"], "gbs": gbs,
+                                   "frac_of_hbm_peak": gbs / hbm if hbm else None}
         roofline = {
-            "bound": "tensor", "kernel": dom + "_kernel (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak_sus,
-            "unit": "TFLOP/s", "frac": achieved / peak_sus if peak_sus else None, "traffic": traffic,
-            "traffic_note": "dram read+write bytes per launch (ncu capture in profiles/r01/contract_ncu_raw.csv); the AO "
-                            "tensor is 8.2 GB: a CTA re-reads its 1 MB row tile once per column tile and 148 MB of "
-                            "concurrent tiles exceed L2, but the kernel is DMMA-bound (DRAM < 10% busy)",
+            "bound": "tensor", "kernel": dom + "_kernel (FP64 DMMA.8x8x4)",
+            "achieved": kern[dom]["executed_tflops"], "peak": peak_sus, "unit": "TFLOP/s",
+            "frac": kern[dom]["executed_frac_of_peak"], "traffic": traffic,
+            "frac_definition": "EXECUTED DMMA FLOP per launch / launch time / cuBLAS DGEMM sustained peak measured in this "
+                               "run (the pipe fraction); the algorithmic figure is under `algorithmic`",
+            "algorithmic": {"flop_per_launch": fl, "tflops": achieved_alg,
+                            "frac_of_peak": achieved_alg / peak_sus if peak_sus else None,
+                            "note": "SURVEY 8d's 2*G*N^2 per launch; exceeds the pipe fraction because symmetric operands "
+                                    "let the kernels skip the lower-triangular blocks"},
+            "executed_flop_per_launch": ex[dom],
+            "traffic_note": "dram read+write bytes per launch from the committed ncu --set full capture of this shape "
+                            "(profiles/ncu_traffic.json); algorithmic bytes = the AO tensor read once = "
+                            f"{8.0 * res['npad'] * res['Gl'] / 1e9:.2f} GB",
             "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, sustained (MEASURED_PEAKS.json has no FP64 figure); "
                            f"burst {peak_burst:.1f} TFLOP/s",
-            "algorithmic_flop_per_launch": fl, "executed_flop_per_launch": ex[dom],
-            "executed_tflops": kern[dom]["executed_tflops"], "executed_frac": kern[dom]["executed_frac_of_peak"],
-            "note": "achieved/frac use SURVEY 8d's ALGORITHMIC 2*G*N^2 FLOP per launch; the operands are symmetric "
-                    "(S = sym(dm), V_xc = ao^T diag ao), so the kernels execute only the upper-triangular tiles "
-                    "(executed_* fields): frac > 1 is the symmetry saving, executed_frac is the DMMA-pipe efficiency",
+            "streaming": streaming, "hbm_peak_gbs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json (of measured)",
             "kernels": kern,
         }
-        cpu = None if args.no_cpu_baseline or world > 1 else cpu_baseline(wl, args.cpu_seconds)
-        hbm = None
-        try:
-            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
-        except Exception:
-            pass
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": wl.describe, "nao": N, "ngrids": G, "ngrids_per_gpu": Gl, "ncomp": wl.ncomp,
-                       "batch": batch, "grid_points_per_step": npts_total,
-                       "network_precision": args.precision, "parallelism": (f"molecules sharded round-robin x{world} (replicas), NCCL all-reduce of theta_bar only" if batch else
-                                       f"grid-sharded x{world}, NCCL all-reduce of packed V_xc|E_xc|nelec and dm_bar|theta_bar"),
-                       "l2": "inputs larger than L2 (AO tensor %.1f GB per pass)" % (Gl * ctx_npad(N) * 8 * wl.ncomp / 1e9),
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.describe, "nao": N, "ngrids": G, "ngrids_per_gpu": res["Gl"], "ncomp": wl.ncomp,
+                       "batch": res["batch"], "grid_points_per_step": res["npts_total"],
+                       "network_precision": args.precision,
+                       "parallelism": (f"molecules sharded round-robin x{world} (replicas), NCCL all-reduce of theta_bar only"
+                                       if res["batch"] else
+                                       f"grid-sharded x{world} (128-aligned contiguous ranges), NCCL all-reduce of packed "
+                                       "V_xc|E_xc|nelec and dm_bar|theta_bar via qexxc_allreduce"),
+                       "l2": "inputs larger than L2 (AO tensor %.1f GB per pass)" % (res["Gl"] * res["npad"] * 8 * wl.ncomp / 1e9),
                        "step": "set_grid + eval_ao (K1) + nr_rks fwd + nr_rks VJP",
-                       "launch": "one CUDA graph replay per step (kernel table from an un-graphed pass)" if graph is not None
+                       "launch": "one CUDA graph replay per step (kernel table from an un-graphed pass)" if res["graph"]
                        else "stream launches"},
-            "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": npts_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
-            "mo_path": None if mo_ms is None else {
-                "value": npts_total / (mo_ms * 1e-3), "unit": UNIT, "ms_per_step": mo_ms,
+            "roofline": roofline, "cpu_baseline": res["cpu"], "e2e": res["e2e"],
+            "mo_path": None if res["mo_ms"] is None else {
+                "value": res["npts_total"] / (res["mo_ms"] * 1e-3), "unit": UNIT, "ms_per_step": res["mo_ms"],
                 "note": "same step with stage 2 in its MO form rho = sum_k occ_k (ao C_k)^2 (150 occupied orbitals), the "
                         "branch the reference takes when dm carries mo_coeff/mo_occ (numint_legacy.py:527-545); not the headline"},
-            "gpu_launches": int(launches), "clocks": clocks, "hbm_peak_gbs": hbm,
-            "workspace_gb": ctx.workspace_bytes / 1e9,
+            "collectives": res["coll"], "parity_vs_n1": parity, "configs": subs,
+            "gpu_launches": res["launches"], "clocks": res["clocks"], "hbm_peak_gbs": hbm, "workspace_gb": ctx_ws,
+            "parity_note": "oracle = NumPy restatement of the reference (JAX/pyscfad/horqrux not installable here): MLP, QNN "
+                           "and l>0 AO arithmetic have no reference-held pin; the jax.ffi shim is written but cannot be "
+                           "built or run in this image",
         }
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
-        dist.destroy_process_group()
-
-
-def ctx_npad(N):  # AO row pitch: a multiple of 32 columns (zeros in the pad)
-    return ((N + 31) // 32) * 32
+        tdist.destroy_process_group()
 
 
 def run_widening(args):
     """`--config n2jk` / `--config c4scf`: the measurements of scripts/bench_jk.py and scripts/bench_scf_c4.py
     with their CPU baselines; bench.py is the one place that may time code under oracle/."""
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    cores = _set_cpu_threads()
     if args.config == "n2jk":
         import bench_jk
         from oracle import jk_ref
@@ -499,7 +707,7 @@ def run_widening(args):
         t0 = time.perf_counter()
         jk_ref.dot_eri_dm(e_c, d_c)
         t_cpu = time.perf_counter() - t0
-        cpu = {"value": 8.0 * Nc**4 / t_cpu / 1e9, "unit": "GB/s", "cores": _cpu_threads(), "kind": "port",
+        cpu = {"value": 8.0 * Nc**4 / t_cpu / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
                "sample": f"numpy einsum oracle (J and K) on a [{Nc}]^4 tensor"}
         line = bench_jk.measure(bench_jk.parse([]), cpu)
     elif args.config == "c1train":
@@ -515,7 +723,7 @@ def run_widening(args):
             t0 = time.perf_counter()
             train_ref.batch_loss(theta, spec, data, 1.0, 1.0, is_global=is_global, max_cycle=cycles)
             t = time.perf_counter() - t0
-            return {"value": 1.0 / t, "unit": "it/s", "cores": _cpu_threads(), "kind": "port",
+            return {"value": 1.0 / t, "unit": "it/s", "cores": cores, "kind": "port",
                     "sample": "ONE forward evaluation of the batch loss by the numpy restatement (no gradient: the "
                               "reference's step adds a reverse pass, so this over-states its rate)"}
 
@@ -534,7 +742,7 @@ def run_widening(args):
                                  lambda rho: mlp_ref.exc_and_vrho_local(spec, theta, rho), max_cycle=cycles)
             s_per_mol = (time.perf_counter() - t0) / nc
             return {"value": grids[0].size * (cycles + 1) / s_per_mol, "unit": "grid-pts/s", "kind": "port",
-                    "cores": _cpu_threads(), "s_per_molecule": s_per_mol,
+                    "cores": cores, "s_per_molecule": s_per_mol,
                     "sample": f"numpy oracle scf_loop on {nc} of the {len(mols)} molecules"}
 
         line = bench_scf_c4.measure(bench_scf_c4.parse([]), cpu_fn)

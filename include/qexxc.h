@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QEXXC_VERSION 100
+#define QEXXC_VERSION 200
 
 #define QEXXC_OK 0
 #define QEXXC_ERR_CUDA (-1)        /* a CUDA runtime call or kernel launch failed */
@@ -94,6 +94,13 @@ long qexxc_n_params(const qexxc_net_desc* net, int ngrids);
  * (JAX allocates implicitly); it is the price of "no allocation on the hot call". */
 int qexxc_create(qexxc_ctx** ctx, int device, int nbatch, int ncomp, int ngrids_max, int nao,
                  const qexxc_net_desc* net);
+/* As qexxc_create, with flags.  QEXXC_FLAG_SHARED_AO: the nbatch elements are `nset` density matrices of ONE
+ * molecule / grid (the `for idm in range(nset)` loop of nr_rks, numint_legacy.py:141-156,292-310, as one launch
+ * per stage): a single AO tensor [C][G][N], grid and geometry serve the whole batch -- set_grid takes coords
+ * [G][3], weights [G]; set_basis env [nenv]; set_ao / get_ao [C][G][N]; dm, out, resid keep their [B] dimension. */
+#define QEXXC_FLAG_SHARED_AO 1u
+int qexxc_create_ex(qexxc_ctx** ctx, int device, int nbatch, int ncomp, int ngrids_max, int nao,
+                    const qexxc_net_desc* net, unsigned flags);
 int qexxc_destroy(qexxc_ctx* ctx);
 /* bytes of device memory held by the context */
 size_t qexxc_workspace_bytes(const qexxc_ctx* ctx);
@@ -134,16 +141,19 @@ int qexxc_eval_rho_vjp(qexxc_ctx* ctx, const double* rho_bar_dev, int ncomp, int
  *   (, vgamma_bar) -> rho_bar [B][C][G], theta_bar [n_params] (summed over batch and grid).
  * qexxc_apply_fn_fwd/_vjp: network apply_fn(params, inputs) (networks.py:43-75;
  *   classical_models.py:168-172; quantum_models.py:759-774): x [npts][n_features] -> y [npts]
- *   (global MLP: x [ngrids] -> y [1]); VJP: y_bar -> x_bar, theta_bar. */
-int qexxc_xc_fwd(qexxc_ctx* ctx, int xctype, const double* rho_dev, const double* theta_dev,
+ *   (global MLP: x [ngrids] -> y [1]); VJP: y_bar -> x_bar, theta_bar.
+ * Every entry that takes `theta_dev` also takes its length `n_theta` and fails with QEXXC_ERR_ARG unless it
+ * equals qexxc_n_params(net, G) for the grid in use (the reference raises a shape error when the parameter
+ * tree does not fit the network; a bare pointer could not be checked). */
+int qexxc_xc_fwd(qexxc_ctx* ctx, int xctype, const double* rho_dev, const double* theta_dev, long n_theta,
                  double* exc_dev, double* vrho_dev, double* vgamma_dev, void* stream);
-int qexxc_xc_vjp(qexxc_ctx* ctx, int xctype, const double* rho_dev, const double* theta_dev,
+int qexxc_xc_vjp(qexxc_ctx* ctx, int xctype, const double* rho_dev, const double* theta_dev, long n_theta,
                  const double* exc_bar_dev, const double* vrho_bar_dev,
                  const double* vgamma_bar_dev, double* rho_bar_dev, double* theta_bar_dev,
                  void* stream);
-int qexxc_apply_fn_fwd(qexxc_ctx* ctx, const double* x_dev, long npts, const double* theta_dev,
+int qexxc_apply_fn_fwd(qexxc_ctx* ctx, const double* x_dev, long npts, const double* theta_dev, long n_theta,
                        double* y_dev, void* stream);
-int qexxc_apply_fn_vjp(qexxc_ctx* ctx, const double* x_dev, long npts, const double* theta_dev,
+int qexxc_apply_fn_vjp(qexxc_ctx* ctx, const double* x_dev, long npts, const double* theta_dev, long n_theta,
                        const double* y_bar_dev, double* x_bar_dev, double* theta_bar_dev,
                        void* stream);
 
@@ -179,12 +189,34 @@ size_t qexxc_resid_doubles(const qexxc_ctx* ctx);
 int qexxc_eval_rho_mo(qexxc_ctx* ctx, const double* mo_coeff_dev, const double* mo_occ_dev, int nmo,
                       double* rho_dev, void* stream);
 int qexxc_nr_rks_fwd_mo(qexxc_ctx* ctx, int xctype, const double* mo_coeff_dev, const double* mo_occ_dev, int nmo,
-                        const double* theta_dev, double* out_dev, double* resid_dev, void* stream);
+                        const double* theta_dev, long n_theta, double* out_dev, double* resid_dev, void* stream);
 int qexxc_nr_rks_fwd(qexxc_ctx* ctx, int xctype, int hermi, const double* dm_dev,
-                     const double* theta_dev, double* out_dev, double* resid_dev, void* stream);
-int qexxc_nr_rks_vjp(qexxc_ctx* ctx, int xctype, int hermi, const double* theta_dev,
+                     const double* theta_dev, long n_theta, double* out_dev, double* resid_dev, void* stream);
+int qexxc_nr_rks_vjp(qexxc_ctx* ctx, int xctype, int hermi, const double* theta_dev, long n_theta,
                      const double* resid_dev, const double* e_bar_dev, const double* v_bar_dev,
                      double* bar_dev, void* stream);
+
+/* ---- multi-GPU: the one exchange step of the path -------------------------------
+ * The grid shards by point ranges, one process per GPU; dm / theta / basis are replicated.  The reference has no
+ * multi-device code; these calls are what a grid-sharded caller adds around nr_rks:
+ *   qexxc_allreduce: in-place sum over ranks of a packed output buffer -- `out` [B][N*N+2] of qexxc_nr_rks_fwd
+ *     (vmat | excsum | nelec) or `bar` of qexxc_nr_rks_vjp (dm_bar | theta_bar) -- one collective per direction;
+ *   qexxc_bcast: replicate (dm | theta | cotangents) from the rank that received them from the host.
+ * A qexxc_comm wraps an ncclComm_t: either created here (rank 0 calls qexxc_comm_unique_id, ships the 128 bytes to
+ * the other ranks by any side channel, every rank calls qexxc_comm_create) or borrowed from the host framework
+ * (qexxc_comm_wrap; not destroyed by qexxc_comm_destroy).  NCCL is bound with dlopen at first use; without it the
+ * calls fail with QEXXC_ERR_STATE.  Collectives are enqueued on `stream` and never synchronise the host. */
+typedef struct qexxc_comm qexxc_comm;
+int qexxc_comm_nccl_version(int* version);
+int qexxc_comm_unique_id(unsigned char id[128]);
+int qexxc_comm_create(qexxc_comm** comm, int device, int world, int rank, const unsigned char id[128]);
+int qexxc_comm_wrap(qexxc_comm** comm, void* nccl_comm, int device, int world, int rank);
+int qexxc_comm_destroy(qexxc_comm* comm);
+int qexxc_comm_rank(const qexxc_comm* comm);
+int qexxc_comm_world(const qexxc_comm* comm);
+long qexxc_comm_calls(const qexxc_comm* comm); /* collectives enqueued since creation */
+int qexxc_allreduce(qexxc_comm* comm, double* buf_dev, long count, void* stream);
+int qexxc_bcast(qexxc_comm* comm, double* buf_dev, long count, int root, void* stream);
 
 /* ---- introspection for the benchmark -------------------------------------------------------
  * Number of kernels this library launched on the context since creation (gpu_launches). */
@@ -197,7 +229,8 @@ long qexxc_launch_count(const qexxc_ctx* ctx);
 #define QEXXC_PROF_XC_FWD 2
 #define QEXXC_PROF_XC_VJP 3
 #define QEXXC_PROF_EVAL_AO 4
-#define QEXXC_PROF_NCLASS 5
+#define QEXXC_PROF_STAGE4 5 /* the streaming stage-4 kernels: wv / E_xc / nelec forward, and their adjoint */
+#define QEXXC_PROF_NCLASS 6
 int qexxc_profile_enable(qexxc_ctx* ctx, int on);
 int qexxc_profile_read(qexxc_ctx* ctx, int cls, double* ms_total, long* count);
 /* DMMA FLOPs the contraction kernels actually execute for the current problem shape (zero-padded and

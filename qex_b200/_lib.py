@@ -22,7 +22,7 @@ ACTIVATIONS = {
 ERR_CUDA, ERR_ARG, ERR_STATE, ERR_UNSUPPORTED, ERR_NODEVICE = -1, -2, -3, -4, -5
 
 EXPORTS = [
-    "qexxc_version", "qexxc_last_error", "qexxc_n_params", "qexxc_create", "qexxc_destroy",
+    "qexxc_version", "qexxc_last_error", "qexxc_n_params", "qexxc_create", "qexxc_create_ex", "qexxc_destroy",
     "qexxc_workspace_bytes", "qexxc_set_grid", "qexxc_set_basis", "qexxc_eval_ao", "qexxc_set_ao",
     "qexxc_get_ao", "qexxc_eval_rho", "qexxc_eval_rho_vjp", "qexxc_xc_fwd", "qexxc_xc_vjp",
     "qexxc_apply_fn_fwd", "qexxc_apply_fn_vjp", "qexxc_vxc_assemble", "qexxc_vxc_assemble_vjp",
@@ -31,6 +31,8 @@ EXPORTS = [
     "qexxc_jk_workspace_doubles", "qexxc_dot_eri_dm", "qexxc_dot_eri_dm_vjp", "qexxc_jk_launch_count",
     "qexxc_dot_eri_dm_batched", "qexxc_dot_eri_dm_vjp_batched", "qexxc_generalized_eigh_batched",
     "qexxc_becke_partition", "qexxc_grid_launch_count", "qexxc_lda_exchange", "qexxc_lda_launch_count",
+    "qexxc_comm_nccl_version", "qexxc_comm_unique_id", "qexxc_comm_create", "qexxc_comm_wrap", "qexxc_comm_destroy",
+    "qexxc_comm_rank", "qexxc_comm_world", "qexxc_comm_calls", "qexxc_allreduce", "qexxc_bcast",
 ]
 
 
@@ -46,6 +48,10 @@ class QexxcError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libqexxc error {code}: {msg}")
         self.code = code
+
+
+class QexxcArgError(QexxcError, ValueError):
+    """QEXXC_ERR_ARG: a shape / size mismatch (the reference raises a shape ValueError there)."""
 
 
 _lib = None
@@ -73,6 +79,7 @@ def load(build_if_missing: bool = False):
         "qexxc_last_error": (C.c_char_p, []),
         "qexxc_n_params": (l, [C.POINTER(NetDesc), i]),
         "qexxc_create": (i, [C.POINTER(vp), i, i, i, i, i, C.POINTER(NetDesc)]),
+        "qexxc_create_ex": (i, [C.POINTER(vp), i, i, i, i, i, C.POINTER(NetDesc), C.c_uint]),
         "qexxc_destroy": (i, [vp]),
         "qexxc_workspace_bytes": (C.c_size_t, [vp]),
         "qexxc_set_grid": (i, [vp, p, p, i, vp]),
@@ -82,20 +89,20 @@ def load(build_if_missing: bool = False):
         "qexxc_get_ao": (i, [vp, p, i, vp]),
         "qexxc_eval_rho": (i, [vp, p, i, i, p, vp]),
         "qexxc_eval_rho_vjp": (i, [vp, p, i, i, p, vp]),
-        "qexxc_xc_fwd": (i, [vp, i, p, p, p, p, p, vp]),
-        "qexxc_xc_vjp": (i, [vp, i, p, p, p, p, p, p, p, vp]),
-        "qexxc_apply_fn_fwd": (i, [vp, p, l, p, p, vp]),
-        "qexxc_apply_fn_vjp": (i, [vp, p, l, p, p, p, p, vp]),
+        "qexxc_xc_fwd": (i, [vp, i, p, p, l, p, p, p, vp]),
+        "qexxc_xc_vjp": (i, [vp, i, p, p, l, p, p, p, p, p, vp]),
+        "qexxc_apply_fn_fwd": (i, [vp, p, l, p, l, p, vp]),
+        "qexxc_apply_fn_vjp": (i, [vp, p, l, p, l, p, p, p, vp]),
         "qexxc_vxc_assemble": (i, [vp, i, p, p, p, p, p, vp]),
         "qexxc_vxc_assemble_vjp": (i, [vp, i, p, p, p, p, p, p, p, p, p, p, vp]),
         "qexxc_resid_doubles": (C.c_size_t, [vp]),
-        "qexxc_nr_rks_fwd": (i, [vp, i, i, p, p, p, p, vp]),
-        "qexxc_nr_rks_vjp": (i, [vp, i, i, p, p, p, p, p, vp]),
+        "qexxc_nr_rks_fwd": (i, [vp, i, i, p, p, l, p, p, vp]),
+        "qexxc_nr_rks_vjp": (i, [vp, i, i, p, l, p, p, p, p, vp]),
         "qexxc_launch_count": (l, [vp]),
         "qexxc_debug_run_contraction": (i, [vp, i, vp]),
         "qexxc_profile_enable": (i, [vp, i]),
         "qexxc_eval_rho_mo": (i, [vp, p, p, i, p, vp]),
-        "qexxc_nr_rks_fwd_mo": (i, [vp, i, p, p, i, p, p, p, vp]),
+        "qexxc_nr_rks_fwd_mo": (i, [vp, i, p, p, i, p, l, p, p, vp]),
         "qexxc_contraction_flops": (i, [vp, i, i, C.POINTER(C.c_double)]),
         "qexxc_profile_read": (i, [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
         "qexxc_jk_workspace_doubles": (i, [i, i, C.POINTER(C.c_long)]),
@@ -109,6 +116,16 @@ def load(build_if_missing: bool = False):
         "qexxc_grid_launch_count": (l, []),
         "qexxc_lda_exchange": (i, [i, p, l, p, p, vp]),
         "qexxc_lda_launch_count": (l, []),
+        "qexxc_comm_nccl_version": (i, [C.POINTER(i)]),
+        "qexxc_comm_unique_id": (i, [p]),
+        "qexxc_comm_create": (i, [C.POINTER(vp), i, i, i, p]),
+        "qexxc_comm_wrap": (i, [C.POINTER(vp), vp, i, i, i]),
+        "qexxc_comm_destroy": (i, [vp]),
+        "qexxc_comm_rank": (i, [vp]),
+        "qexxc_comm_world": (i, [vp]),
+        "qexxc_comm_calls": (l, [vp]),
+        "qexxc_allreduce": (i, [vp, p, l, vp]),
+        "qexxc_bcast": (i, [vp, p, l, i, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -127,4 +144,6 @@ def check(rc: int):
         msg = last_error()
         if rc == ERR_UNSUPPORTED:
             raise NotImplementedError(msg)  # the reference raises NotImplementedError / ValueError here
+        if rc == ERR_ARG:
+            raise QexxcArgError(rc, msg)
         raise QexxcError(rc, msg)

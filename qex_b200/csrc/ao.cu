@@ -281,14 +281,15 @@ __global__ void unpack_ao_kernel(double* __restrict__ dst, const double* __restr
     }
 }
 
+// shared: one source grid [G] for every batch element (weights are replicated, coordinates kept once)
 __global__ void set_grid_kernel(const double* __restrict__ coords, const double* __restrict__ weights,
-                                double* __restrict__ cdst, double* __restrict__ wdst, int G, int GpadMax) {
-    const int b = blockIdx.y;
+                                double* __restrict__ cdst, double* __restrict__ wdst, int G, int GpadMax, int shared) {
+    const int b = blockIdx.y, bs = shared ? 0 : b;
     for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < GpadMax;
          gi += (long)gridDim.x * blockDim.x) {
         const bool in = gi < G;
-        wdst[(long)b * GpadMax + gi] = in ? weights[(long)b * G + gi] : 0.0;
-        if (coords) {
+        wdst[(long)b * GpadMax + gi] = in ? weights[(long)bs * G + gi] : 0.0;
+        if (coords && (!shared || b == 0)) {
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 cdst[((long)b * GpadMax + gi) * 3 + k] = in ? coords[((long)b * G + gi) * 3 + k] : 0.0;
@@ -308,7 +309,7 @@ inline unsigned grid_for(long total, int threads, int num_sms) {
 
 int launch_set_grid(qexxc_ctx* c, const double* coords, const double* weights, int G, cudaStream_t st) {
     dim3 grid(grid_for(c->GpadMax, 256, c->num_sms), c->B);
-    set_grid_kernel<<<grid, 256, 0, st>>>(coords, weights, c->coords, c->weights, G, c->GpadMax);
+    set_grid_kernel<<<grid, 256, 0, st>>>(coords, weights, c->coords, c->weights, G, c->GpadMax, c->ao_shared ? 1 : 0);
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;
 }
@@ -322,7 +323,7 @@ int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
     if (P >= 1) {
         const size_t smem = ((size_t)(deriv ? 68 : 17) * (((size_t)P * c->natm) | 1) +
                              (size_t)P * c->nrad * (deriv ? 2 : 1)) * 8;
-        dim3 tgrid((unsigned)((c->Gpad + P - 1) / P), c->B);
+        dim3 tgrid((unsigned)((c->Gpad + P - 1) / P), c->ao_shared ? 1 : c->B);
         // two resident CTAs share the SM's shared memory whatever the block size, so wide blocks double the
         // resident warps (the kernel is latency-bound, not pipe-bound); small molecules keep 256 threads
         int nthr = ((long)P * c->natm >= 256 || c->Npad >= 512) ? 512 : 256;
@@ -341,7 +342,7 @@ int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
         QX_LAUNCH_CHECK(c);
         return QEXXC_OK;
     }
-    dim3 grid(grid_for((long)c->Gpad * 32, 256, c->num_sms), c->B);
+    dim3 grid(grid_for((long)c->Gpad * 32, 256, c->num_sms), c->ao_shared ? 1 : c->B);
     eval_ao_kernel<<<grid, 256, 0, st>>>(c->coords, c->shells, c->nshell, c->env, c->nenv, c->ao, c->G,
                                          c->Gpad, c->GpadMax, c->N, c->Npad, c->C, deriv);
     QX_LAUNCH_CHECK(c);
@@ -349,14 +350,14 @@ int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
 }
 
 int launch_pack_ao(qexxc_ctx* c, const double* src, int ncomp, int G, cudaStream_t st) {
-    dim3 grid(grid_for((long)c->Gpad * c->Npad, 256, c->num_sms), ncomp, c->B);
+    dim3 grid(grid_for((long)c->Gpad * c->Npad, 256, c->num_sms), ncomp, c->ao_shared ? 1 : c->B);
     pack_ao_kernel<<<grid, 256, 0, st>>>(src, c->ao, ncomp, G, c->Gpad, c->GpadMax, c->N, c->Npad, c->C);
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;
 }
 
 int launch_unpack_ao(qexxc_ctx* c, double* dst, int ncomp, cudaStream_t st) {
-    dim3 grid(grid_for((long)c->G * c->N, 256, c->num_sms), ncomp, c->B);
+    dim3 grid(grid_for((long)c->G * c->N, 256, c->num_sms), ncomp, c->ao_shared ? 1 : c->B);
     unpack_ao_kernel<<<grid, 256, 0, st>>>(dst, c->ao, ncomp, c->G, c->GpadMax, c->N, c->Npad, c->C);
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;

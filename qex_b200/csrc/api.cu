@@ -41,6 +41,21 @@ static int dev_alloc(qexxc_ctx* c, T** p, size_t count, bool zero = true) {
     return QEXXC_OK;
 }
 
+// frees a buffer obtained from dev_alloc (count = the element count it was allocated with)
+template <typename T>
+static void dev_free(qexxc_ctx* c, T** p, size_t count) {
+    if (!*p) return;
+    if (count == 0) count = 1;
+    for (size_t k = 0; k < c->allocs.size(); ++k)
+        if (c->allocs[k] == (void*)*p) {
+            c->allocs.erase(c->allocs.begin() + k);
+            break;
+        }
+    cudaFree(*p);
+    c->bytes -= count * sizeof(T);
+    *p = nullptr;
+}
+
 static int ncomp_of(int xctype) { return xctype == QEXXC_XC_GGA ? 4 : 1; }
 
 static int check_xctype(const qexxc_ctx* c, int xctype, bool need_net) {
@@ -156,6 +171,17 @@ static int nr_rks_after_rho(qexxc_ctx* c, int xctype, const double* theta_dev, d
     return QEXXC_OK;
 }
 
+// theta length check (the reference raises a shape error when the parameter tree does not fit the network)
+static int check_theta(const qexxc_ctx* c, long n_theta, long G) {
+    const long want = qexxc_n_params(&c->net, (int)G);
+    if (n_theta != want) {
+        set_error("theta has %ld parameters but the context's network needs %ld (kind %d, n_features %d, n_hidden %d, "
+                  "width %d, grid %ld)", n_theta, want, c->net.kind, c->net.n_features, c->net.n_hidden, c->net.width, G);
+        return QEXXC_ERR_ARG;
+    }
+    return QEXXC_OK;
+}
+
 static int need_ao(const qexxc_ctx* c, int ncomp) {
     if (!c->have_grid) {
         set_error("qexxc_set_grid has not been called");
@@ -197,7 +223,13 @@ long qexxc_n_params(const qexxc_net_desc* net, int ngrids) {
 
 int qexxc_create(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngrids_max, int nao,
                  const qexxc_net_desc* net) {
+    return qexxc_create_ex(out, device, nbatch, ncomp, ngrids_max, nao, net, 0u);
+}
+
+int qexxc_create_ex(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngrids_max, int nao,
+                    const qexxc_net_desc* net, unsigned flags) {
     QX_ARG(out != nullptr, "ctx out pointer is null");
+    QX_ARG((flags & ~(unsigned)QEXXC_FLAG_SHARED_AO) == 0, "unknown flag bits");
     *out = nullptr;
     QX_ARG(nbatch >= 1 && ngrids_max >= 1 && nao >= 1, "nbatch, ngrids_max, nao must be >= 1");
     QX_ARG(ncomp == 1 || ncomp == 4, "ncomp must be 1 or 4");
@@ -211,6 +243,7 @@ int qexxc_create(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngrids_
     QX_CUDA(cudaSetDevice(device));
     qexxc_ctx* c = new qexxc_ctx();
     c->device = device;
+    c->ao_shared = (flags & QEXXC_FLAG_SHARED_AO) != 0;
     c->B = nbatch;
     c->C = ncomp;
     c->Gmax = ngrids_max;
@@ -241,7 +274,7 @@ int qexxc_create(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngrids_
     if (rc == QEXXC_OK) rc = dev_alloc(c, &(ptr), (count))
     QX_A(c->coords, B * Gp * 3);
     QX_A(c->weights, B * Gp);
-    QX_A(c->ao, B * C * Gp * Np);
+    QX_A(c->ao, (c->ao_shared ? 1 : B) * C * Gp * Np);
     QX_A(c->S, B * Np * Np);
     QX_A(c->mosgn, B * Np);
     QX_A(c->rho, B * C * Gp);
@@ -332,6 +365,7 @@ int qexxc_set_basis(qexxc_ctx* c, const int* atm, int natm, const int* bas, int 
     QX_ARG(c != nullptr, "ctx is null");
     QX_ARG(atm && bas && env && natm > 0 && nbas > 0 && nenv > 0, "null/empty basis tables");
     QX_CUDA(cudaSetDevice(c->device));
+    const int nb = c->ao_shared ? 1 : c->B;  // geometries held: one per batch element unless the AO tensor is shared
     std::vector<ShellDev> sh(nbas);
     std::vector<AoMeta> meta(c->Npad, AoMeta{0, 0, -1});
     std::vector<int> acoord(natm), shatom(nbas);
@@ -365,24 +399,23 @@ int qexxc_set_basis(qexxc_ctx* c, const int* atm, int natm, const int* bas, int 
         set_error("basis has %d spherical AOs but the context was created with nao = %d", off, c->N);
         return QEXXC_ERR_ARG;
     }
-    if (c->nshell != nbas || !c->shells) {
-        c->shells = nullptr;
+    // (re)allocate the basis tables; a replaced buffer is freed and dropped from the context's bookkeeping
+    if (c->nshell != nbas || !c->shells || !c->shell_atom) {
+        dev_free(c, &c->shells, (size_t)c->nshell);
+        dev_free(c, &c->shell_atom, (size_t)c->nshell);
         QX_TRY(dev_alloc(c, &c->shells, (size_t)nbas, false));
+        QX_TRY(dev_alloc(c, &c->shell_atom, (size_t)nbas, false));
         c->nshell = nbas;
     }
     if (c->nenv != nenv || !c->env) {
-        c->env = nullptr;
-        QX_TRY(dev_alloc(c, &c->env, (size_t)c->B * nenv, false));
+        dev_free(c, &c->env, (size_t)nb * c->nenv);
+        QX_TRY(dev_alloc(c, &c->env, (size_t)nb * nenv, false));
         c->nenv = nenv;
     }
     if (!c->ao_meta) QX_TRY(dev_alloc(c, &c->ao_meta, (size_t)c->Npad, false));
     if (c->natm != natm || !c->atom_coord) {
-        c->atom_coord = nullptr;
+        dev_free(c, &c->atom_coord, (size_t)c->natm);
         QX_TRY(dev_alloc(c, &c->atom_coord, (size_t)natm, false));
-    }
-    if (!c->shell_atom || c->nshell != nbas) {
-        c->shell_atom = nullptr;
-        QX_TRY(dev_alloc(c, &c->shell_atom, (size_t)nbas, false));
     }
     c->natm = natm;
     c->nrad = rad;
@@ -391,7 +424,7 @@ int qexxc_set_basis(qexxc_ctx* c, const int* atm, int natm, const int* bas, int 
     QX_CUDA(cudaMemcpy(c->atom_coord, acoord.data(), sizeof(int) * natm, cudaMemcpyHostToDevice));
     QX_CUDA(cudaMemcpy(c->shell_atom, shatom.data(), sizeof(int) * nbas, cudaMemcpyHostToDevice));
     QX_CUDA(cudaMemcpy(c->shells, sh.data(), sizeof(ShellDev) * nbas, cudaMemcpyHostToDevice));
-    QX_CUDA(cudaMemcpy(c->env, env, sizeof(double) * (size_t)c->B * nenv, cudaMemcpyHostToDevice));
+    QX_CUDA(cudaMemcpy(c->env, env, sizeof(double) * (size_t)nb * nenv, cudaMemcpyHostToDevice));
     c->have_basis = true;
     c->ao_ncomp = 0;
     return QEXXC_OK;
@@ -471,14 +504,15 @@ int qexxc_eval_rho_vjp(qexxc_ctx* c, const double* rho_bar_dev, int ncomp, int h
 }
 
 // ---- stage 3 --------------------------------------------------------------------------------
-int qexxc_xc_fwd(qexxc_ctx* c, int xctype, const double* rho_dev, const double* theta_dev, double* exc_dev,
-                 double* vrho_dev, double* vgamma_dev, void* stream) {
+int qexxc_xc_fwd(qexxc_ctx* c, int xctype, const double* rho_dev, const double* theta_dev, long n_theta,
+                 double* exc_dev, double* vrho_dev, double* vgamma_dev, void* stream) {
     QX_ARG(c != nullptr && rho_dev && theta_dev && exc_dev && vrho_dev, "null pointer");
     QX_TRY(check_xctype(c, xctype, true));
     if (!c->have_grid) {
         set_error("qexxc_set_grid has not been called");
         return QEXXC_ERR_STATE;
     }
+    QX_TRY(check_theta(c, n_theta, c->G));
     QX_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long ld = c->GpadMax;
@@ -496,7 +530,7 @@ int qexxc_xc_fwd(qexxc_ctx* c, int xctype, const double* rho_dev, const double* 
     return QEXXC_OK;
 }
 
-int qexxc_xc_vjp(qexxc_ctx* c, int xctype, const double* rho_dev, const double* theta_dev,
+int qexxc_xc_vjp(qexxc_ctx* c, int xctype, const double* rho_dev, const double* theta_dev, long n_theta,
                  const double* exc_bar_dev, const double* vrho_bar_dev, const double* vgamma_bar_dev,
                  double* rho_bar_dev, double* theta_bar_dev, void* stream) {
     QX_ARG(c != nullptr && rho_dev && theta_dev && exc_bar_dev && vrho_bar_dev && rho_bar_dev && theta_bar_dev,
@@ -507,6 +541,7 @@ int qexxc_xc_vjp(qexxc_ctx* c, int xctype, const double* rho_dev, const double* 
         return QEXXC_ERR_STATE;
     }
     QX_ARG(xctype != QEXXC_XC_GGA || vgamma_bar_dev != nullptr, "vgamma_bar is null for xctype GGA");
+    QX_TRY(check_theta(c, n_theta, c->G));
     QX_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long ld = c->GpadMax;
@@ -578,16 +613,18 @@ static int apply_fn_common(qexxc_ctx* c, bool vjp, const double* x_dev, long npt
     return launch_transpose_out(c, x_bar_dev, c->rbar, npad, npts, F, st);
 }
 
-int qexxc_apply_fn_fwd(qexxc_ctx* c, const double* x_dev, long npts, const double* theta_dev, double* y_dev,
-                       void* stream) {
+int qexxc_apply_fn_fwd(qexxc_ctx* c, const double* x_dev, long npts, const double* theta_dev, long n_theta,
+                       double* y_dev, void* stream) {
     QX_ARG(c != nullptr && x_dev && theta_dev && y_dev, "null pointer");
+    QX_TRY(check_theta(c, n_theta, npts));
     QX_CUDA(cudaSetDevice(c->device));
     return apply_fn_common(c, false, x_dev, npts, theta_dev, y_dev, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-int qexxc_apply_fn_vjp(qexxc_ctx* c, const double* x_dev, long npts, const double* theta_dev,
+int qexxc_apply_fn_vjp(qexxc_ctx* c, const double* x_dev, long npts, const double* theta_dev, long n_theta,
                        const double* y_bar_dev, double* x_bar_dev, double* theta_bar_dev, void* stream) {
     QX_ARG(c != nullptr && x_dev && theta_dev && y_bar_dev && x_bar_dev && theta_bar_dev, "null pointer");
+    QX_TRY(check_theta(c, n_theta, npts));
     QX_CUDA(cudaSetDevice(c->device));
     return apply_fn_common(c, true, x_dev, npts, theta_dev, nullptr, y_bar_dev, x_bar_dev, theta_bar_dev,
                            (cudaStream_t)stream);
@@ -662,11 +699,12 @@ int qexxc_vxc_assemble_vjp(qexxc_ctx* c, int xctype, const double* rho_dev, cons
 size_t qexxc_resid_doubles(const qexxc_ctx* c) { return c ? (size_t)c->B * c->GpadMax * (c->C + 3) : 0; }
 
 int qexxc_nr_rks_fwd(qexxc_ctx* c, int xctype, int hermi, const double* dm_dev, const double* theta_dev,
-                     double* out_dev, double* resid_dev, void* stream) {
+                     long n_theta, double* out_dev, double* resid_dev, void* stream) {
     QX_ARG(c != nullptr && dm_dev && theta_dev && out_dev, "null pointer");
     QX_TRY(check_xctype(c, xctype, true));
     const int nc = ncomp_of(xctype);
     QX_TRY(need_ao(c, nc));
+    QX_TRY(check_theta(c, n_theta, c->G));
     QX_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long ld = c->GpadMax;
@@ -691,7 +729,7 @@ int qexxc_eval_rho_mo(qexxc_ctx* c, const double* mo_coeff_dev, const double* mo
 }
 
 int qexxc_nr_rks_fwd_mo(qexxc_ctx* c, int xctype, const double* mo_coeff_dev, const double* mo_occ_dev, int nmo,
-                        const double* theta_dev, double* out_dev, double* resid_dev, void* stream) {
+                        const double* theta_dev, long n_theta, double* out_dev, double* resid_dev, void* stream) {
     QX_ARG(c != nullptr && mo_coeff_dev && mo_occ_dev && theta_dev && out_dev, "null pointer");
     QX_ARG(nmo >= 1 && nmo <= c->N, "nmo must be in [1, nao]");
     QX_TRY(check_xctype(c, xctype, true));
@@ -700,6 +738,7 @@ int qexxc_nr_rks_fwd_mo(qexxc_ctx* c, int xctype, const double* mo_coeff_dev, co
         return QEXXC_ERR_UNSUPPORTED;
     }
     QX_TRY(need_ao(c, 1));
+    QX_TRY(check_theta(c, n_theta, c->G));
     QX_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long ld = c->GpadMax;
@@ -710,12 +749,14 @@ int qexxc_nr_rks_fwd_mo(qexxc_ctx* c, int xctype, const double* mo_coeff_dev, co
     return nr_rks_after_rho(c, xctype, theta_dev, out_dev, resid_dev, st);
 }
 
-int qexxc_nr_rks_vjp(qexxc_ctx* c, int xctype, int hermi, const double* theta_dev, const double* resid_dev,
-                     const double* e_bar_dev, const double* v_bar_dev, double* bar_dev, void* stream) {
+int qexxc_nr_rks_vjp(qexxc_ctx* c, int xctype, int hermi, const double* theta_dev, long n_theta,
+                     const double* resid_dev, const double* e_bar_dev, const double* v_bar_dev, double* bar_dev,
+                     void* stream) {
     QX_ARG(c != nullptr && theta_dev && resid_dev && e_bar_dev && v_bar_dev && bar_dev, "null pointer");
     QX_TRY(check_xctype(c, xctype, true));
     const int nc = ncomp_of(xctype);
     QX_TRY(need_ao(c, nc));
+    QX_TRY(check_theta(c, n_theta, c->G));
     QX_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long ld = c->GpadMax;

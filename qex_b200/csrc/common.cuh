@@ -84,9 +84,10 @@ struct qexxc_ctx {
     // stage 1
     double* coords = nullptr;   // [B][GpadMax][3]
     double* weights = nullptr;  // [B][GpadMax] (zero beyond G)
-    double* ao = nullptr;       // [B][C][GpadMax][Npad], zero padded
+    double* ao = nullptr;       // [B or 1][C][GpadMax][Npad], zero padded
     int ao_ncomp = 0;           // components currently valid in `ao`
     bool have_grid = false, have_basis = false;
+    bool ao_shared = false;     // QEXXC_FLAG_SHARED_AO: one AO tensor / grid / geometry for the whole batch (nset density matrices)
     qexxc::ShellDev* shells = nullptr;
     int nshell = 0;
     double* env = nullptr;  // [B][nenv]

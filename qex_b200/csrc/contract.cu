@@ -920,7 +920,7 @@ int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const doub
     const int Sc = round_up(nk > 0 ? nk : 1, kNBlock);
     const int BN = pick_bn(Sc);
     dim3 grid(c->Gpad / BM, c->B);
-    const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = ao_cs * c->C, L_bs = (long)c->Npad * ldL;
+    const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = c->ao_shared ? 0 : ao_cs * c->C, L_bs = (long)c->Npad * ldL;
 #define QX_RQM(BNV)                                                                              \
     do {                                                                                         \
         QX_TRY(set_smem(rowquad_kernel<BNV>, RowquadCfg<BNV>::SMEM));                            \
@@ -953,7 +953,7 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double*
     const int BN = pick_bn(c->Nc), NT = (c->Nc + BN - 1) / BN, T = c->Gpad / BM;
     const int ntail = rowquad_tail_tiles(c, tri), nbulk = T - ntail;
     dim3 grid(nbulk + ntail * NT, c->B);
-    const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = ao_cs * c->C, S_bs = (long)c->Npad * c->Npad;
+    const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = c->ao_shared ? 0 : ao_cs * c->C, S_bs = (long)c->Npad * c->Npad;
 #define QX_RQ(BNV)                                                                               \
     do {                                                                                         \
         QX_TRY(set_smem(rowquad_kernel<BNV>, RowquadCfg<BNV>::SMEM));                            \
@@ -980,7 +980,7 @@ int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bs
     const bool sym = (Bsrc == nullptr);
     WsPlan plan;
     QX_TRY(ws_schedule(c, sym, plan, st));
-    const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = ao_cs * c->C;
+    const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = c->ao_shared ? 0 : ao_cs * c->C;
     const double* Bp = sym ? c->ao : Bsrc;
     const long B_bs = sym ? ao_bs : (long)c->GpadMax * c->Npad;
     const WsItem* items = reinterpret_cast<const WsItem*>(c->ws_items[sym ? 1 : 0]);
@@ -1009,7 +1009,7 @@ int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bs
 int launch_build_aow(qexxc_ctx* c, const double* wv, long wv_bstride, long wv_cstride,
                      const double* fac4, cudaStream_t st) {
     const long total2 = (long)c->Gpad * c->Npad / 2;
-    const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = ao_cs * c->C;
+    const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = c->ao_shared ? 0 : ao_cs * c->C;
     long blocks = (total2 + 255) / 256;
     if (blocks > (long)c->num_sms * 16) blocks = (long)c->num_sms * 16;
     dim3 grid((unsigned)blocks, c->B);

@@ -27,7 +27,7 @@ static qexxc_ctx* Ctx(int64_t h) { return reinterpret_cast<qexxc_ctx*>(static_ca
 // numint_legacy.py:122-348 (forward) --------------------------------------------------------------
 static ffi::Error NrRksFwd(cudaStream_t s, int64_t ctx, int32_t xctype, int32_t hermi, F64 dm, F64 theta, R64 out,
                            R64 resid) {
-  return Check(qexxc_nr_rks_fwd(Ctx(ctx), xctype, hermi, dm.typed_data(), theta.typed_data(), out->typed_data(),
+  return Check(qexxc_nr_rks_fwd(Ctx(ctx), xctype, hermi, dm.typed_data(), theta.typed_data(), (long)theta.element_count(), out->typed_data(),
                                 resid->typed_data(), s));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(QexxcNrRksFwd, NrRksFwd,
@@ -44,7 +44,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(QexxcNrRksFwd, NrRksFwd,
 // reverse rule (trainer_legacy_no_jit.py:284) -------------------------------------------------------
 static ffi::Error NrRksVjp(cudaStream_t s, int64_t ctx, int32_t xctype, int32_t hermi, F64 theta, F64 resid, F64 e_bar,
                            F64 v_bar, R64 bar) {
-  return Check(qexxc_nr_rks_vjp(Ctx(ctx), xctype, hermi, theta.typed_data(), resid.typed_data(), e_bar.typed_data(),
+  return Check(qexxc_nr_rks_vjp(Ctx(ctx), xctype, hermi, theta.typed_data(), (long)theta.element_count(), resid.typed_data(), e_bar.typed_data(),
                                 v_bar.typed_data(), bar->typed_data(), s));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(QexxcNrRksVjp, NrRksVjp,
@@ -85,7 +85,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(QexxcEvalRhoVjp, EvalRhoVjp,
 
 // network apply_fn (networks.py:43-75) and its reverse ------------------------------------------------
 static ffi::Error ApplyFwd(cudaStream_t s, int64_t ctx, int64_t npts, F64 x, F64 theta, R64 y) {
-  return Check(qexxc_apply_fn_fwd(Ctx(ctx), x.typed_data(), npts, theta.typed_data(), y->typed_data(), s));
+  return Check(qexxc_apply_fn_fwd(Ctx(ctx), x.typed_data(), npts, theta.typed_data(), (long)theta.element_count(), y->typed_data(), s));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(QexxcApplyFwd, ApplyFwd,
                               ffi::Ffi::Bind()
@@ -97,7 +97,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(QexxcApplyFwd, ApplyFwd,
                                   .Ret<F64>());
 static ffi::Error ApplyVjp(cudaStream_t s, int64_t ctx, int64_t npts, F64 x, F64 theta, F64 y_bar, R64 x_bar,
                            R64 theta_bar) {
-  return Check(qexxc_apply_fn_vjp(Ctx(ctx), x.typed_data(), npts, theta.typed_data(), y_bar.typed_data(),
+  return Check(qexxc_apply_fn_vjp(Ctx(ctx), x.typed_data(), npts, theta.typed_data(), (long)theta.element_count(), y_bar.typed_data(),
                                   x_bar->typed_data(), theta_bar->typed_data(), s));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(QexxcApplyVjp, ApplyVjp,

@@ -152,6 +152,7 @@ int launch_stage4_pointwise(qexxc_ctx* c, int xctype, const double* rho, const d
                             long sums_bstride, cudaStream_t st) {
     const unsigned nb = nblk(c->Gpad, c->num_sms);
     dim3 grid(nb, c->B);
+    ProfScope prof(c, QEXXC_PROF_STAGE4, st);
     stage4_fwd_kernel<<<grid, PW_THREADS, 0, st>>>(xctype, rho, exc, vrho, vgamma, c->weights, wv, c->red,
                                                   c->Gpad, c->GpadMax, c->C);
     QX_LAUNCH_CHECK(c);
@@ -165,6 +166,7 @@ int launch_stage4_pointwise_vjp(qexxc_ctx* c, int xctype, const double* rho, con
                                 const double* wvb, double* rho_bar, double* exc_bar, double* vrho_bar,
                                 double* vgamma_bar, cudaStream_t st) {
     dim3 grid(nblk(c->Gpad, c->num_sms), c->B);
+    ProfScope prof(c, QEXXC_PROF_STAGE4, st);
     stage4_vjp_kernel<<<grid, PW_THREADS, 0, st>>>(xctype, rho, exc, vrho, vgamma, c->weights, e_bar, wvb,
                                                   rho_bar, exc_bar, vrho_bar, vgamma_bar, c->Gpad,
                                                   c->GpadMax, c->C);

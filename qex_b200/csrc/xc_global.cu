@@ -253,6 +253,7 @@ int launch_global_mlp(qexxc_ctx* c, bool vjp, const double* rho, long ld, int G,
         set_error("GlobalMLP: width=%d (1..%d) / n_layers=%d (1..%d) unsupported", net.width, GMAXH, net.n_hidden, GMAXL);
         return QEXXC_ERR_UNSUPPORTED;
     }
+    ProfScope prof(c, vjp ? QEXXC_PROF_XC_VJP : QEXXC_PROF_XC_FWD, st);
     GlobalParams p{};
     p.G = G;
     p.L = net.n_hidden;
@@ -271,14 +272,16 @@ int launch_global_mlp(qexxc_ctx* c, bool vjp, const double* rho, long ld, int G,
     p.vrho_bar = vrho_bar;
     p.rho_bar = rho_bar;
     p.theta_part = c->red;
-    p.n_theta = c->n_theta;
+    // the first Dense has G inputs: the parameter count follows the grid in use (<= the context's capacity)
+    const long nth = qexxc_n_params(&net, G);
+    p.n_theta = nth;
     const size_t sm = global_mlp_smem(p.L, p.H);
     if (vjp) {
         QX_CUDA(cudaFuncSetAttribute(global_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         global_mlp_kernel<true><<<nbatch, GT, sm, st>>>(p);
         QX_LAUNCH_CHECK(c);
-        theta_reduce_kernel2<<<(unsigned)((c->n_theta + 255) / 256), 256, 0, st>>>(c->red, nbatch, c->n_theta,
-                                                                                theta_bar, accumulate_theta);
+        theta_reduce_kernel2<<<(unsigned)((nth + 255) / 256), 256, 0, st>>>(c->red, nbatch, nth, theta_bar,
+                                                                             accumulate_theta);
         QX_LAUNCH_CHECK(c);
     } else {
         QX_CUDA(cudaFuncSetAttribute(global_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

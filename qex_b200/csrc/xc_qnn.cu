@@ -385,6 +385,7 @@ int launch_qnn(qexxc_ctx* c, bool vjp, const unsigned char* tables, const double
         return QEXXC_ERR_UNSUPPORTED;
     }
     if (npts <= 0) return QEXXC_OK;
+    ProfScope prof(c, vjp ? QEXXC_PROF_XC_VJP : QEXXC_PROF_XC_FWD, st);
     QnnParams p{};
     p.nq = c->net.width;
     p.nl = c->net.n_hidden;

@@ -55,7 +55,9 @@ def _xct(xctype) -> int:
 
 class XCContext:
     def __init__(self, nao: int, ngrids_max: int, ncomp: int = 1, nbatch: int = 1, net: NetSpec | None = None,
-                 device: int | None = None):
+                 device: int | None = None, shared_ao: bool = False):
+        """shared_ao: the batch is `nset` density matrices of ONE molecule (numint_legacy.py:141-156): a single
+        AO tensor / grid / geometry serves all batch elements (QEXXC_FLAG_SHARED_AO)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.QexxcError(_lib.ERR_NODEVICE, "no CUDA device: qex_b200 has no CPU fallback")
@@ -65,8 +67,10 @@ class XCContext:
         self.net = net or NetSpec()
         self._desc = self.net.desc()
         self._h = C.c_void_p()
-        check(self.lib.qexxc_create(C.byref(self._h), self.device, self.nbatch, self.ncomp, self.ngrids_max,
-                                    self.nao, C.byref(self._desc)))
+        self.shared_ao = bool(shared_ao)
+        self._nb_geom = 1 if self.shared_ao else self.nbatch
+        check(self.lib.qexxc_create_ex(C.byref(self._h), self.device, self.nbatch, self.ncomp, self.ngrids_max,
+                                       self.nao, C.byref(self._desc), 1 if self.shared_ao else 0))
         self.ngrids = 0
         self.n_params = int(self.lib.qexxc_n_params(C.byref(self._desc), self.ngrids_max))
 
@@ -116,7 +120,7 @@ class XCContext:
 
     # ---- stage 1 ---------------------------------------------------------------------------
     def set_grid(self, coords, weights):
-        B = self.nbatch
+        B = self._nb_geom
         w = self.dev(weights)
         G = w.numel() // B
         w = w.reshape(B, G)
@@ -131,9 +135,9 @@ class XCContext:
         atm = np.ascontiguousarray(atm, dtype=np.int32).reshape(-1, 6)
         bas = np.ascontiguousarray(bas, dtype=np.int32).reshape(-1, 8)
         env = np.ascontiguousarray(env, dtype=np.float64)
-        env = np.broadcast_to(env, (self.nbatch, env.shape[-1])) if env.ndim == 1 else env
+        env = np.broadcast_to(env, (self._nb_geom, env.shape[-1])) if env.ndim == 1 else env
         env = np.ascontiguousarray(env)
-        if env.shape[0] != self.nbatch:
+        if env.shape[0] != self._nb_geom:
             raise ValueError("env must be [nenv] or [nbatch, nenv]")
         check(self.lib.qexxc_set_basis(self._h, atm.ctypes.data_as(C.c_void_p), atm.shape[0],
                                        bas.ctypes.data_as(C.c_void_p), bas.shape[0],
@@ -146,7 +150,7 @@ class XCContext:
         return self
 
     def set_ao(self, ao, ncomp: int | None = None):
-        B, G, N = self.nbatch, self.ngrids, self.nao
+        B, G, N = self._nb_geom, self.ngrids, self.nao
         a = self.dev(ao)
         if ncomp is None:
             ncomp = a.numel() // (B * G * N)
@@ -156,7 +160,7 @@ class XCContext:
         return self
 
     def get_ao(self, ncomp: int = 1) -> torch.Tensor:
-        out = self.empty(self.nbatch, ncomp, self.ngrids, self.nao)
+        out = self.empty(self._nb_geom, ncomp, self.ngrids, self.nao)
         with torch.cuda.device(self.device):
             check(self.lib.qexxc_get_ao(self._h, self._p(out), ncomp, _stream()))
         return out
@@ -187,7 +191,7 @@ class XCContext:
         vrho = self.empty(B, G)
         vgamma = self.empty(B, G) if xt == XC_GGA else None
         with torch.cuda.device(self.device):
-            check(self.lib.qexxc_xc_fwd(self._h, xt, self._p(r), self._p(th), self._p(exc), self._p(vrho),
+            check(self.lib.qexxc_xc_fwd(self._h, xt, self._p(r), self._p(th), th.numel(), self._p(exc), self._p(vrho),
                                         self._p(vgamma), _stream()))
         return exc, vrho, vgamma
 
@@ -203,7 +207,7 @@ class XCContext:
         rbar = self.empty(B, nc, G)
         tbar = self.empty(th.numel())
         with torch.cuda.device(self.device):
-            check(self.lib.qexxc_xc_vjp(self._h, xt, self._p(r), self._p(th), self._p(eb), self._p(vb), self._p(gb),
+            check(self.lib.qexxc_xc_vjp(self._h, xt, self._p(r), self._p(th), th.numel(), self._p(eb), self._p(vb), self._p(gb),
                                         self._p(rbar), self._p(tbar), _stream()))
         return rbar, tbar
 
@@ -217,7 +221,7 @@ class XCContext:
             npts = xx.numel() // F
             y = self.empty(npts)
         with torch.cuda.device(self.device):
-            check(self.lib.qexxc_apply_fn_fwd(self._h, self._p(xx), npts, self._p(th), self._p(y), _stream()))
+            check(self.lib.qexxc_apply_fn_fwd(self._h, self._p(xx), npts, self._p(th), th.numel(), self._p(y), _stream()))
         return y
 
     def apply_fn_vjp(self, x, theta, y_bar):
@@ -232,7 +236,7 @@ class XCContext:
         xb = torch.empty_like(xx)
         tb = self.empty(th.numel())
         with torch.cuda.device(self.device):
-            check(self.lib.qexxc_apply_fn_vjp(self._h, self._p(xx), npts, self._p(th), self._p(yb), self._p(xb),
+            check(self.lib.qexxc_apply_fn_vjp(self._h, self._p(xx), npts, self._p(th), th.numel(), self._p(yb), self._p(xb),
                                               self._p(tb), _stream()))
         return xb, tb
 
@@ -283,7 +287,7 @@ class XCContext:
         if want_resid and resid is None:
             resid = self.empty(self.resid_doubles)
         with torch.cuda.device(self.device):
-            check(self.lib.qexxc_nr_rks_fwd(self._h, xt, int(hermi), self._p(d), self._p(th), self._p(out),
+            check(self.lib.qexxc_nr_rks_fwd(self._h, xt, int(hermi), self._p(d), self._p(th), th.numel(), self._p(out),
                                             self._p(resid if want_resid else None), _stream()))
         return out, (resid if want_resid else None)
 
@@ -312,7 +316,7 @@ class XCContext:
         if want_resid and resid is None:
             resid = self.empty(self.resid_doubles)
         with torch.cuda.device(self.device):
-            check(self.lib.qexxc_nr_rks_fwd_mo(self._h, xt, self._p(C_), self._p(occ), nmo, self._p(th), self._p(out),
+            check(self.lib.qexxc_nr_rks_fwd_mo(self._h, xt, self._p(C_), self._p(occ), nmo, self._p(th), th.numel(), self._p(out),
                                                self._p(resid if want_resid else None), _stream()))
         return out, (resid if want_resid else None)
 
@@ -326,7 +330,7 @@ class XCContext:
         if out is None:
             out = self.empty(B * N * N + th.numel())
         with torch.cuda.device(self.device):
-            check(self.lib.qexxc_nr_rks_vjp(self._h, xt, int(hermi), self._p(th), self._p(resid), self._p(eb),
+            check(self.lib.qexxc_nr_rks_vjp(self._h, xt, int(hermi), self._p(th), th.numel(), self._p(resid), self._p(eb),
                                             self._p(vb), self._p(out), _stream()))
         return out
 
@@ -340,7 +344,7 @@ class XCContext:
         check(self.lib.qexxc_contraction_flops(self._h, int(which), 1 if symmetric else 0, C.byref(v)))
         return v.value
 
-    PROF_CLASSES = {"rowquad": 0, "wsyrk": 1, "xc_fwd": 2, "xc_vjp": 3, "eval_ao": 4}
+    PROF_CLASSES = {"rowquad": 0, "wsyrk": 1, "xc_fwd": 2, "xc_vjp": 3, "eval_ao": 4, "stage4": 5}
 
     def profile_enable(self, on: bool = True):
         check(self.lib.qexxc_profile_enable(self._h, 1 if on else 0))

@@ -18,6 +18,7 @@ raise ``NotImplementedError`` above it); AO values are evaluated on the device, 
 """
 from __future__ import annotations
 
+import hashlib
 from functools import partial
 
 import numpy as np
@@ -78,22 +79,36 @@ class NumInt:
             return _native_apply(fn.keywords["network"]), bool(fn.keywords.get("is_global_xc", True))
         return None, None
 
-    def _ctx(self, nao, ngrids, ncomp, spec: NetSpec | None):
-        key = (nao, ncomp, None if spec is None else tuple(sorted(vars(spec).items())))
+    def _ctx(self, nao, ngrids, ncomp, spec: NetSpec | None, nset: int = 1):
+        """One cached context per (nao, ncomp, network, nset).  nset > 1 = several density matrices of one
+        molecule: a batched context whose elements share the AO tensor (engine.XCContext(shared_ao=True))."""
+        key = (nao, ncomp, None if spec is None else tuple(sorted(vars(spec).items())), nset)
         ctx = self._ctxs.get(key)
         if ctx is None or ctx.ngrids_max < ngrids:
             if ctx is not None:
+                self._ao_key.pop(id(ctx), None)
                 ctx.close()
-            ctx = XCContext(nao=nao, ngrids_max=ngrids, ncomp=ncomp, net=spec, device=self.device)
+            ctx = XCContext(nao=nao, ngrids_max=ngrids, ncomp=ncomp, nbatch=nset, net=spec, device=self.device,
+                            shared_ao=nset > 1)
             self._ctxs[key] = ctx
             self._ao_key.pop(id(ctx), None)
         return ctx
 
+    @staticmethod
+    def _fingerprint(mol, coords, weights, deriv):
+        """Content hash of everything stage 1 depends on (geometry + basis tables, grid, derivative order)."""
+        h = hashlib.blake2b(digest_size=16)
+        for a in (mol._atm, mol._bas, mol._env, coords, weights):
+            a = np.ascontiguousarray(a)
+            h.update(str((a.dtype.str, a.shape)).encode())
+            h.update(a.tobytes())
+        return h.hexdigest(), int(deriv)
+
     def _load(self, ctx, mol, grids, deriv):
         """Stage 1 on the device: grid upload + AO evaluation (re-done per call like the reference's
-        block_loop, unless cache_ao and the same mol/grid fingerprint)."""
+        block_loop, unless cache_ao and the same content fingerprint of mol tables + grid)."""
         coords, weights = np.asarray(grids.coords), np.asarray(grids.weights)
-        fp = (hash(np.asarray(mol._env).tobytes()), coords.shape, float(coords.sum()), float(weights.sum()), deriv)
+        fp = self._fingerprint(mol, coords, weights, deriv) if self.cache_ao else None
         if self.cache_ao and self._ao_key.get(id(ctx)) == fp:
             return
         ctx.set_grid(coords, weights)
@@ -165,90 +180,95 @@ class NumInt:
     # ---- B1 -------------------------------------------------------------------------------
     def nr_rks(self, mol, grids, xc_code, dms, relativity=0, hermi=0, max_memory=2000, verbose=None, params=None,
                return_resid=False):
+        """numint_legacy.py:122-348.  `dms` [N,N] or [nset,N,N]; the results are unwrapped when nset == 1
+        (:344-348).  The nset density matrices of one call go through ONE batched launch per stage (they share
+        the AO tensor), not a host loop.  With `return_resid`, a fourth value is appended: the residual buffer of
+        the whole call (all nset density matrices), to be handed to `nr_rks_vjp`."""
         xctype = _xctype(self, xc_code)
         dms_in = dms
         dms = _np(dms)
-        single = dms.ndim == 2
-        dm_list = [dms] if single else list(dms)
+        dm_arr = dms[None] if dms.ndim == 2 else dms
+        nset = dm_arr.shape[0]
         fn, is_global = self._native()
         gga = xctype == "GGA"
         ncomp = 4 if gga else 1
         N, G = mol.nao_nr(), int(np.asarray(grids.weights).shape[0])
-        nelec, excsum, vmat, resids = [], [], [], []
+        kind = "NN" if xctype == "LDA" else xctype
         # numint_legacy.py:527-545: a dm tagged with mo_coeff / mo_occ takes the MO form of rho (eval_rho2)
         mo_coeff, mo_occ = getattr(dms_in, "mo_coeff", None), getattr(dms_in, "mo_occ", None)
-        use_mo = mo_coeff is not None and mo_occ is not None and single and not gga
+        use_mo = mo_coeff is not None and mo_occ is not None and nset == 1 and not gga
         if use_mo:
             mo_coeff, mo_occ = _np(mo_coeff), _np(mo_occ)
             keep = np.abs(mo_occ) > 1e-12  # OCCDROP: only occupied orbitals enter (pos/neg handled by sign)
             mo_coeff, mo_occ = np.ascontiguousarray(mo_coeff[:, keep]), np.ascontiguousarray(mo_occ[keep])
             use_mo = mo_occ.size > 0
-        if fn is not None:
-            if xctype == "NN-AmplitudeEncoding" and not is_global:
-                raise ValueError("xctype 'NN-AmplitudeEncoding' needs eval_xc built with is_global_xc=True")
-            ctx = self._ctx(N, G, ncomp, fn.qex_spec)
+        if fn is not None and xctype == "NN-AmplitudeEncoding" and not is_global:
+            raise ValueError("xctype 'NN-AmplitudeEncoding' needs eval_xc built with is_global_xc=True")
+        # a local network under is_global_xc=True (the reference's default flag) is the sum of its per-point
+        # outputs (trainer_legacy_no_jit.py:46-53): no fused kernel for that pairing, so it runs as
+        # eval_rho -> eval_xc -> vxc_assemble on the device buffers below
+        fused = fn is not None and not (is_global and fn.qex_spec.kind != _lib.NET_GLOBAL_MLP)
+        resid = None
+        if fused:
+            ctx = self._ctx(N, G, ncomp, fn.qex_spec, nset)
             self._load(ctx, mol, grids, 1 if gga else 0)
             theta = _theta(fn, params)
-            for dm in dm_list:
-                if use_mo:
-                    out, resid = ctx.nr_rks_fwd_mo(mo_coeff, mo_occ, theta, "NN" if xctype == "LDA" else xctype,
-                                                   want_resid=return_resid)
-                else:
-                    out, resid = ctx.nr_rks_fwd(dm, theta, "NN" if xctype == "LDA" else xctype, hermi,
-                                                want_resid=return_resid)
-                o = out[0].cpu().numpy()
-                vmat.append(o[: N * N].reshape(N, N).copy())
-                excsum.append(float(o[N * N]))
-                nelec.append(float(o[N * N + 1]))
-                resids.append(resid)
+            if use_mo:
+                out, resid = ctx.nr_rks_fwd_mo(mo_coeff, mo_occ, theta, kind, want_resid=return_resid)
+            else:
+                out, resid = ctx.nr_rks_fwd(dm_arr, theta, kind, hermi, want_resid=return_resid)
         else:
             builtin_lda = not callable(self.eval_xc) and xctype == "LDA"
             if not callable(self.eval_xc) and not builtin_lda:
                 raise ValueError("NumInt.eval_xc is not set: install a functional first (define_xc_)")
-            ctx = self._ctx(N, G, ncomp, None)
+            ctx = self._ctx(N, G, ncomp, None, nset)
             self._load(ctx, mol, grids, 1 if gga else 0)
-            for dm in dm_list:
-                rho = ctx.eval_rho_mo(mo_coeff, mo_occ) if use_mo else ctx.eval_rho(dm, ncomp, hermi)
-                if builtin_lda:
-                    # the reference's libxc route for xc_code "lda" (Slater exchange), all on the device
-                    exc_d, vrho_d = lda_exchange(rho[:, 0, :])
-                    o = ctx.vxc_assemble(rho, exc_d, vrho_d, None, "NN")[0].cpu().numpy()
-                    vmat.append(o[: N * N].reshape(N, N).copy())
-                    excsum.append(float(o[N * N]))
-                    nelec.append(float(o[N * N + 1]))
-                    resids.append(None)
-                    continue
-                r = rho[0].cpu().numpy()
-                exc, vxc = self.eval_xc(xc_code, r[0] if ncomp == 1 else r, spin=0, relativity=relativity, deriv=1,
-                                        verbose=verbose, params=params)[:2]
-                kind = "NN-AmplitudeEncoding" if xctype == "NN-AmplitudeEncoding" else ("GGA" if gga else "NN")
-                out = ctx.vxc_assemble(rho, np.atleast_1d(_np(exc)), _np(vxc[0]), _np(vxc[1]) if gga else None, kind)
-                o = out[0].cpu().numpy()
-                vmat.append(o[: N * N].reshape(N, N).copy())
-                excsum.append(float(o[N * N]))
-                nelec.append(float(o[N * N + 1]))
-                resids.append(None)
-        if single:  # numint_legacy.py:344-348
+            rho = ctx.eval_rho_mo(mo_coeff, mo_occ) if use_mo else ctx.eval_rho(dm_arr, ncomp, hermi)
+            if builtin_lda:
+                # the reference's libxc route for xc_code "lda" (Slater exchange), all on the device
+                exc_d, vrho_d = lda_exchange(rho[:, 0, :])
+                out = ctx.vxc_assemble(rho, exc_d, vrho_d, None, "NN")
+            else:
+                r = rho.cpu().numpy()
+                excs, vrhos, vgams = [], [], []
+                for i in range(nset):  # host callback per density matrix, as the reference's `for idm in range(nset)`
+                    exc, vxc = self.eval_xc(xc_code, r[i, 0] if ncomp == 1 else r[i], spin=0, relativity=relativity,
+                                            deriv=1, verbose=verbose, params=params)[:2]
+                    excs.append(np.atleast_1d(_np(exc)))
+                    vrhos.append(_np(vxc[0]))
+                    if gga:
+                        vgams.append(_np(vxc[1]))
+                akind = "NN-AmplitudeEncoding" if xctype == "NN-AmplitudeEncoding" else ("GGA" if gga else "NN")
+                out = ctx.vxc_assemble(rho, np.stack(excs), np.stack(vrhos), np.stack(vgams) if gga else None, akind)
+        o = out.cpu().numpy()  # the one host synchronisation of the call
+        vmat = [o[i, : N * N].reshape(N, N).copy() for i in range(nset)]
+        excsum = [float(o[i, N * N]) for i in range(nset)]
+        nelec = [float(o[i, N * N + 1]) for i in range(nset)]
+        if nset == 1:  # numint_legacy.py:344-348
             res = (nelec[0], excsum[0], vmat[0])
-            return res + (resids[0],) if return_resid else res
-        res = (nelec, excsum, vmat)
-        return res + (resids,) if return_resid else res
+        else:
+            res = (nelec, excsum, vmat)
+        return res + (resid,) if return_resid else res
 
     def nr_rks_vjp(self, mol, grids, xc_code, resid, e_bar, v_bar, hermi=0, params=None):
         """Reverse rule of ``nr_rks`` (native functional only): cotangents of (excsum, vmat) ->
-        (dm_bar [N,N], theta_bar flat).  ``resid`` comes from ``nr_rks(..., return_resid=True)``."""
+        (dm_bar [N,N], theta_bar flat); for nset > 1: e_bar [nset], v_bar [nset,N,N] -> dm_bar [nset,N,N] and
+        theta_bar summed over the set.  ``resid`` comes from ``nr_rks(..., return_resid=True)``."""
         fn, _ = self._native()
         if fn is None:
             raise NotImplementedError("nr_rks_vjp needs a native functional (xc.make_eval_xc)")
         xctype = _xctype(self, xc_code)
         gga = xctype == "GGA"
         N, G = mol.nao_nr(), int(np.asarray(grids.weights).shape[0])
-        ctx = self._ctx(N, G, 4 if gga else 1, fn.qex_spec)
+        v_bar = _np(v_bar)
+        nset = 1 if v_bar.ndim == 2 else v_bar.shape[0]
+        ctx = self._ctx(N, G, 4 if gga else 1, fn.qex_spec, nset)
         self._load(ctx, mol, grids, 1 if gga else 0)
         theta = _theta(fn, params)
-        bar = ctx.nr_rks_vjp(theta, resid, np.atleast_1d(np.asarray(e_bar, dtype=np.float64)), _np(v_bar),
+        bar = ctx.nr_rks_vjp(theta, resid, np.atleast_1d(np.asarray(e_bar, dtype=np.float64)), v_bar,
                              "NN" if xctype == "LDA" else xctype, hermi).cpu().numpy()
-        return bar[: N * N].reshape(N, N), bar[N * N :]
+        dm_bar = bar[: nset * N * N].reshape(nset, N, N)
+        return (dm_bar[0] if nset == 1 else dm_bar), bar[nset * N * N :]
 
 
 _default = None

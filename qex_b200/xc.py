@@ -61,7 +61,10 @@ def exc_and_vrho_global(network, params, rho):
     """trainer_legacy_no_jit.py:46-53: exc is the scalar sum of the network output."""
     fn = _native_apply(network)
     if fn.qex_spec.kind != _lib.NET_GLOBAL_MLP:
-        raise NotImplementedError("is_global_xc=True needs a global network (GlobalMLP)")
+        # a per-point network under the global flag (the reference's default `is_global_xc=True`):
+        # exc = jnp.sum(network.apply(params, rho)), vrho = its per-point derivative
+        exc, vrho = exc_and_vrho_local(network, params, rho)
+        return exc.sum(), vrho
     G = int(np.prod(rho.shape))
     ctx = _ctx_for(fn, G)
     ctx.set_grid(None, np.ones(G)) if ctx.ngrids != G else None

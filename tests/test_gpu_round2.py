@@ -1,0 +1,437 @@
+"""GPU tests added in round 2: argument validation the reference does by shape checks, context reuse,
+`nset > 1` in one launch, the BASELINE configs at their FULL stated sizes, and the N-rank vs 1-rank parity of
+the grid-sharded path on hardware (skipped below 2 GPUs)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gto_ref, mlp_ref, numint_ref, step_ref
+from tests._util import elem_err, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL64 = 1e-10
+TOL_ELEM = 1e-10  # element-wise, denominators floored at 1e-6 max|ref| (tests/_util.py)
+
+
+def _h2():
+    from qex_b200 import gen_grid, gto
+
+    mol = gto.h2(0.74, "6-31g")
+    grids = gen_grid.Grids(mol, n_rad=31, n_theta=5, n_phi=4).build()
+    rng = np.random.default_rng(0)
+    c = rng.standard_normal((mol.nao_nr(), 1)) * 0.4
+    return mol, grids, 2.0 * c @ c.T
+
+
+# ---- theta length, set_basis reuse -------------------------------------------------------------------
+def test_theta_length_is_checked_like_a_shape_error():
+    """A parameter vector that does not fit the context's network must raise (the reference raises a shape error);
+    a bare device pointer used to be read out of bounds silently."""
+    from qex_b200 import workloads
+    from qex_b200.engine import XCContext
+
+    wl = workloads.make("c5", ngrids=512)
+    ctx = XCContext(nao=wl.nao, ngrids_max=512, net=workloads.net_spec(wl))
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env).set_grid(wl.coords, wl.weights).eval_ao(0)
+    bad = np.concatenate([wl.theta, [0.0]])
+    with pytest.raises(ValueError):
+        ctx.nr_rks_fwd(wl.dm, bad, "NN")
+    with pytest.raises(ValueError):
+        ctx.nr_rks_fwd(wl.dm, wl.theta[:-3], "NN")
+    with pytest.raises(ValueError):
+        ctx.apply_fn(np.ones(64), bad)
+    rho = np.abs(np.random.default_rng(0).standard_normal((1, 1, 512)))
+    with pytest.raises(ValueError):
+        ctx.xc_fwd(rho, bad, "NN")
+    out, resid = ctx.nr_rks_fwd(wl.dm, wl.theta, "NN")
+    with pytest.raises(ValueError):
+        ctx.nr_rks_vjp(bad, resid, [1.0], wl.v_bar, "NN")
+    # a global network's parameter count follows the grid in use, not the context capacity
+    from qex_b200 import _lib
+    from qex_b200.engine import NetSpec
+
+    G = 300
+    g = XCContext(nao=4, ngrids_max=400, net=NetSpec(kind=_lib.NET_GLOBAL_MLP, n_hidden=2, width=16))
+    g.set_grid(None, np.ones(G))
+    spec = mlp_ref.MLPSpec([G, 16, 16, 1], "tanh")
+    th = mlp_ref.pack(*mlp_ref.init_params(spec, 0))
+    x = np.abs(np.random.default_rng(1).standard_normal(G))
+    e, v, _ = g.xc_fwd(x.reshape(1, 1, G), th, "NN-AmplitudeEncoding")
+    e_ref, v_ref = mlp_ref.exc_and_vrho_global(spec, th, x)
+    assert abs(float(e[0]) - e_ref) <= 1e-12 * max(1.0, abs(e_ref)) and rel_err(v[0].cpu().numpy(), v_ref) <= TOL64
+    rb, tb = g.xc_vjp(x.reshape(1, 1, G), th, [0.7], np.ones((1, G)), xctype="NN-AmplitudeEncoding")
+    assert tb.numel() == th.size  # theta_bar has the length of theta for THIS grid
+    with pytest.raises(ValueError):  # parameters of a 400-point network on a 300-point grid
+        g.xc_fwd(x.reshape(1, 1, G), mlp_ref.pack(*mlp_ref.init_params(mlp_ref.MLPSpec([400, 16, 16, 1], "tanh"), 0)),
+                 "NN-AmplitudeEncoding")
+
+
+def test_set_basis_twice_with_more_shells_at_equal_nao():
+    """A reused context whose new basis has the same nao but more shells (NumInt caches contexts by nao):
+    the shell tables must be reallocated, and replaced buffers must be freed."""
+    from qex_b200 import gto
+    from qex_b200.engine import XCContext
+
+    rng = np.random.default_rng(0)
+    coords = rng.standard_normal((700, 3)) * 1.5
+    # 9 AOs as (1 atom: s s s p p) = 5 shells ... and as 9 s shells on 3 atoms
+    molA = gto.synthetic_molecule(1, (3, 2, 0), seed=1)
+    molB = gto.synthetic_molecule(3, (3, 0, 0), seed=2)
+    assert molA.nao_nr() == molB.nao_nr() == 9 and len(molB._bas) > len(molA._bas)
+    ctx = XCContext(nao=9, ngrids_max=700)
+    ctx.set_grid(coords, np.ones(700))
+    sizes = []
+    for mol in (molA, molB, molA, molB):
+        ctx.set_basis(mol._atm, mol._bas, mol._env).eval_ao(0)
+        ao = ctx.get_ao(1)[0, 0].cpu().numpy()
+        ref = gto_ref.eval_ao(mol._atm, mol._bas, mol._env, coords, 0)
+        assert np.abs(ao - ref).max() <= 1e-13
+        sizes.append(ctx.workspace_bytes)
+    assert sizes[0] == sizes[2] and sizes[1] == sizes[3]  # no growth: replaced tables are released
+
+
+# ---- nset > 1 in one launch --------------------------------------------------------------------------------------
+def test_nset_density_matrices_share_one_batched_launch():
+    """numint_legacy.py:141-156 loops `for idm in range(nset)`; here the set is one batched launch per stage on a
+    shared AO tensor.  Results must equal the single-dm calls, lists are returned for nset > 1 and unwrapped for
+    a stacked [1,N,N] input (:344-348)."""
+    from qex_b200 import xc
+    from qex_b200.networks import LocalMLP
+    from qex_b200.numint import NumInt
+
+    mol, grids, dm = _h2()
+    N = mol.nao_nr()
+    net = LocalMLP().build_network(grids.coords)
+    params = net[0](0, None)[1]
+    ni = NumInt()
+    ni.eval_xc = xc.make_eval_xc(net, is_global_xc=False)
+    rng = np.random.default_rng(5)
+    dms = np.stack([dm, 0.5 * dm + 0.01 * rng.standard_normal((N, N)), 1.5 * dm])
+    singles = [ni.nr_rks(mol, grids, "NN", d, params=params) for d in dms]
+    n0 = ni._ctxs[next(iter(ni._ctxs))].launch_count
+    nl, el, vl, resid = ni.nr_rks(mol, grids, "NN", dms, params=params, return_resid=True)
+    assert isinstance(nl, list) and len(nl) == len(el) == len(vl) == 3
+    for i, (n1, e1, v1) in enumerate(singles):
+        assert abs(nl[i] - n1) <= 1e-12 and abs(el[i] - e1) <= 1e-12 and rel_err(vl[i], v1) <= 1e-13
+    # batched reverse: per-dm cotangents, theta_bar summed over the set
+    e_bar, v_bar = rng.standard_normal(3), rng.standard_normal((3, N, N))
+    D, tb = ni.nr_rks_vjp(mol, grids, "NN", resid, e_bar, v_bar, params=params)
+    assert D.shape == (3, N, N)
+    tsum = 0
+    for i in range(3):
+        _, _, _, r1 = ni.nr_rks(mol, grids, "NN", dms[i], params=params, return_resid=True)
+        d1, t1 = ni.nr_rks_vjp(mol, grids, "NN", r1, e_bar[i], v_bar[i], params=params)
+        assert rel_err(D[i], d1) <= 1e-12
+        tsum = tsum + t1
+    assert rel_err(tb, tsum) <= 1e-12
+    # the batched context really is a shared-AO one (one AO tensor for 3 density matrices)
+    b3 = [c for k, c in ni._ctxs.items() if k[3] == 3][0]
+    assert b3.shared_ao and b3.get_ao(1).shape[0] == 1
+    # stacked [1,N,N] unwraps like the reference (nset == 1)
+    n1, e1, v1 = ni.nr_rks(mol, grids, "NN", dm[None], params=params)
+    assert isinstance(n1, float) and v1.shape == (N, N) and abs(e1 - singles[0][1]) <= 1e-12
+    # host-callback route with nset > 1
+    ni2 = NumInt()
+    ni2.eval_xc = lambda code, rho, *a, **k: (0.01 * rho**2, (0.02 * rho, None, None, None), None, None)
+    ao = gto_ref.eval_ao(mol._atm, mol._bas, mol._env, grids.coords, 0)
+    nl, el, vl = ni2.nr_rks(mol, grids, "NN", dms)
+    for i in range(3):
+        n_r, e_r, v_r = numint_ref.nr_rks(ao, grids.weights, dms[i], ni2.eval_xc, "NN")
+        assert abs(el[i] - e_r) <= 1e-9 and rel_err(vl[i], v_r) <= TOL64
+
+
+def test_global_flag_with_a_local_network_sums_the_outputs():
+    """`is_global_xc=True` is the reference's default; with a per-point network exc_and_vrho_global is
+    jnp.sum(network.apply(params, rho)) (trainer_legacy_no_jit.py:46-53)."""
+    from qex_b200 import xc
+    from qex_b200.networks import LocalMLP
+    from qex_b200.numint import NumInt
+
+    mol, grids, dm = _h2()
+    net = LocalMLP().build_network(grids.coords)
+    params = net[0](0, None)[1]
+    spec = mlp_ref.MLPSpec([1, 64, 64, 64, 1], "tanh")
+    theta = mlp_ref.pack(*mlp_ref.from_stax(params))
+    ao = gto_ref.eval_ao(mol._atm, mol._bas, mol._env, grids.coords, 0)
+    rho = numint_ref.eval_rho(ao, dm, "LDA")
+    e, (v, *_), _, _ = xc.eval_xc("NN-AmplitudeEncoding", rho, params=params, network=net, is_global_xc=True)
+    e_ref, v_ref = mlp_ref.exc_and_vrho_local(spec, theta, rho)
+    assert np.ndim(e) == 0 and abs(float(e) - e_ref.sum()) <= 1e-10 and rel_err(v, v_ref) <= TOL64
+    ni = NumInt()
+    ni.eval_xc = xc.make_eval_xc(net, is_global_xc=True)
+    nelec, exc, vmat = ni.nr_rks(mol, grids, "NN-AmplitudeEncoding", dm, params=params)
+
+    def ref_xc(code, r, **k):
+        ee, vv = mlp_ref.exc_and_vrho_local(spec, theta, r)
+        return ee.sum(), (vv, None, None, None), None, None
+
+    n_r, e_r, v_r = numint_ref.nr_rks(ao, grids.weights, dm, ref_xc, "NN-AmplitudeEncoding")
+    assert abs(exc - e_r) <= 1e-9 and rel_err(vmat, v_r) <= TOL64
+
+
+def test_cache_ao_is_keyed_on_content():
+    """Two grids with identical sums but different points must not share a cached AO tensor."""
+    from qex_b200 import gen_grid, xc
+    from qex_b200.networks import LocalMLP
+    from qex_b200.numint import NumInt
+
+    mol, grids, dm = _h2()
+    net = LocalMLP().build_network(grids.coords)
+    params = net[0](0, None)[1]
+    ni = NumInt(cache_ao=True)
+    ni.eval_xc = xc.make_eval_xc(net, is_global_xc=False)
+    a = ni.nr_rks(mol, grids, "NN", dm, params=params)
+    c2 = grids.coords.copy()
+    c2[[0, 1]] = c2[[1, 0]] + np.array([[0.25, 0, 0], [-0.25, 0, 0]])  # same coordinate sum, different points
+    assert abs(c2.sum() - grids.coords.sum()) < 1e-9
+    g2 = gen_grid.Grids(mol, coords=c2, weights=grids.weights)
+    b = ni.nr_rks(mol, g2, "NN", dm, params=params)
+    fresh = NumInt()
+    fresh.eval_xc = ni.eval_xc
+    b_ref = fresh.nr_rks(mol, g2, "NN", dm, params=params)
+    assert abs(b[1] - b_ref[1]) <= 1e-13 and abs(a[1] - b[1]) > 1e-9
+    # and an unchanged (mol, grid) does hit the cache: no new AO launch
+    ctx = next(iter(ni._ctxs.values()))
+    ctx.profile_enable(True)
+    ni.nr_rks(mol, g2, "NN", dm, params=params)
+    assert ctx.profile_read()["eval_ao"][1] == 0
+    ctx.profile_enable(False)
+
+
+# ---- the BASELINE configs at their full stated sizes -------------------------------------------------------------
+def _run_full(wl, precision="f64"):
+    import torch
+
+    from qex_b200 import workloads
+    from qex_b200.engine import XCContext
+
+    N, G = wl.nao, wl.ngrids
+    ctx = XCContext(nao=N, ngrids_max=G, ncomp=wl.ncomp, net=workloads.net_spec(wl, precision))
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env).set_grid(wl.coords, wl.weights).eval_ao(1 if wl.ncomp == 4 else 0)
+    out, resid = ctx.nr_rks_fwd(wl.dm, wl.theta, wl.xctype)
+    bar = ctx.nr_rks_vjp(wl.theta, resid, [wl.e_bar], wl.v_bar, wl.xctype)
+    torch.cuda.synchronize()
+    return ctx, out, bar, resid
+
+
+def _check_vs_oracle(out, bar, ref, N):
+    o, b = out.cpu().numpy()[0], bar.cpu().numpy()
+    V, D, tb = o[: N * N].reshape(N, N), b[: N * N].reshape(N, N), b[N * N :]
+    assert abs(o[N * N] - ref["excsum"]) <= 1e-9 and abs(o[N * N + 1] - ref["nelec"]) <= 1e-9 * max(1.0, abs(ref["nelec"]))
+    assert rel_err(V, ref["vmat"]) <= TOL64 and rel_err(D, ref["dm_bar"]) <= TOL64 and rel_err(tb, ref["theta_bar"]) <= TOL64
+    assert elem_err(V, ref["vmat"]) <= TOL_ELEM and elem_err(D, ref["dm_bar"]) <= TOL_ELEM
+    assert elem_err(tb, ref["theta_bar"]) <= TOL_ELEM
+
+
+def test_full_size_c3_against_the_oracle():
+    """BASELINE configs[2] at its stated size: 120 AOs x 50 000 points, C = 4 (GGA features), the WHOLE grid against
+    the NumPy oracle (the oracle needs a few seconds at this size), max-norm and element-wise."""
+    from qex_b200 import workloads
+
+    wl = workloads.make("c3")
+    assert wl.nao == 120 and wl.ngrids == 50_000 and wl.ncomp == 4
+    ctx, out, bar, _ = _run_full(wl)
+    m = wl.mol
+    ref = step_ref.xc_step(m._atm, m._bas, m._env, wl.coords, wl.weights, wl.dm, wl.net, wl.theta, "GGA", wl.e_bar, wl.v_bar)
+    _check_vs_oracle(out, bar, ref, wl.nao)
+    ctx.close()
+
+
+def test_full_size_c4_64_molecules_against_the_oracle():
+    """BASELINE configs[3]'s XC step at its stated batch: 64 bond lengths in one launch per stage, every molecule
+    against the oracle."""
+    import torch
+
+    from qex_b200 import workloads
+    from qex_b200.engine import XCContext
+
+    wl = workloads.make("c4")
+    B, N, G = wl.extra["batch"], wl.nao, wl.ngrids
+    assert B == 64
+    ctx = XCContext(nao=N, ngrids_max=G, nbatch=B, net=workloads.net_spec(wl))
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.extra["envs"]).set_grid(wl.coords, wl.weights).eval_ao(0)
+    out, resid = ctx.nr_rks_fwd(wl.dm, wl.theta, "NN")
+    rng = np.random.default_rng(11)
+    e_bar, v_bar = rng.standard_normal(B), rng.standard_normal((B, N, N))
+    bar = ctx.nr_rks_vjp(wl.theta, resid, e_bar, v_bar, "NN")
+    torch.cuda.synchronize()
+    out, bar = out.cpu().numpy(), bar.cpu().numpy()
+    tsum = 0
+    for b in range(B):
+        m = wl.extra["mols"][b]
+        ref = step_ref.xc_step(m._atm, m._bas, m._env, wl.coords[b], wl.weights[b], wl.dm[b], wl.net, wl.theta, "NN",
+                               e_bar[b], v_bar[b])
+        V, D = out[b, : N * N].reshape(N, N), bar[b * N * N : (b + 1) * N * N].reshape(N, N)
+        assert rel_err(V, ref["vmat"]) <= TOL64 and rel_err(D, ref["dm_bar"]) <= TOL64
+        assert elem_err(V, ref["vmat"]) <= TOL_ELEM and elem_err(D, ref["dm_bar"]) <= TOL_ELEM
+        assert abs(out[b, N * N] - ref["excsum"]) <= 1e-9 and abs(out[b, N * N + 1] - ref["nelec"]) <= 1e-9
+        tsum = tsum + ref["theta_bar"]
+    assert rel_err(bar[B * N * N :], tsum) <= TOL64 and elem_err(bar[B * N * N :], tsum) <= TOL_ELEM
+    ctx.close()
+
+
+def test_full_size_c5gga_properties():
+    """c5 with GGA features at full size (1000 AOs x 1e6 points x 4 components = 33.6 GB of AO values):
+    determinism, the four-component rho and the V_xc contraction against library GEMMs on the same AO tensor,
+    additivity over grid shards, and a leading shard against the oracle."""
+    import torch
+
+    from qex_b200 import workloads
+    from qex_b200.engine import XCContext
+
+    wl = workloads.make("c5gga")
+    N, G = wl.nao, wl.ngrids
+    assert N == 1000 and G == 1_000_000 and wl.ncomp == 4
+    ctx = XCContext(nao=N, ngrids_max=G, ncomp=4, net=workloads.net_spec(wl))
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env)
+
+    def run(lo, hi):
+        ctx.set_grid(wl.coords[lo:hi], wl.weights[lo:hi]).eval_ao(1)
+        out, resid = ctx.nr_rks_fwd(wl.dm, wl.theta, "GGA")
+        bar = ctx.nr_rks_vjp(wl.theta, resid, [wl.e_bar], wl.v_bar, "GGA")
+        return out.clone(), bar.clone(), resid
+
+    out, bar, _ = run(0, G)
+    out2, bar2, resid = run(0, G)
+    assert torch.equal(out, out2) and torch.equal(bar, bar2)
+    assert torch.isfinite(out).all() and torch.isfinite(bar).all()
+    # rho[0..3] and the GGA V_xc at FULL size against cuBLAS DGEMM (torch.matmul) on the same AO tensor
+    ld = resid.numel() // 7  # [rho x4 | exc | vrho | vgamma], each GpadMax long
+    rho_k = resid[: 4 * ld].view(4, ld)[:, :G]
+    vrho_k, vgam_k = resid[5 * ld : 5 * ld + G], resid[6 * ld : 6 * ld + G]
+    S = torch.as_tensor(0.5 * (wl.dm + wl.dm.T)).cuda()
+    wt = torch.as_tensor(wl.weights).cuda()
+    ao = ctx.get_ao(4)[0]  # [4, G, N] view of a fresh copy (32 GB)
+    Vref = torch.zeros(N, N, dtype=torch.float64, device="cuda")
+    worst = 0.0
+    for lo in range(0, G, 32768):
+        sl = slice(lo, lo + 32768)
+        a0 = ao[0, sl]
+        c0 = a0 @ S
+        r = [(c0 * a0).sum(1)] + [2.0 * (c0 * ao[k, sl]).sum(1) for k in (1, 2, 3)]
+        for k in range(4):
+            worst = max(worst, (r[k] - rho_k[k, sl]).abs().max().item())
+        wv0 = 0.5 * wt[sl] * vrho_k[sl]
+        aow = a0 * wv0[:, None]
+        for k in (1, 2, 3):
+            aow += ao[k, sl] * (2.0 * wt[sl] * vgam_k[sl] * rho_k[k, sl])[:, None]
+        Vref += a0.T @ aow
+    del ao
+    V = out.cpu().numpy()[0][: N * N].reshape(N, N)
+    Vr = (Vref + Vref.T).cpu().numpy()
+    assert worst <= 1e-12 * rho_k.abs().max().item()
+    assert rel_err(V, Vr) <= 1e-11
+    del Vref
+    cut = 2048
+    oa, ba, _ = run(0, cut)
+    ob, bb, _ = run(cut, G)
+    assert rel_err((oa + ob).cpu().numpy(), out.cpu().numpy()) <= 1e-11
+    assert rel_err((ba + bb).cpu().numpy(), bar.cpu().numpy()) <= 1e-11
+    m = wl.mol
+    ref = step_ref.xc_step(m._atm, m._bas, m._env, wl.coords[:cut], wl.weights[:cut], wl.dm, wl.net, wl.theta, "GGA",
+                           wl.e_bar, wl.v_bar)
+    _check_vs_oracle(oa, ba, ref, N)
+    ctx.close()
+
+
+# ---- N ranks vs 1 rank on hardware ---------------------------------------------------------------------------------
+def _rank_main(rank, world, port, G, q):
+    import torch
+    import torch.distributed as tdist
+
+    from qex_b200 import workloads
+    from qex_b200.dist import Comm, ShardedXC, shard_range
+    from qex_b200.engine import XCContext
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    tdist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    comm = Comm(rank, world, rank)
+    wl = workloads.make("c5", ngrids=G)
+    N = wl.nao
+    lo, hi = shard_range(G, rank, world)
+    ctx = XCContext(nao=N, ngrids_max=hi - lo, net=workloads.net_spec(wl), device=rank)
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env).set_grid(wl.coords[lo:hi], wl.weights[lo:hi]).eval_ao(0)
+    sx = ShardedXC(ctx, comm=comm)
+    d_dm, d_th = ctx.dev(wl.dm, (1, N, N)), ctx.dev(wl.theta)
+    d_eb, d_vb = ctx.dev([wl.e_bar]), ctx.dev(wl.v_bar, (1, N, N))
+    out, bar, resid = ctx.empty(1, N * N + 2), ctx.empty(N * N + wl.theta.size), ctx.empty(ctx.resid_doubles)
+    runs = []
+    for _ in range(2):
+        sx.step(d_dm, d_th, d_eb, d_vb, "NN", out, bar, resid)
+        torch.cuda.synchronize()
+        runs.append((out.cpu().numpy().copy(), bar.cpu().numpy().copy()))
+    # host-buffer path (rank 0 uploads + NCCL broadcast, results on rank 0 only)
+    io = sx.make_host_io(1, wl.theta.size)
+    if rank == 0:
+        sx.pack_host_inputs(io, wl.dm, wl.theta, wl.e_bar, wl.v_bar)
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    d_c, d_w = ctx.empty(hi - lo, 3), ctx.empty(hi - lo)
+    h_out, h_bar = sx.step_host(io, pin(wl.coords[lo:hi]), pin(wl.weights[lo:hi]), d_c, d_w, "NN", 0)
+    host = (h_out.numpy().copy(), h_bar.numpy().copy()) if rank == 0 else None
+    q.put((rank, runs, host))
+    tdist.barrier()
+    comm.close()
+    tdist.destroy_process_group()
+
+
+def _ngpus():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_n_rank_allreduced_result_equals_one_rank(world):
+    """The grid-sharded step (dist.shard_range + qexxc_allreduce over NCCL) against the same step on ONE GPU:
+    |dE_xc| <= 1e-9, V_xc / dm_bar / theta_bar within 1e-10 (max-norm and element-wise), bit-identical between two
+    runs at the same N and on every rank, and the host-buffer pipeline (rank-0 upload + NCCL broadcast) returns the
+    same bits as the device-resident step."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from qex_b200 import workloads
+    from qex_b200.engine import XCContext
+
+    G = 262_144 + 77  # ragged: the last shard is not a multiple of the 128-row tile
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29600 + (os.getpid() + world) % 1500
+    procs = [mpc.Process(target=_rank_main, args=(r, world, port, G, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, runs, host = q.get(timeout=600)
+        got[r] = (runs, host)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # one rank, whole grid
+    wl = workloads.make("c5", ngrids=G)
+    N = wl.nao
+    torch.cuda.set_device(0)
+    ctx = XCContext(nao=N, ngrids_max=G, net=workloads.net_spec(wl), device=0)
+    ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env).set_grid(wl.coords, wl.weights).eval_ao(0)
+    o1, r1 = ctx.nr_rks_fwd(wl.dm, wl.theta, "NN")
+    b1 = ctx.nr_rks_vjp(wl.theta, r1, [wl.e_bar], wl.v_bar, "NN").cpu().numpy()
+    o1 = o1.cpu().numpy()[0]
+    nn = N * N
+    (oa, ba), (ob, bb) = got[0][0]
+    assert np.array_equal(oa, ob) and np.array_equal(ba, bb)  # bit-identical between two runs at the same N
+    for r in range(1, world):  # and on every rank
+        assert np.array_equal(got[r][0][0][0], oa) and np.array_equal(got[r][0][0][1], ba)
+    h_out, h_bar = got[0][1]
+    assert np.array_equal(h_out, oa) and np.array_equal(h_bar, ba)  # host pipeline == device-resident step
+    on = oa[0]
+    assert abs(on[nn] - o1[nn]) <= 1e-9 and abs(on[nn + 1] - o1[nn + 1]) <= 1e-9 * max(1.0, abs(o1[nn + 1]))
+    for a, b in ((on[:nn], o1[:nn]), (ba[:nn], b1[:nn]), (ba[nn:], b1[nn:])):
+        assert rel_err(a, b) <= TOL64 and elem_err(a, b) <= TOL_ELEM
+    ctx.close()

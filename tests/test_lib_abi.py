@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [n for n in _declared() if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(_lib.EXPORTS) == _declared()
-    assert lib.qexxc_version() == 100
+    assert lib.qexxc_version() == 200
 
 
 def test_n_params(lib):
@@ -66,7 +66,7 @@ def test_bad_arguments_return_codes(lib):
     h = C.c_void_p()
     assert lib.qexxc_create(C.byref(h), 0, 0, 1, 128, 4, None) == _lib.ERR_ARG
     assert lib.qexxc_create(C.byref(h), 0, 1, 3, 128, 4, None) == _lib.ERR_ARG
-    assert lib.qexxc_nr_rks_fwd(None, 0, 0, None, None, None, None, None) == _lib.ERR_ARG
+    assert lib.qexxc_nr_rks_fwd(None, 0, 0, None, None, 0, None, None, None) == _lib.ERR_ARG
     assert lib.qexxc_destroy(None) == 0
     # grid partition: argument checks come before any device work; an empty grid is a no-op
     assert lib.qexxc_becke_partition(0, None, 10, None, None, None, None, 0, 0, None, None, None) == _lib.ERR_ARG
