@@ -183,7 +183,11 @@ def test_cache_ao_is_keyed_on_content():
     ni.eval_xc = xc.make_eval_xc(net, is_global_xc=False)
     a = ni.nr_rks(mol, grids, "NN", dm, params=params)
     c2 = grids.coords.copy()
-    c2[[0, 1]] = c2[[1, 0]] + np.array([[0.25, 0, 0], [-0.25, 0, 0]])  # same coordinate sum, different points
+    # same coordinate sum, different points -- on the two points that carry the most weight * density, so the
+    # change is visible in E_xc (the first points of the grid sit on the innermost shell with ~0 weight)
+    r = np.linalg.norm(grids.coords[:, None, :] - np.asarray(mol.atom_coords())[None], axis=-1).min(axis=1)
+    i, j = np.argsort(grids.weights * np.exp(-2.0 * r))[-2:]
+    c2[[i, j]] = c2[[j, i]] + np.array([[0.25, 0, 0], [-0.25, 0, 0]])
     assert abs(c2.sum() - grids.coords.sum()) < 1e-9
     g2 = gen_grid.Grids(mol, coords=c2, weights=grids.weights)
     b = ni.nr_rks(mol, g2, "NN", dm, params=params)
