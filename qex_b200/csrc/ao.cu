@@ -124,21 +124,115 @@ eval_ao_kernel(const double* __restrict__ coords, const ShellDev* __restrict__ s
 
 
 // ---- tiled evaluator -------------------------------------------------------------------------------
-// CTA = P grid points.  Phase A: every (point, atom) gets its 16 real solid harmonics (and their
+// CTA = P grid points.  Phase A: every (point, atom) gets its (lmax+1)^2 real solid harmonics (and their
 // gradients), every (point, radial function) its contracted radial sum -- each exp is evaluated
 // exactly once and staged in shared memory.  Phase B: warps sweep (point, 32-AO chunk) pairs;
 // lane n multiplies harmonic x radial for AO n and the warp stores 256 contiguous bytes of the AO
 // row, so the 8*N bytes per point stream to HBM fully coalesced.
+//
+// The kernel is co-limited by the FP64 pipe (one exp per primitive per point: 800 per point at c5) and the
+// HBM write stream (8 KB per point), so the exponential is a table-driven one: exp(x) = 2^(k/64) * e^r with
+// k = round(64 x / ln 2), |r| <= ln2/128, a degree-5 Taylor tail (remainder r^6/720 < 4e-17) and a
+// 64-entry table of correctly rounded 2^(j/64) -- 9 FP64 instructions instead of libm's ~17, relative error
+// <= 2.5e-16 -- and the radial sums of four points are interleaved so four exp chains are in flight per thread.
+__device__ const double kExp2Tab[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
+};
+
+// exp(x) for x <= 0; returns 0 below -700 (the true value is < 1e-304)
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ T) {
+    const double L = 92.33248261689366, C1 = 0x1.62e42fe000000p-7, C2 = 0x1.f473de6af278fp-36;
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of x*L + MAGIC is round(x*L)
+    const double xs = x < -700.0 ? -700.0 : x;
+    double kd = fma(xs, L, MAGIC);
+    const int k = __double2loint(kd);
+    kd -= MAGIC;
+    double r = fma(kd, -C1, xs);
+    r = fma(kd, -C2, r);
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double y = T[k & 63] * p;
+    const double sc = __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));
+    return x < -700.0 ? 0.0 : sc;
+}
+
 template <int L>
-__device__ __forceinline__ void fill_harm(double* __restrict__ H, int stride, bool deriv, double x, double y, double z) {
+__device__ __forceinline__ void fill_harm(double* __restrict__ H, int stride, int NH, bool deriv, double x, double y, double z) {
 #pragma unroll
     for (int m = 0; m < 2 * L + 1; ++m) {
         const V4 s = solid<L>(m, x, y, z);
         H[(L * L + m) * stride] = s.v;
-        if (deriv) {  // rows 17.., 33.., 49.. hold d/dx, d/dy, d/dz
-            H[(17 + L * L + m) * stride] = s.x;
-            H[(33 + L * L + m) * stride] = s.y;
-            H[(49 + L * L + m) * stride] = s.z;
+        if (deriv) {  // row blocks NH+1.., 2NH+1.., 3NH+1.. hold d/dx, d/dy, d/dz
+            H[(NH + 1 + L * L + m) * stride] = s.x;
+            H[(2 * NH + 1 + L * L + m) * stride] = s.y;
+            H[(3 * NH + 1 + L * L + m) * stride] = s.z;
+        }
+    }
+}
+
+// rows of the harmonic table for NH = (lmax+1)^2 harmonics
+__host__ __device__ inline int ao_tab_rows(int NH, bool deriv) { return deriv ? 4 * NH + 4 : NH + 1; }
+
+template <bool DERIV, int Q>
+__device__ __forceinline__ void radial_items(const ShellDev* __restrict__ shells, const int* __restrict__ shell_atom,
+                                             const double* __restrict__ envb, const double* __restrict__ Hs,
+                                             double* __restrict__ Rs, const double* __restrict__ T, int hstr, int NH,
+                                             int nshell, int natm, int nrad, int P, long g0, int G) {
+    constexpr int RS = DERIV ? 2 : 1;
+    const int nq = (P + Q - 1) / Q;
+    for (int it = threadIdx.x; it < nshell * nq; it += blockDim.x) {
+        const int pq = it / nshell, s = it - pq * nshell;
+        const ShellDev sh = shells[s];
+        const int ia = shell_atom[s];
+        const double* ex = envb + sh.ptr_exp;
+        double rr[Q];
+#pragma unroll
+        for (int h = 0; h < Q; ++h) {
+            const int p = min(pq * Q + h, P - 1);
+            rr[h] = Hs[NH * hstr + p * natm + ia];
+        }
+        for (int ic = 0; ic < sh.nctr; ++ic) {
+            const double* cf = envb + sh.ptr_coef + ic * sh.nprim;
+            double R0[Q], R1[Q];
+#pragma unroll
+            for (int h = 0; h < Q; ++h) R0[h] = R1[h] = 0.0;
+            for (int q = 0; q < sh.nprim; ++q) {
+                const double a = ex[q], cq = cf[q];
+#pragma unroll
+                for (int h = 0; h < Q; ++h) {
+                    const double e = cq * exp_neg(-a * rr[h], T);
+                    R0[h] += e;
+                    if (DERIV) R1[h] -= 2.0 * a * e;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < Q; ++h) {
+                const int p = pq * Q + h;
+                if (p < P) {
+                    const bool live = g0 + p < G;  // padding rows come out exactly zero
+                    double* R = Rs + ((size_t)p * nrad + sh.rad_off + ic) * RS;
+                    R[0] = live ? R0[h] : 0.0;
+                    if (DERIV) R[1] = live ? R1[h] : 0.0;
+                }
+            }
         }
     }
 }
@@ -152,17 +246,20 @@ eval_ao_tiled_kernel(const double* __restrict__ coords, const ShellDev* __restri
                      int GpadMax, int N, int Npad, int C, int P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // Hs[row][col], col = p*natm + atom, odd column stride (conflict-free both ways).
-    // rows: 0..15 harmonics | 16 r^2 | (DERIV) 17..64 d/dx,d/dy,d/dz of the harmonics | 65..67 x,y,z
-    constexpr int NROW = DERIV ? 68 : 17;
+    // rows: 0..NH-1 harmonics | NH r^2 | (DERIV) d/dx, d/dy, d/dz blocks of NH rows | x, y, z
+    const int NH = (lmax + 1) * (lmax + 1);
+    const int NROW = ao_tab_rows(NH, DERIV);
     constexpr int RS = DERIV ? 2 : 1;  // per (point, radial): R0 (+ R1)
     const int hstr = (P * natm) | 1;
     double* Hs = reinterpret_cast<double*>(smem_raw);
     double* Rs = Hs + (size_t)NROW * hstr;  // [P][nrad][RS]
+    double* T = Rs + (size_t)P * nrad * RS;  // [64] 2^(j/64)
     const int b = blockIdx.y;
     const long g0 = (long)blockIdx.x * P;
     const double* envb = env + (long)b * nenv;
     const long cstride = (long)GpadMax * Npad;
     const int tid = threadIdx.x;
+    if (tid < 64) T[tid] = kExp2Tab[tid];
 
     // ---- phase A1: harmonics and r^2 per (point, atom) ----
     for (int it = tid; it < P * natm; it += blockDim.x) {
@@ -177,46 +274,20 @@ eval_ao_tiled_kernel(const double* __restrict__ coords, const ShellDev* __restri
             z = r[2] - envb[ac + 2];
         }
         double* H = Hs + it;
-        fill_harm<0>(H, hstr, DERIV, x, y, z);
-        fill_harm<1>(H, hstr, DERIV, x, y, z);
-        if (lmax >= 2) fill_harm<2>(H, hstr, DERIV, x, y, z);
-        if (lmax >= 3) fill_harm<3>(H, hstr, DERIV, x, y, z);
-        H[16 * hstr] = x * x + y * y + z * z;
+        fill_harm<0>(H, hstr, NH, DERIV, x, y, z);
+        if (lmax >= 1) fill_harm<1>(H, hstr, NH, DERIV, x, y, z);
+        if (lmax >= 2) fill_harm<2>(H, hstr, NH, DERIV, x, y, z);
+        if (lmax >= 3) fill_harm<3>(H, hstr, NH, DERIV, x, y, z);
+        H[NH * hstr] = x * x + y * y + z * z;
         if (DERIV) {
-            H[65 * hstr] = x;
-            H[66 * hstr] = y;
-            H[67 * hstr] = z;
+            H[(4 * NH + 1) * hstr] = x;
+            H[(4 * NH + 2) * hstr] = y;
+            H[(4 * NH + 3) * hstr] = z;
         }
     }
     __syncthreads();
-    // ---- phase A2: radial sums; an item = one shell x two points (shell data loaded once) ----
-    const int npair = (P + 1) >> 1;
-    for (int it = tid; it < nshell * npair; it += blockDim.x) {
-        const int pp = it / nshell, s = it - pp * nshell;
-        const ShellDev sh = shells[s];
-        const int ia = shell_atom[s];
-        const double* ex = envb + sh.ptr_exp;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int p = 2 * pp + h;
-            if (p >= P) break;
-            const bool live = g0 + p < G;
-            const double rr = Hs[16 * hstr + p * natm + ia];
-            for (int ic = 0; ic < sh.nctr; ++ic) {
-                const double* cf = envb + sh.ptr_coef + ic * sh.nprim;
-                double R0 = 0.0, R1 = 0.0;
-                for (int q = 0; q < sh.nprim; ++q) {
-                    const double a = ex[q];
-                    const double e = cf[q] * exp(-a * rr);
-                    R0 += e;
-                    if (DERIV) R1 -= 2.0 * a * e;
-                }
-                double* R = Rs + ((size_t)p * nrad + sh.rad_off + ic) * RS;
-                R[0] = live ? R0 : 0.0;  // padding rows come out exactly zero
-                if (DERIV) R[1] = live ? R1 : 0.0;
-            }
-        }
-    }
+    // ---- phase A2: radial sums; an item = one shell x four points (shell data loaded once, four exp chains) ----
+    radial_items<DERIV, 4>(shells, shell_atom, envb, Hs, Rs, T, hstr, NH, nshell, natm, nrad, P, g0, G);
     __syncthreads();
     // ---- phase B: a warp owns a 32-AO chunk for all P points; 256-byte coalesced row stores ----
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
@@ -231,26 +302,34 @@ eval_ao_tiled_kernel(const double* __restrict__ coords, const ShellDev* __restri
         const double* H = Hs + (on ? m.lm * hstr + m.atom : 0);
         const double* R = Rs + (on ? m.rad * RS : 0);
         double* row = ao + ((long)b * C * GpadMax + g0) * Npad + n;
+        if (!DERIV) {
+            int p = 0;
+            for (; p + 4 <= pmax; p += 4, row += 4 * (long)Npad) {  // four independent load pairs in flight
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = on ? H[(p + u) * natm] * R[(size_t)(p + u) * nrad] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) __stcs(row + u * (long)Npad, v[u]);
+            }
+            for (; p < pmax; ++p, row += Npad) __stcs(row, on ? H[p * natm] * R[(size_t)p * nrad] : 0.0);
+            continue;
+        }
         for (int p = 0; p < pmax; ++p, row += Npad) {
             double v0 = 0.0, vx = 0.0, vy = 0.0, vz = 0.0;
             if (on) {
                 const double* Hp = H + p * natm;
                 const double h = Hp[0], R0 = R[(size_t)p * nrad * RS];
                 v0 = h * R0;
-                if (DERIV) {
-                    const double R1 = R[(size_t)p * nrad * RS + 1];
-                    const double* Xp = Hs + p * natm + m.atom;
-                    vx = Hp[17 * hstr] * R0 + h * Xp[65 * hstr] * R1;
-                    vy = Hp[33 * hstr] * R0 + h * Xp[66 * hstr] * R1;
-                    vz = Hp[49 * hstr] * R0 + h * Xp[67 * hstr] * R1;
-                }
+                const double R1 = R[(size_t)p * nrad * RS + 1];
+                const double* Xp = Hs + p * natm + m.atom;
+                vx = Hp[(NH + 1) * hstr] * R0 + h * Xp[(4 * NH + 1) * hstr] * R1;
+                vy = Hp[(2 * NH + 1) * hstr] * R0 + h * Xp[(4 * NH + 2) * hstr] * R1;
+                vz = Hp[(3 * NH + 1) * hstr] * R0 + h * Xp[(4 * NH + 3) * hstr] * R1;
             }
-            row[0] = v0;
-            if (DERIV) {
-                row[cstride] = vx;
-                row[2 * cstride] = vy;
-                row[3 * cstride] = vz;
-            }
+            __stcs(row, v0);
+            __stcs(row + cstride, vx);
+            __stcs(row + 2 * cstride, vy);
+            __stcs(row + 3 * cstride, vz);
         }
     }
 }
@@ -317,12 +396,16 @@ int launch_set_grid(qexxc_ctx* c, const double* coords, const double* weights, i
 int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
     ProfScope prof(c, QEXXC_PROF_EVAL_AO, st);
     // tiled kernel when the per-point staging fits in shared memory (it does up to ~1500 atoms)
-    const size_t per_pt = ((size_t)c->natm * (deriv ? 68 : 17) + (size_t)c->nrad * (deriv ? 2 : 1)) * 8;
-    int P = (int)((deriv ? 140 * 1024 : 100 * 1024) / (per_pt ? per_pt : 1));
+    const int NH = (c->lmax + 1) * (c->lmax + 1);
+    const int nrow = ao_tab_rows(NH, deriv != 0);
+    const size_t per_pt = ((size_t)c->natm * nrow + (size_t)c->nrad * (deriv ? 2 : 1)) * 8;
+    // two 512-thread CTAs per SM (the register file allows no more): up to ~110 KB of tables each
+    int P = (int)((110 * 1024) / (per_pt ? per_pt : 1));
     if (P > 16) P = 16;
+    if (P >= 4) P &= ~3;  // radial sums run four points at a time
+    if (getenv("QEXXC_AO_P")) P = atoi(getenv("QEXXC_AO_P"));
     if (P >= 1) {
-        const size_t smem = ((size_t)(deriv ? 68 : 17) * (((size_t)P * c->natm) | 1) +
-                             (size_t)P * c->nrad * (deriv ? 2 : 1)) * 8;
+        const size_t smem = ((size_t)nrow * (((size_t)P * c->natm) | 1) + (size_t)P * c->nrad * (deriv ? 2 : 1) + 64) * 8;
         dim3 tgrid((unsigned)((c->Gpad + P - 1) / P), c->ao_shared ? 1 : c->B);
         // two resident CTAs share the SM's shared memory whatever the block size, so wide blocks double the
         // resident warps (the kernel is latency-bound, not pipe-bound); small molecules keep 256 threads

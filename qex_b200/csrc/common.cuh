@@ -206,6 +206,16 @@ int launch_mlp_local_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_b
                          const double* vgamma_bar, long in_bstride, double* rho_bar, int accumulate,
                          double* theta_bar, int accumulate_theta, int nbatch, long npts_per_batch,
                          cudaStream_t st);
+// xc_mlp_tc.cu: FP32 network path on tcgen05 / TMEM (width <= 64, <= 3 hidden layers)
+bool mlp_tc_enabled(const qexxc_ctx* c);
+int launch_mlp_tc_fwd(qexxc_ctx* c, int xctype, const double* rho, long rho_bstride, long rho_cstride,
+                      const double* theta, double* exc, double* vrho, double* vgamma, long out_bstride, int nbatch,
+                      long npts_per_batch, cudaStream_t st);
+size_t mlp_tc_tape_bytes(const qexxc_ctx* c);
+int launch_mlp_tc_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_bstride, long rho_cstride,
+                      const double* theta, const double* exc_bar, const double* vrho_bar, const double* vgamma_bar,
+                      long in_bstride, double* rho_bar, int accumulate, int nbatch, long npts_per_batch, int* grid_out,
+                      cudaStream_t st);
 // xc_global.cu
 size_t global_mlp_smem(int L, int H);
 int launch_global_mlp(qexxc_ctx* c, bool vjp, const double* rho, long ld, int G, const double* theta, double* exc,

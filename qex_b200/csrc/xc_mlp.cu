@@ -682,7 +682,9 @@ MlpParams base_params(const qexxc_ctx* c, int xctype) {
 int mlp_local_grid(const qexxc_ctx* c) { return c->num_sms; }
 size_t mlp_local_tape_bytes(const qexxc_ctx* c) {
     const size_t el = c->net.precision == QEXXC_PREC_F32 ? 4 : 8;
-    return (size_t)mlp_local_grid(c) * c->net.n_hidden * NW * MB * NB * 32 * 2 * el;
+    const size_t resident = (size_t)mlp_local_grid(c) * c->net.n_hidden * NW * MB * NB * 32 * 2 * el;
+    const size_t tc = mlp_tc_enabled(c) ? mlp_tc_tape_bytes(c) : 0;
+    return tc > resident ? tc : resident;
 }
 
 // rho/rho_bar etc. are given as [B][C][ld]-style arrays through explicit strides; npts_per_batch
@@ -691,6 +693,9 @@ int launch_mlp_local_fwd(qexxc_ctx* c, int xctype, const double* rho, long rho_b
                          const double* theta, double* exc, double* vrho, double* vgamma, long out_bstride,
                          int nbatch, long npts_per_batch, cudaStream_t st) {
     QX_TRY(check_supported(c->net));
+    if (mlp_tc_enabled(c))
+        return launch_mlp_tc_fwd(c, xctype, rho, rho_bstride, rho_cstride, theta, exc, vrho, vgamma, out_bstride, nbatch,
+                                 npts_per_batch, st);
     MlpParams p = base_params(c, xctype);
     p.rho = rho;
     p.rho_bstride = rho_bstride;
@@ -759,6 +764,17 @@ int launch_mlp_local_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_b
     if (grid <= 0) return QEXXC_OK;
     const bool f32 = c->net.precision == QEXXC_PREC_F32;
     ProfScope prof(c, QEXXC_PROF_XC_VJP, st);
+    if (mlp_tc_enabled(c)) {
+        int tgrid = 0;
+        QX_TRY(launch_mlp_tc_vjp(c, xctype, rho, rho_bstride, rho_cstride, theta, exc_bar, vrho_bar, vgamma_bar, in_bstride,
+                                 rho_bar, accumulate, nbatch, npts_per_batch, &tgrid, st));
+        if (tgrid > 0) {
+            theta_reduce_kernel<<<(unsigned)((c->n_theta + 255) / 256), 256, 0, st>>>(c->red, tgrid, c->n_theta, theta_bar,
+                                                                                   accumulate_theta);
+            QX_LAUNCH_CHECK(c);
+        }
+        return QEXXC_OK;
+    }
 #define QX_VJP(T, A)                                                                        \
     do {                                                                                    \
         const size_t sm = smem_elems<T>(p.L, true) * sizeof(T);                             \
