@@ -17,7 +17,8 @@ def _functional(net: dict, theta, ngrids):
     if kind == "local_mlp":
         F = net.get("n_features", 1)
         spec = mlp_ref.MLPSpec([F] + [net["width"]] * net["n_hidden"] + [1], net.get("activation", "tanh"),
-                               in_scale=net.get("in_scale", 0.5))
+                               in_scale=net.get("in_scale", 0.5),
+                               out_transform="neg_scale_swish" if net.get("out_transform") else "none")
         if F == 1:
             fwd = lambda r, p: mlp_ref.exc_and_vrho_local(spec, theta, r)
             vjp = lambda r, p, eb, vb: mlp_ref.exc_and_vrho_local_vjp(spec, theta, r, eb, vb)

@@ -302,7 +302,13 @@ int qexxc_create_ex(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngri
         }
     }
     size_t red = 2 * B * (size_t)stage4_nblocks(c) + 16;
-    if (c->net.kind == QEXXC_NET_LOCAL_MLP) {
+    if (c->net.kind == QEXXC_NET_LOCAL_MLP && mlp_is_wide(c->net)) {
+        if (c->net.n_features < 1 || c->net.n_features > 2 || c->net.width < 1 || c->net.n_hidden < 1) {
+            set_error("LocalMLP: n_features must be 1 or 2, n_neurons and n_layers positive");
+            rc = QEXXC_ERR_UNSUPPORTED;
+        }
+        QX_A(c->wide_ws, mlp_wide_ws_doubles(c));
+    } else if (c->net.kind == QEXXC_NET_LOCAL_MLP) {
         const size_t r = (size_t)mlp_local_grid(c) * c->n_theta;
         if (r > red) red = r;
         c->tape_bytes = mlp_local_tape_bytes(c);

@@ -119,6 +119,7 @@ struct qexxc_ctx {
     size_t ws_items_bytes = 0, ws_start_cap = 0;
     double* red = nullptr;      // per-CTA partial sums (excsum, nelec, theta_bar ...)
     size_t red_doubles = 0;
+    double* wide_ws = nullptr;  // LocalMLP wider than 64 or deeper than 3: layer-by-layer workspace (xc_mlp_wide.cu)
     void* tape = nullptr;       // MLP reverse-mode tape (per-CTA slots)
     size_t tape_bytes = 0;
     unsigned char* qperm = nullptr;  // QNN ring permutation tables (2 x 256 bytes)
@@ -206,6 +207,16 @@ int launch_mlp_local_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_b
                          const double* vgamma_bar, long in_bstride, double* rho_bar, int accumulate,
                          double* theta_bar, int accumulate_theta, int nbatch, long npts_per_batch,
                          cudaStream_t st);
+// xc_mlp_wide.cu: any width / depth, layer by layer (float64)
+bool mlp_is_wide(const qexxc_net_desc& net);
+size_t mlp_wide_ws_doubles(const qexxc_ctx* c);
+int launch_mlp_wide_fwd(qexxc_ctx* c, int xctype, const double* rho, long rho_bstride, long rho_cstride,
+                        const double* theta, double* exc, double* vrho, double* vgamma, long out_bstride, int nbatch,
+                        long npts_per_batch, cudaStream_t st);
+int launch_mlp_wide_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_bstride, long rho_cstride,
+                        const double* theta, const double* exc_bar, const double* vrho_bar, const double* vgamma_bar,
+                        long in_bstride, double* rho_bar, int accumulate, double* theta_bar, int accumulate_theta,
+                        int nbatch, long npts_per_batch, cudaStream_t st);
 // xc_mlp_tc.cu: FP32 network path on tcgen05 / TMEM (width <= 64, <= 3 hidden layers)
 bool mlp_tc_enabled(const qexxc_ctx* c);
 int launch_mlp_tc_fwd(qexxc_ctx* c, int xctype, const double* rho, long rho_bstride, long rho_cstride,

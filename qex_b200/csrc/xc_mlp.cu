@@ -692,6 +692,9 @@ size_t mlp_local_tape_bytes(const qexxc_ctx* c) {
 int launch_mlp_local_fwd(qexxc_ctx* c, int xctype, const double* rho, long rho_bstride, long rho_cstride,
                          const double* theta, double* exc, double* vrho, double* vgamma, long out_bstride,
                          int nbatch, long npts_per_batch, cudaStream_t st) {
+    if (mlp_is_wide(c->net))
+        return launch_mlp_wide_fwd(c, xctype, rho, rho_bstride, rho_cstride, theta, exc, vrho, vgamma, out_bstride, nbatch,
+                                   npts_per_batch, st);
     QX_TRY(check_supported(c->net));
     if (mlp_tc_enabled(c))
         return launch_mlp_tc_fwd(c, xctype, rho, rho_bstride, rho_cstride, theta, exc, vrho, vgamma, out_bstride, nbatch,
@@ -742,6 +745,9 @@ int launch_mlp_local_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_b
                          const double* vgamma_bar, long in_bstride, double* rho_bar, int accumulate,
                          double* theta_bar, int accumulate_theta, int nbatch, long npts_per_batch,
                          cudaStream_t st) {
+    if (mlp_is_wide(c->net))
+        return launch_mlp_wide_vjp(c, xctype, rho, rho_bstride, rho_cstride, theta, exc_bar, vrho_bar, vgamma_bar, in_bstride,
+                                   rho_bar, accumulate, theta_bar, accumulate_theta, nbatch, npts_per_batch, st);
     QX_TRY(check_supported(c->net));
     MlpParams p = base_params(c, xctype);
     p.rho = rho;
