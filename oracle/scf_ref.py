@@ -203,3 +203,73 @@ def scf_fixed_point(dm, eri, ao_grid, grid_weights, s1e, h1e, nelectron, exc_vrh
         delta = np.abs(new - dm).max()
         dm = new
     return dm, delta
+
+
+# ---- padded / masked variants (scf_functions_masked.py:244-309,546-588,917-967; generalized_eigensolver_masked.py:19-89)
+def masked_generalized_eigh(fock, s1e, mask):
+    n = fock.shape[0]
+    m2 = mask[:, None] & mask[None, :]
+    pad = np.where((~mask)[:, None] & np.eye(n, dtype=bool), 1e-12, 0.0)
+    f = np.where(m2, fock, 0.0) + pad
+    s = np.where(m2, s1e, pad)
+    w, v = generalized_eigh(f, s)
+    key = np.where(mask, w, 1e12)  # the reference keys on the mask by position
+    idx = np.argsort(key, kind="stable")
+    w = w[idx] * mask[idx]
+    v = np.where(m2[:, idx], v[:, idx], 0.0)
+    return w, v
+
+
+def get_occ_masked(nelectron, mo_energy, mask):
+    e = np.where(mask, mo_energy, 1e10)
+    e_idx = np.argsort(e, kind="stable")
+    idx = np.arange(mo_energy.shape[0])
+    occ = np.where((idx < nelectron // 2) & mask[e_idx], 2.0, 0.0)
+    return occ[np.argsort(e_idx)]
+
+
+def make_rdm1_masked(mo_coeff, mo_occ, mask):
+    c = np.where(mask[:, None], mo_coeff, 0.0)
+    occ = np.where(mask, mo_occ, 0.0)
+    dm = np.einsum("ij,j,kj->ik", c, occ, c)
+    return np.where(mask[:, None] & mask[None, :], dm, 0.0)
+
+
+def get_veff_masked(dm, eri, ao_grid, grid_weights, mask, exc_vrho, eps=1e-12):
+    """The definition in force in the reference module (the later, "stable" one): padded entries are eps, rho += eps."""
+    m2 = mask[:, None] & mask[None, :]
+    m4 = mask[:, None, None, None] & mask[None, :, None, None] & mask[None, None, :, None] & mask[None, None, None, :]
+    dm_m = np.where(m2, dm, eps)
+    eri_m = np.where(m4, eri, eps)
+    ao_m = np.where(mask[None, :], ao_grid, eps)
+    J = np.einsum("ijkl,kl->ij", eri_m, dm_m)
+    rho = np.einsum("gi,ij,gj->g", ao_m, dm_m, ao_m) + eps
+    exc, vrho = exc_vrho(rho)
+    vxc = np.einsum("gi,g,gj->ij", ao_m, grid_weights * vrho, ao_m)
+    J = np.where(m2, J, 0.0)
+    vxc = np.where(m2, vxc, 0.0)
+    return J + vxc, float(np.sum(exc * rho * grid_weights)), J
+
+
+def energy_tot_masked(dm, h1e, J, exc_energy, energy_nuc, mask):
+    m2 = mask[:, None] & mask[None, :]
+    dm, h1e, J = np.where(m2, dm, 0.0), np.where(m2, h1e, 0.0), np.where(m2, J, 0.0)
+    return float(np.einsum("ij,ji->", dm, h1e) + 0.5 * np.einsum("ij,ij->", dm, J) + exc_energy + energy_nuc)
+
+
+def scf_loop_padded(dm, eri, ao_grid, grid_weights, s1e, h1e, energy_nuc, nelectron, mask, exc_vrho, max_cycle=15,
+                    diis_max_vec=15, diis_min_vec=2, diis_start_cycle=1, diis_damping=0.0, eps=1e-12):
+    vhf, exc_e, J = get_veff_masked(dm, eri, ao_grid, grid_weights, mask, exc_vrho, eps)
+    e_tot = energy_tot_masked(dm, h1e, J, exc_e, energy_nuc, mask)
+    st = initialize_diis(diis_max_vec)
+    energies = []
+    for cycle in range(max_cycle):
+        fock = h1e + vhf
+        if cycle >= diis_start_cycle:
+            fock, st = apply_diis(st, fock, dm, s1e, diis_max_vec, diis_min_vec, diis_damping)
+        mo_energy, mo_coeff = masked_generalized_eigh(fock, s1e, mask)
+        dm = make_rdm1_masked(mo_coeff, get_occ_masked(nelectron, mo_energy, mask), mask)
+        vhf, exc_e, J = get_veff_masked(dm, eri, ao_grid, grid_weights, mask, exc_vrho, eps)
+        e_tot = energy_tot_masked(dm, h1e, J, exc_e, energy_nuc, mask)
+        energies.append(e_tot)
+    return e_tot, dm, np.array(energies)

@@ -144,3 +144,50 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 }  // namespace tc05
 }  // namespace qexxc
+
+// ---- 16-bit (bf16) operands -------------------------------------------------------------------------------------
+// MN-major TF32 operands exist only in a different swizzle (SWIZZLE_128B_BASE32B), so a TF32 plane cannot serve
+// both views.  16-bit planes can: a [R rows x 64] bf16 matrix stored as R rows x 128 bytes with the 16-byte chunk
+// index XOR-ed with (row & 7) is a K-major operand (rows = M/N, columns = K, 16 columns = 32 bytes per
+// instruction) AND an MN-major operand (columns = M/N, rows = K, 16 rows = two 1024-byte blocks per instruction).
+namespace qexxc {
+namespace tc05 {
+
+__device__ __host__ __forceinline__ uint32_t plane16_off(int r, int c) {  // byte offset of element (r, c), c < 64
+    return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
+}
+__device__ __host__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major: one instruction consumes 16 columns (32 bytes); kstep = 0..3 for a 64-column plane
+__device__ __forceinline__ uint64_t desc16_k(uint32_t plane_saddr, int kstep) {
+    return smem_desc(plane_saddr + (uint32_t)kstep * 32u, 16, 1024);
+}
+// MN-major: one instruction consumes 16 rows (2048 bytes); the next 64 M/N elements are the next plane (stride R*128)
+__device__ __forceinline__ uint64_t desc16_mn(uint32_t plane_saddr, int R, int kstep) {
+    return smem_desc(plane_saddr + (uint32_t)kstep * 2048u, (uint32_t)R * 128u, 1024);
+}
+// x = b1 + b2 + b3 (+ O(2^-24 x)), each part exactly representable in bf16 (truncation splits are exact)
+__device__ __forceinline__ void split_bf16x3(float x, uint32_t& b1, uint32_t& b2, uint32_t& b3) {
+    b1 = __float_as_uint(x) & 0xFFFF0000u;
+    const float r1 = x - __uint_as_float(b1);
+    b2 = __float_as_uint(r1) & 0xFFFF0000u;
+    const float r2 = r1 - __uint_as_float(b2);
+    b3 = __float_as_uint(r2) & 0xFFFF0000u;
+}
+// pack the high halves of two such words: lo 16 bits <- a, hi 16 bits <- b
+__device__ __forceinline__ uint32_t pack_hi16(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
+
+}  // namespace tc05
+}  // namespace qexxc

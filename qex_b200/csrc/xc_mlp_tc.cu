@@ -7,16 +7,19 @@
 //   * a CTA owns 128 grid points per iteration: thread (quadrant q = warp & 3, column chunk cc = warp >> 2) owns
 //     point 32 q + lane and neurons [16 cc, 16 cc + 16) of EVERY stream of that point (value, tangent(s)), so the
 //     activation epilogue finds z and z-dot in the same thread;
-//   * every hidden Dense layer is a tcgen05.mma (kind::tf32, M = 128 points, N = 64, K = 64) per stream, issued by
-//     one thread, operands in 128-byte-swizzled shared-memory planes (csrc/tc05.cuh), accumulators in tensor
-//     memory, read back with tcgen05.ld (32 lanes x 16 columns per warp);
-//   * FP32 accuracy on the TF32 pipe comes from the 3xTF32 split  a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
-//     (a_hi, w_hi exact in TF32): relative error ~2^-21 per product, i.e. FP32-grade; accumulation is FP32 in TMEM;
+//   * every hidden Dense layer is a tcgen05.mma (kind::f16 on bf16 operands, M = 128 points, N = 64, K = 64) per
+//     stream, issued by one thread, operands in 128-byte-swizzled shared-memory planes (csrc/tc05.cuh), FP32
+//     accumulators in tensor memory, read back with tcgen05.ld (32 lanes x 16 columns per warp);
+//   * FP32 accuracy on the bf16 pipe comes from the exact three-way split x = x1 + x2 + x3 (each part a bf16) and
+//     the six products x1 w1 + x1 w2 + x2 w1 + x2 w2 + x1 w3 + x3 w1, smallest first: measured 1.6e-7 relative on
+//     K = 64 (scripts/probe/tc_probe16.cu), i.e. FP32-grade.  (3xTF32 costs the same tensor time but MN-major
+//     TF32 operands need a different swizzle, so one plane could not serve two views; bf16 planes can);
 //   * the first Dense (1 or 2 inputs) and the last (1 output) are CUDA-core work inside the epilogue.
 //
-// The reverse kernel keeps the same ownership; its three products per hidden layer -- back-propagation
-// [z_bar] W^T, and the weight gradient H^T [z_bar] -- read the SAME planes once as a K-major and once as an MN-major
-// operand, and the weight gradients accumulate in tensor memory over all the tiles of the persistent CTA.
+// The reverse kernel keeps the same ownership; its products per hidden layer -- back-propagation [z_bar] W^T and the
+// weight gradient H^T [z_bar] -- read the SAME planes once as a K-major and once as an MN-major operand, and the
+// weight gradients accumulate in tensor memory over all the tiles of the persistent CTA (the tangent-stream half of
+// the weight gradient runs on the tensor cores while the threads already work on the next layer's epilogue).
 #include "common.cuh"
 #include "tc05.cuh"
 #include "xc_act.cuh"
@@ -29,8 +32,10 @@ constexpr int TC_THREADS = 512;
 constexpr int TP = 128;  // points per tile
 constexpr int HP = 64;   // padded hidden width
 constexpr int CW = 16;   // neurons per thread
-constexpr uint32_t PLANE = TP * HP * 4;   // one [128 x 64] float plane: 32 KB
-constexpr uint32_t WPLANE = HP * HP * 4;  // one [64 x 64] weight plane: 16 KB
+constexpr uint32_t PL = TP * HP * 2;    // one [128 x 64] bf16 plane: 16 KB
+constexpr uint32_t MAT = 3 * PL;       // a matrix = three planes (bf16x3 split): 48 KB
+constexpr uint32_t WPL = HP * HP * 2;  // one [64 x 64] bf16 weight plane: 8 KB
+constexpr uint32_t WMAT = 3 * WPL;
 constexpr int MAXL_TC = 3;
 
 struct TcParams {
@@ -81,9 +86,10 @@ __device__ __forceinline__ void act3(int act, float z, float& s0, float& s1, flo
 }
 
 struct TcSmem {
-    unsigned char* X;   // value-stream planes: hi [128 x 64], lo
-    unsigned char* Y;   // tangent-stream planes
-    unsigned char* W;   // hidden Dense l = 1..L-1: hi [64 in x 64 out], lo
+    unsigned char* X;   // matrix region 0 (value stream)
+    unsigned char* Y;   // matrix region 1 (tangent stream / previous-layer activations)
+    unsigned char* Z;   // matrix region 2 (second tangent stream / zdot_bar)
+    unsigned char* W;   // hidden Dense l = 1..L-1: three planes [64 in x 64 out]
     float* W1;          // [2][64]
     float* bias;        // [L][64]
     float* wl;          // [64]
@@ -93,7 +99,7 @@ struct TcSmem {
     uint32_t* tslot;
 };
 __host__ __device__ inline size_t tc_smem_bytes(int L, bool vjp) {
-    size_t n = 2 * 2 * (size_t)PLANE + (size_t)(L - 1) * 2 * WPLANE;
+    size_t n = 3 * (size_t)MAT + (size_t)(L - 1) * WMAT;
     n += (2 * HP + (size_t)L * HP + HP + 4 * TP * 4) * 4;
     if (vjp) n += (size_t)16 * 8 * 16 * 4;
     n += 16;
@@ -103,9 +109,10 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* raw, int L, bool vjp) 
     TcSmem s;
     unsigned char* b = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     s.X = b;
-    s.Y = b + 2 * PLANE;
-    s.W = b + 4 * PLANE;
-    float* f = (float*)(s.W + (size_t)(L - 1) * 2 * WPLANE);
+    s.Y = b + MAT;
+    s.Z = b + 2 * MAT;
+    s.W = b + 3 * MAT;
+    float* f = (float*)(s.W + (size_t)(L - 1) * WMAT);
     s.W1 = f; f += 2 * HP;
     s.bias = f; f += (size_t)L * HP;
     s.wl = f; f += HP;
@@ -126,15 +133,16 @@ __device__ void tc_load_weights(const TcParams& p, const TcSmem& s) {
     }
     for (int l = 1; l < L; ++l) {
         const long off = th_off(F, H, l);
-        unsigned char* Whi = s.W + (size_t)(l - 1) * 2 * WPLANE;
+        unsigned char* Wb = s.W + (size_t)(l - 1) * WMAT;
         for (int i = threadIdx.x; i < HP * HP; i += blockDim.x) {
             const int r = i / HP, c = i % HP;
             const float v = (r < H && c < H) ? (float)th[off + (long)r * H + c] : 0.0f;
-            float hi, lo;
-            split_tf32(v, hi, lo);
-            const uint32_t o = plane_off(r, c, HP);
-            *(float*)(Whi + o) = hi;
-            *(float*)(Whi + WPLANE + o) = lo;
+            uint32_t b1, b2, b3;
+            split_bf16x3(v, b1, b2, b3);
+            const uint32_t o = plane16_off(r, c);
+            *(unsigned short*)(Wb + o) = (unsigned short)(b1 >> 16);
+            *(unsigned short*)(Wb + WPL + o) = (unsigned short)(b2 >> 16);
+            *(unsigned short*)(Wb + 2 * WPL + o) = (unsigned short)(b3 >> 16);
         }
     }
     const long offl = th_off(F, H, L);
@@ -145,50 +153,64 @@ __device__ void tc_load_weights(const TcParams& p, const TcSmem& s) {
     }
 }
 
-// thread (row r, columns [j0, j0+16)) writes its 16 values, split hi/lo, into the two planes at `P`
+// thread (row r, columns [j0, j0+16)) writes its 16 values, split three ways, into the three planes of matrix `P`
 __device__ __forceinline__ void store_planes(unsigned char* P, int r, int j0, const float (&v)[CW]) {
-    const uint32_t rowb = (uint32_t)(j0 >> 5) * (TP * 128u) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    const int ch0 = (j0 & 31) >> 2;
+    const uint32_t rowb = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+    const int ch0 = j0 >> 3;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float4 hi, lo;
-        split_tf32(v[4 * i + 0], hi.x, lo.x);
-        split_tf32(v[4 * i + 1], hi.y, lo.y);
-        split_tf32(v[4 * i + 2], hi.z, lo.z);
-        split_tf32(v[4 * i + 3], hi.w, lo.w);
+    for (int i = 0; i < 2; ++i) {
+        uint32_t w1[4], w2[4], w3[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            uint32_t a1, a2, a3, c1, c2, c3;
+            split_bf16x3(v[8 * i + 2 * e], a1, a2, a3);
+            split_bf16x3(v[8 * i + 2 * e + 1], c1, c2, c3);
+            w1[e] = pack_hi16(a1, c1);
+            w2[e] = pack_hi16(a2, c2);
+            w3[e] = pack_hi16(a3, c3);
+        }
         const uint32_t o = rowb + (uint32_t)(((ch0 + i) ^ (r & 7)) << 4);
-        *(float4*)(P + o) = hi;
-        *(float4*)(P + PLANE + o) = lo;
+        *(uint4*)(P + o) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+        *(uint4*)(P + PL + o) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+        *(uint4*)(P + 2 * PL + o) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
     }
 }
 
-// D[128 x 64] (tmem) = A (planes at sA: hi, lo) x W_l (planes at sW: hi, lo; [in][out] => MN-major B), 3xTF32
+// the six products of the bf16x3 split, smallest first: (part of A, part of B)
+__device__ __constant__ int kPa[6] = {2, 0, 1, 1, 0, 0};
+__device__ __constant__ int kPb[6] = {0, 2, 1, 0, 1, 0};
+
+// D[128 x 64] (tmem) = A (matrix at sA) x W_l (matrix at sW, stored [in][out] => MN-major B)
 __device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t sA, uint32_t sW) {
-    constexpr uint32_t id = idesc_tf32(TP, HP, 0, 1);
+    constexpr uint32_t id = idesc_bf16(TP, HP, 0, 1);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mma_tf32(d, desc_kmajor(sA, TP, k), desc_mnmajor(sW, HP, k), id, k > 0);
+    for (int t = 0; t < 6; ++t)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mma_tf32(d, desc_kmajor(sA + PLANE, TP, k), desc_mnmajor(sW, HP, k), id, 1);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) mma_tf32(d, desc_kmajor(sA, TP, k), desc_mnmajor(sW + WPLANE, HP, k), id, 1);
+        for (int k = 0; k < 4; ++k)
+            mma_bf16(d, desc16_k(sA + kPa[t] * PL, k), desc16_mn(sW + kPb[t] * WPL, HP, k), id, (t | k) != 0);
 }
 // D[128 x 64] = A x W_l^T  (B[n = in][k = out] = W[in][out] => K-major B)
 __device__ __forceinline__ void issue_bwd(uint32_t d, uint32_t sA, uint32_t sW) {
-    constexpr uint32_t id = idesc_tf32(TP, HP, 0, 0);
+    constexpr uint32_t id = idesc_bf16(TP, HP, 0, 0);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mma_tf32(d, desc_kmajor(sA, TP, k), desc_kmajor(sW, HP, k), id, k > 0);
+    for (int t = 0; t < 6; ++t)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mma_tf32(d, desc_kmajor(sA + PLANE, TP, k), desc_kmajor(sW, HP, k), id, 1);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) mma_tf32(d, desc_kmajor(sA, TP, k), desc_kmajor(sW + WPLANE, HP, k), id, 1);
+        for (int k = 0; k < 4; ++k)
+            mma_bf16(d, desc16_k(sA + kPa[t] * PL, k), desc16_k(sW + kPb[t] * WPL, k), id, (t | k) != 0);
 }
-// D[128 x 64] (+)= [Y_hi | Y_lo]^T x (X_hi + X_lo): rows 0..63 = Y_hi^T X, rows 64..127 = Y_lo^T X (K = 128 points)
-__device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t sY, uint32_t sX, uint32_t accumulate) {
-    constexpr uint32_t id = idesc_tf32(TP, HP, 1, 1);
+// weight gradient Y^T X over the 128 points of the tile (both operands MN-major):
+//   main accumulator (M = 128 spans planes 1|2 of Y): rows 0..63 += Y1^T (X1+X2+X3), rows 64..127 += Y2^T (X1+X2+X3)
+//   aux accumulator (M = 64): += Y3^T X1            -- together (Y1+Y2+Y3)^T (X1+X2+X3) up to O(2^-24) terms
+__device__ __forceinline__ void issue_wgrad(uint32_t dmain, uint32_t daux, uint32_t sY, uint32_t sX, uint32_t accumulate) {
+    constexpr uint32_t id = idesc_bf16(TP, HP, 1, 1), id64 = idesc_bf16(64, HP, 1, 1);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) mma_tf32(d, desc_mnmajor(sY, TP, k), desc_mnmajor(sX, TP, k), id, (k > 0) | accumulate);
+    for (int pb = 2; pb >= 0; --pb)
 #pragma unroll
-    for (int k = 0; k < 16; ++k) mma_tf32(d, desc_mnmajor(sY, TP, k), desc_mnmajor(sX + PLANE, TP, k), id, 1);
+        for (int k = 0; k < 8; ++k)
+            mma_bf16(dmain, desc16_mn(sY, TP, k), desc16_mn(sX + pb * PL, TP, k), id, accumulate | (uint32_t)(pb != 2 || k != 0));
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        mma_bf16(daux, desc16_mn(sY + 2 * PL, TP, k), desc16_mn(sX, TP, k), id64, accumulate | (uint32_t)(k != 0));
 }
 
 __device__ __forceinline__ void tc_block_to_bg(const TcParams& p, int blk, int& b, long& g0) {
@@ -238,7 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const TcParam
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = *s.tslot;
-    const uint32_t sX = smem_u32(s.X), sY = smem_u32(s.Y), sW = smem_u32(s.W);
+    const uint32_t sX = smem_u32(s.X), sY = smem_u32(s.Y), sZ = smem_u32(s.Z), sW = smem_u32(s.W);
     uint32_t phase = 0;
 
     for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
@@ -263,9 +285,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const TcParam
         }
         // ---- hidden Dense layers on the tensor cores ----
         for (int l = 1; l < L; ++l) {
-            const uint32_t sWl = sW + (uint32_t)(l - 1) * 2 * WPLANE;
+            const uint32_t sWl = sW + (uint32_t)(l - 1) * WMAT;
             store_planes(s.X, pt, j0, h);
             store_planes(s.Y, pt, j0, hd[0]);
+            if (NT == 2) store_planes(s.Z, pt, j0, hd[NT - 1]);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -273,20 +296,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const TcParam
                 tc_fence_after();
                 issue_fwd(tm, sX, sWl);
                 issue_fwd(tm + HP, sY, sWl);
+                if (NT == 2) issue_fwd(tm + 2 * HP, sZ, sWl);
                 mma_commit(s.bar);
-            }
-            if (NT == 2) {
-                mbar_wait(s.bar, phase);
-                phase ^= 1;
-                store_planes(s.Y, pt, j0, hd[NT - 1]);
-                fence_async_smem();
-                tc_fence_before();
-                __syncthreads();
-                if (tid == 0) {
-                    tc_fence_after();
-                    issue_fwd(tm + 2 * HP, sY, sWl);
-                    mma_commit(s.bar);
-                }
             }
             mbar_wait(s.bar, phase);
             phase ^= 1;
@@ -418,13 +429,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_vjp_kernel(const TcParam
         mbar_init(s.bar, 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(s.tslot, 256);
+    if (warp == 0) tmem_alloc(s.tslot, 512);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = *s.tslot;
-    const uint32_t sX = smem_u32(s.X), sY = smem_u32(s.Y), sW = smem_u32(s.W);
+    const uint32_t sX = smem_u32(s.X), sY = smem_u32(s.Y), sZ = smem_u32(s.Z), sW = smem_u32(s.W);
     const float bl = (float)p.theta[th_off(F, H, L) + H];
     uint32_t phase = 0;
     // per-thread gradient accumulators: lane pair (2i, 2i+1) carries neuron j0 + i
@@ -432,6 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_vjp_kernel(const TcParam
 #pragma unroll
     for (int l = 0; l < MAXL_TC; ++l) bacc[l] = 0.0f;
     uint32_t wg_started = 0;  // bit l: the tensor-memory accumulator of Dense l has been written once
+    bool pending = false;     // a committed MMA batch (tangent half of a weight gradient) has not been waited for yet
 
     for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
         int b;
@@ -466,7 +478,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_vjp_kernel(const TcParam
             tape_put(tape, 0, cc, pt, ta, tz);
         }
         for (int l = 1; l < L; ++l) {
-            const uint32_t sWl = sW + (uint32_t)(l - 1) * 2 * WPLANE;
+            const uint32_t sWl = sW + (uint32_t)(l - 1) * WMAT;
+            if (pending) {  // the previous tile's last weight-gradient batch still reads Y and Z
+                mbar_wait(s.bar, phase);
+                phase ^= 1;
+                pending = false;
+            }
             store_planes(s.X, pt, j0, h);
             store_planes(s.Y, pt, j0, hd);
             fence_async_smem();
@@ -563,8 +580,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_vjp_kernel(const TcParam
             for (int k = 0; k < MAXL_TC; ++k)
                 if (k == l) bacc[k] += bsum;
             if (l > 0) {
-                const uint32_t sWl = sW + (uint32_t)(l - 1) * 2 * WPLANE;
-                const uint32_t wg = tm + 2 * HP + (uint32_t)(l - 1) * HP;
+                const uint32_t sWl = sW + (uint32_t)(l - 1) * WMAT;
+                const uint32_t wg = tm + 2 * HP + (uint32_t)(l - 1) * 2 * HP;  // main | aux accumulators
                 float a0[CW], a1[CW];
                 {
                     float ta[CW], tz[CW];
@@ -582,8 +599,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_vjp_kernel(const TcParam
                         a1[j] = s1 * tz[j];
                     }
                 }
-                // round a: value stream
+                // round a: both back-propagation products and the value half of the weight gradient
+                if (pending) {
+                    mbar_wait(s.bar, phase);
+                    phase ^= 1;
+                    pending = false;
+                }
                 store_planes(s.X, pt, j0, zb);
+                store_planes(s.Z, pt, j0, zdb);
                 store_planes(s.Y, pt, j0, a0);
                 fence_async_smem();
                 tc_fence_before();
@@ -591,26 +614,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_vjp_kernel(const TcParam
                 if (tid == 0) {
                     tc_fence_after();
                     issue_bwd(tm, sX, sWl);
-                    issue_wgrad(wg, sY, sX, (wg_started >> l) & 1u);
+                    issue_bwd(tm + HP, sZ, sWl);
+                    issue_wgrad(wg, wg + HP, sY, sX, (wg_started >> l) & 1u);
                     mma_commit(s.bar);
                 }
                 wg_started |= 1u << l;
                 mbar_wait(s.bar, phase);
                 phase ^= 1;
-                // round b: tangent stream
-                store_planes(s.X, pt, j0, zdb);
+                // round b: the tangent half of the weight gradient; it runs while the threads go on
                 store_planes(s.Y, pt, j0, a1);
                 fence_async_smem();
                 tc_fence_before();
                 __syncthreads();
                 if (tid == 0) {
                     tc_fence_after();
-                    issue_bwd(tm + HP, sX, sWl);
-                    issue_wgrad(wg, sY, sX, 1u);
+                    issue_wgrad(wg, wg + HP, sY, sZ, 1u);
                     mma_commit(s.bar);
                 }
-                mbar_wait(s.bar, phase);
-                phase ^= 1;
+                pending = true;
                 __syncwarp();
                 tc_fence_after();
                 tmem_ld16(tmem_addr(tm, 32 * q, j0), hb);
@@ -659,6 +680,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_vjp_kernel(const TcParam
     }
     // ---------------- per-CTA theta_bar partial ----------------
     double* out = p.theta_part + (size_t)blockIdx.x * p.n_theta;
+    if (pending) {
+        mbar_wait(s.bar, phase);
+        phase ^= 1;
+        pending = false;
+    }
+    __syncwarp();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -671,19 +698,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_vjp_kernel(const TcParam
         r[5 * 16] = w1acc[1];
         if (lane == 0) r[6 * 16] = blacc;
     }
-    // hidden weight gradients: tensor memory rows i (from the hi planes) + 64 + i (from the lo planes)
-    float* stage = (float*)s.X;  // [128][64] plain floats; the planes are free now
+    // hidden weight gradients: main accumulator rows i (Y1 part) and 64 + i (Y2 part), aux accumulator (M = 64 MMA:
+    // row i lives in lane 32 (i / 16) + i % 16) for the Y3 part
+    float* stage = (float*)s.X;            // [128][64] floats (32 KB); the planes are free now
+    float* stage2 = stage + TP * HP;       // [64][64] floats (16 KB)
     for (int l = 1; l < L; ++l) {
-        float v[CW];
-        tmem_ld16(tmem_addr(tm, 32 * q, 2 * HP + (l - 1) * HP + j0), v);
+        float v[CW], u[CW];
+        tmem_ld16(tmem_addr(tm, 32 * q, 2 * HP + (l - 1) * 2 * HP + j0), v);
+        tmem_ld16(tmem_addr(tm, 32 * q, 2 * HP + (l - 1) * 2 * HP + HP + j0), u);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < CW; ++j) stage[(size_t)pt * HP + j0 + j] = v[j];
+        if (lane < 16) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) stage2[(size_t)(16 * q + lane) * HP + j0 + j] = u[j];
+        }
         __syncthreads();
         const long off = th_off(F, H, l);
         for (int i = tid; i < HP * HP; i += TC_THREADS) {
             const int r = i / HP, c = i % HP;
-            if (r < H && c < H) out[off + (long)r * H + c] = (double)(stage[i] + stage[HP * HP + i]);
+            if (r < H && c < H) out[off + (long)r * H + c] = (double)((stage[i] + stage[HP * HP + i]) + stage2[i]);
         }
         __syncthreads();
     }
@@ -710,7 +744,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_vjp_kernel(const TcParam
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_free(tm, 256);
+    if (warp == 0) tmem_free(tm, 512);
 }
 
 int tc_supported(const qexxc_net_desc& net) {

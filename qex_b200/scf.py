@@ -419,3 +419,101 @@ def scf_loop_batched(xc, theta, dm, eri, s1e, h1e, energy_nuc, nelectron, xctype
         e_tot = energy(dm, J, exc_e)
         energies.append(e_tot)
     return e_tot, dm, torch.stack(energies)
+
+
+# ---------------------------------------------------------------- padded / masked batches (row N1, second half)
+# Mixed-size batches (different nao and grid sizes per molecule) run through the same fixed-shape kernels once every
+# molecule is padded to the batch maximum: zero rows/columns in dm, h1e, s1e and eri, zero AO columns for padded
+# orbitals, zero weights (and zero AO rows) for padded grid points.  With that padding stages 2-4 and the J kernel need
+# no mask at all (padded entries contribute exact zeros); the mask matters in the eigensolver, the occupations and the
+# density-matrix build.  Mirrors scf_functions_masked.py:244-309,546-588,917-967 and
+# generalized_eigensolver_masked.py:19-89.  The reference's "stable" get_veff pads with eps = 1e-12 instead of 0 and
+# adds eps to rho (scf_functions_masked.py:567-579); that perturbs energies at the 1e-11 Ha level and is not reproduced.
+def pad_stack(mats, n: int | None = None):
+    """List of square [N_b, N_b] (or [N_b]^4) tensors -> zero-padded stack [B, n, n(, n, n)] and mask [B, n]."""
+    n = n or max(int(m.shape[0]) for m in mats)
+    out = torch.zeros((len(mats),) + (n,) * mats[0].dim(), dtype=mats[0].dtype, device=mats[0].device)
+    mask = torch.zeros(len(mats), n, dtype=torch.bool, device=mats[0].device)
+    for b, m in enumerate(mats):
+        k = int(m.shape[0])
+        out[(b,) + (slice(0, k),) * m.dim()] = m
+        mask[b, :k] = True
+    return out, mask
+
+
+def masked_generalized_eigh(fock, s1e, mask, eps: float = 1.0e-12):
+    """`masked_generalized_eigh` (generalized_eigensolver_masked.py:19-89) for [..., N, N] stacks: padded block of the
+    Fock matrix zeroed with 1e-12 on its diagonal, padded diagonal of the overlap set to 1e-12, degenerate-safe
+    generalised eigensolver, real eigenpairs first in ascending order (the reference keys the sort on the mask by
+    POSITION, reproduced here), padded eigenvalues and coefficient rows/columns zeroed."""
+    single = fock.dim() == 2
+    if single:
+        fock, s1e, mask = fock[None], s1e[None], mask[None]
+    n = fock.shape[-1]
+    m2 = mask[:, :, None] & mask[:, None, :]
+    eye = torch.eye(n, dtype=torch.bool, device=fock.device)
+    pad_diag = torch.where((~mask)[:, :, None] & eye, torch.full_like(fock, 1e-12), torch.zeros_like(fock))
+    f = torch.where(m2, fock, torch.zeros_like(fock)) + pad_diag
+    s = torch.where(m2, s1e, pad_diag)
+    w, v = generalized_eigh_batched(f, s, eps)
+    key = torch.where(mask, w, torch.full_like(w, 1e12))
+    idx = torch.argsort(key, dim=-1, stable=True)
+    w = torch.gather(w, -1, idx) * torch.gather(mask, -1, idx).to(w.dtype)
+    v = torch.gather(v, -1, idx[:, None, :].expand_as(v))
+    keep = mask[:, :, None] & torch.gather(mask, -1, idx)[:, None, :]
+    v = torch.where(keep, v, torch.zeros_like(v))
+    return (w[0], v[0]) if single else (w, v)
+
+
+def get_occ_masked(nelectron, mo_energy, mask):
+    """`get_occ_masked` (scf_functions_masked.py:269-288); `nelectron` may be an int or a per-molecule tensor [B]."""
+    e = torch.where(mask, mo_energy, torch.full_like(mo_energy, 1e10))
+    e_idx = torch.argsort(e, dim=-1, stable=True)
+    nocc = torch.as_tensor(nelectron, device=mo_energy.device) // 2
+    idx = torch.arange(mo_energy.shape[-1], device=mo_energy.device)
+    occ_sorted = torch.where((idx < nocc[..., None]) & torch.gather(mask, -1, e_idx), 2.0, 0.0).to(mo_energy.dtype)
+    return torch.gather(occ_sorted, -1, torch.argsort(e_idx, dim=-1))
+
+
+def make_rdm1_masked(mo_coeff, mo_occ, mask):
+    """`make_rdm1_masked` (scf_functions_masked.py:524-541)."""
+    c = torch.where(mask[..., :, None], mo_coeff, torch.zeros_like(mo_coeff))
+    occ = torch.where(mask, mo_occ, torch.zeros_like(mo_occ))
+    dm = (c * occ.unsqueeze(-2)) @ c.transpose(-1, -2)
+    return torch.where(mask[..., :, None] & mask[..., None, :], dm, torch.zeros_like(dm))
+
+
+def get_veff_masked(xc, dm, eri, theta, mask, xctype: str = "NN"):
+    """`get_veff_jax_masked`: J + V_xc, E_xc, J on zero-padded inputs (the XCContext holds the padded AO values and
+    weights); outputs masked again as the reference does."""
+    m2 = (mask[..., :, None] & mask[..., None, :]).to(dm.dtype)
+    vhf, excsum, J = get_veff_batched(xc, dm * m2, eri, theta, xctype)
+    return vhf * m2, excsum, J * m2
+
+
+def energy_tot_masked(dm, h1e, J, exc_energy, energy_nuc, mask):
+    """`energy_tot_jax_masked` (scf_functions_masked.py:244-265), batched."""
+    m2 = (mask[..., :, None] & mask[..., None, :]).to(dm.dtype)
+    dm, h1e, J = dm * m2, h1e * m2, J * m2
+    return (dm * h1e.transpose(-1, -2)).sum((-1, -2)) + 0.5 * (dm * J).sum((-1, -2)) + exc_energy + energy_nuc
+
+
+def scf_loop_padded(xc, theta, dm, eri, s1e, h1e, energy_nuc, nelectron, mask, xctype="NN", max_cycle=15,
+                    diis_max_vec=15, diis_min_vec=2, diis_start_cycle=1):
+    """`_scf_test_padded` (scf_functions_masked.py:917-967) for a batch of molecules of DIFFERENT sizes padded to a
+    common [B, N, N] (see `pad_stack`); nelectron: int or [B].  -> (e_tot [B], dm [B, N, N], energies [cycles, B])."""
+    vhf, exc_e, J = get_veff_masked(xc, dm, eri, theta, mask, xctype)
+    e_tot = energy_tot_masked(dm, h1e, J, exc_e, energy_nuc, mask)
+    ev, fv, energies = [], [], []
+    for cycle in range(max_cycle):
+        fock = h1e + vhf
+        if cycle >= diis_start_cycle:
+            ev = (ev + [get_diis_error(fock, dm, s1e).reshape(fock.shape[0], -1)])[-diis_max_vec:]
+            fv = (fv + [fock.reshape(fock.shape[0], -1)])[-diis_max_vec:]
+            fock = _diis_batched(ev, fv, fock.shape, diis_min_vec)
+        mo_energy, mo_coeff = masked_generalized_eigh(fock, s1e, mask)
+        dm = make_rdm1_masked(mo_coeff, get_occ_masked(nelectron, mo_energy, mask), mask)
+        vhf, exc_e, J = get_veff_masked(xc, dm, eri, theta, mask, xctype)
+        e_tot = energy_tot_masked(dm, h1e, J, exc_e, energy_nuc, mask)
+        energies.append(e_tot)
+    return e_tot, dm, torch.stack(energies)
