@@ -43,7 +43,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "XC grid-integration grid-pts/s (fwd+VJP)"
 UNIT = "grid-pts/s"
-SUB_CONFIGS = ("c1", "c2", "c3", "c4", "c5gga", "c5_f32")
+SUB_CONFIGS = ("c1", "c2", "c3", "c4", "c5gga", "c5_f32", "c3_f32", "c4_f32", "c5w512")
 
 
 def _args():
@@ -585,10 +585,10 @@ def run_ours(args):
     if not args.no_configs and args.ngrids is None and args.config == "c5":
         todo = SUB_CONFIGS if world == 1 else ("c4",)
         for name in todo:
-            cfg, prec = ("c5", "f32") if name == "c5_f32" else (name, "f64")
+            cfg, prec = (name[:-4], "f32") if name.endswith("_f32") else (name, "f64")
             try:
                 r, ex2 = measure(env, args, cfg, prec, args.steps, args.warmup, False, peak_sus,
-                                 0.0 if name == "c5_f32" else min(4.0, args.cpu_seconds))
+                                 0.0 if (name.endswith("_f32") or name == "c5w512") else min(4.0, args.cpu_seconds))
                 ex2["ctx"].close()
                 del ex2
                 torch.cuda.empty_cache()

@@ -154,7 +154,7 @@ __device__ const double kExp2Tab[64] = {
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
 };
 
-// exp(x) for x <= 0; returns 0 below -700 (the true value is < 1e-304)
+// exp(x) for x <= 0; arguments below -700 are clamped (returns ~1e-304 where the true value is smaller still)
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ T) {
     const double L = 92.33248261689366, C1 = 0x1.62e42fe000000p-7, C2 = 0x1.f473de6af278fp-36;
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of x*L + MAGIC is round(x*L)
@@ -170,8 +170,7 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ T
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     const double y = T[k & 63] * p;
-    const double sc = __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));
-    return x < -700.0 ? 0.0 : sc;
+    return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));
 }
 
 template <int L>
@@ -191,46 +190,95 @@ __device__ __forceinline__ void fill_harm(double* __restrict__ H, int stride, in
 // rows of the harmonic table for NH = (lmax+1)^2 harmonics
 __host__ __device__ inline int ao_tab_rows(int NH, bool deriv) { return deriv ? 4 * NH + 4 : NH + 1; }
 
-template <bool DERIV, int Q>
-__device__ __forceinline__ void radial_items(const ShellDev* __restrict__ shells, const int* __restrict__ shell_atom,
+// radial sums of one shell for every point of the CTA: the shell's primitives (exponent, coefficient) sit in
+// registers (fast path: one contraction, <= 4 primitives -- every standard split-valence / polarisation shell), the
+// points go four at a time so four exp chains are in flight
+template <bool DERIV>
+__device__ __forceinline__ void radial_phase(const ShellDev* __restrict__ shells, const int* __restrict__ shell_atom,
                                              const double* __restrict__ envb, const double* __restrict__ Hs,
                                              double* __restrict__ Rs, const double* __restrict__ T, int hstr, int NH,
                                              int nshell, int natm, int nrad, int P, long g0, int G) {
     constexpr int RS = DERIV ? 2 : 1;
-    const int nq = (P + Q - 1) / Q;
-    for (int it = threadIdx.x; it < nshell * nq; it += blockDim.x) {
-        const int pq = it / nshell, s = it - pq * nshell;
+    constexpr int Q = 4;
+    const double* rrow = Hs + NH * hstr;
+    // an item = one shell x `ppi` points: all P points when there are enough shells to occupy the CTA (the shell's
+    // primitives are loaded once), one quad of points otherwise (small molecules: more items than threads matter more)
+    const int ppi = (2 * nshell >= (int)blockDim.x) ? P : Q;
+    const int ngrp = (P + ppi - 1) / ppi;
+    for (int it = threadIdx.x; it < nshell * ngrp; it += blockDim.x) {
+        const int grp = it / nshell, s = it - grp * nshell;
+        const int pbeg = grp * ppi, pend = min(P, pbeg + ppi);
         const ShellDev sh = shells[s];
         const int ia = shell_atom[s];
         const double* ex = envb + sh.ptr_exp;
-        double rr[Q];
+        if (sh.nctr == 1 && sh.nprim <= 4) {
+            const double* cf = envb + sh.ptr_coef;
+            double a[4], c[4];
 #pragma unroll
-        for (int h = 0; h < Q; ++h) {
-            const int p = min(pq * Q + h, P - 1);
-            rr[h] = Hs[NH * hstr + p * natm + ia];
-        }
-        for (int ic = 0; ic < sh.nctr; ++ic) {
-            const double* cf = envb + sh.ptr_coef + ic * sh.nprim;
-            double R0[Q], R1[Q];
-#pragma unroll
-            for (int h = 0; h < Q; ++h) R0[h] = R1[h] = 0.0;
-            for (int q = 0; q < sh.nprim; ++q) {
-                const double a = ex[q], cq = cf[q];
+            for (int q = 0; q < 4; ++q) {
+                const bool in = q < sh.nprim;
+                a[q] = in ? ex[q] : 0.0;
+                c[q] = in ? cf[q] : 0.0;
+            }
+            double* R = Rs + (size_t)sh.rad_off * RS;
+            for (int p0 = pbeg; p0 < pend; p0 += Q) {
+                double rr[Q], R0[Q], R1[Q];
 #pragma unroll
                 for (int h = 0; h < Q; ++h) {
-                    const double e = cq * exp_neg(-a * rr[h], T);
-                    R0[h] += e;
-                    if (DERIV) R1[h] -= 2.0 * a * e;
+                    rr[h] = rrow[min(p0 + h, P - 1) * natm + ia];
+                    R0[h] = R1[h] = 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < sh.nprim) {
+#pragma unroll
+                        for (int h = 0; h < Q; ++h) {
+                            const double e = c[q] * exp_neg(-a[q] * rr[h], T);
+                            R0[h] += e;
+                            if (DERIV) R1[h] = fma(-2.0 * a[q], e, R1[h]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < Q; ++h) {
+                    const int p = p0 + h;
+                    if (p < P) {
+                        const bool live = g0 + p < G;  // padding rows come out exactly zero
+                        R[(size_t)p * nrad * RS] = live ? R0[h] : 0.0;
+                        if (DERIV) R[(size_t)p * nrad * RS + 1] = live ? R1[h] : 0.0;
+                    }
                 }
             }
+            continue;
+        }
+        // general shells: several contractions and/or many primitives
+        for (int p0 = pbeg; p0 < pend; p0 += Q) {
+            double rr[Q];
 #pragma unroll
-            for (int h = 0; h < Q; ++h) {
-                const int p = pq * Q + h;
-                if (p < P) {
-                    const bool live = g0 + p < G;  // padding rows come out exactly zero
-                    double* R = Rs + ((size_t)p * nrad + sh.rad_off + ic) * RS;
-                    R[0] = live ? R0[h] : 0.0;
-                    if (DERIV) R[1] = live ? R1[h] : 0.0;
+            for (int h = 0; h < Q; ++h) rr[h] = rrow[min(p0 + h, P - 1) * natm + ia];
+            for (int ic = 0; ic < sh.nctr; ++ic) {
+                const double* cf = envb + sh.ptr_coef + ic * sh.nprim;
+                double R0[Q], R1[Q];
+#pragma unroll
+                for (int h = 0; h < Q; ++h) R0[h] = R1[h] = 0.0;
+                for (int q = 0; q < sh.nprim; ++q) {
+                    const double aq = ex[q], cq = cf[q];
+#pragma unroll
+                    for (int h = 0; h < Q; ++h) {
+                        const double e = cq * exp_neg(-aq * rr[h], T);
+                        R0[h] += e;
+                        if (DERIV) R1[h] -= 2.0 * aq * e;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < Q; ++h) {
+                    const int p = p0 + h;
+                    if (p < P) {
+                        const bool live = g0 + p < G;
+                        double* R = Rs + ((size_t)p * nrad + sh.rad_off + ic) * RS;
+                        R[0] = live ? R0[h] : 0.0;
+                        if (DERIV) R[1] = live ? R1[h] : 0.0;
+                    }
                 }
             }
         }
@@ -286,8 +334,8 @@ eval_ao_tiled_kernel(const double* __restrict__ coords, const ShellDev* __restri
         }
     }
     __syncthreads();
-    // ---- phase A2: radial sums; an item = one shell x four points (shell data loaded once, four exp chains) ----
-    radial_items<DERIV, 4>(shells, shell_atom, envb, Hs, Rs, T, hstr, NH, nshell, natm, nrad, P, g0, G);
+    // ---- phase A2: radial sums; a thread = one shell, all P points, four exp chains in flight ----
+    radial_phase<DERIV>(shells, shell_atom, envb, Hs, Rs, T, hstr, NH, nshell, natm, nrad, P, g0, G);
     __syncthreads();
     // ---- phase B: a warp owns a 32-AO chunk for all P points; 256-byte coalesced row stores ----
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
@@ -303,15 +351,23 @@ eval_ao_tiled_kernel(const double* __restrict__ coords, const ShellDev* __restri
         const double* R = Rs + (on ? m.rad * RS : 0);
         double* row = ao + ((long)b * C * GpadMax + g0) * Npad + n;
         if (!DERIV) {
-            int p = 0;
-            for (; p + 4 <= pmax; p += 4, row += 4 * (long)Npad) {  // four independent load pairs in flight
+            // 32-bit table indices, one 64-bit row pointer: ~10 instructions per stored value
+            int hi = 0, ri = 0, p = 0;
+            for (; p + 4 <= pmax; p += 4) {  // four independent load pairs in flight
                 double v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = on ? H[(p + u) * natm] * R[(size_t)(p + u) * nrad] : 0.0;
+                for (int u = 0; u < 4; ++u) {
+                    v[u] = H[hi] * R[ri];
+                    hi += natm;
+                    ri += nrad;
+                }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) __stcs(row + u * (long)Npad, v[u]);
+                for (int u = 0; u < 4; ++u) {
+                    __stcs(row, on ? v[u] : 0.0);
+                    row += Npad;
+                }
             }
-            for (; p < pmax; ++p, row += Npad) __stcs(row, on ? H[p * natm] * R[(size_t)p * nrad] : 0.0);
+            for (; p < pmax; ++p, row += Npad, hi += natm, ri += nrad) __stcs(row, on ? H[hi] * R[ri] : 0.0);
             continue;
         }
         for (int p = 0; p < pmax; ++p, row += Npad) {

@@ -191,3 +191,22 @@ __device__ __forceinline__ uint32_t pack_hi16(uint32_t a, uint32_t b) { return _
 
 }  // namespace tc05
 }  // namespace qexxc
+
+// ---- 8-bit integer operands (kind::i8, INT32 accumulation): used by the Ozaki-split study only --------------------
+namespace qexxc {
+namespace tc05 {
+__device__ __host__ constexpr uint32_t idesc_i8(int M, int N) {  // signed 8-bit A and B, K-major, S32 accumulators
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+}  // namespace tc05
+}  // namespace qexxc

@@ -27,7 +27,8 @@ constexpr int PA = KS + 4, PB = WT + 4;
 // C[M x N] = beta * C + op(A) op(B);  TA: A is stored [K x M];  TB: B is stored [N x K].  M, N % 64 == 0, K % 32 == 0.
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) gemm64_kernel(const double* __restrict__ A, long lda, const double* __restrict__ B,
-                                                     long ldb, double* __restrict__ C, long ldc, int K, int beta) {
+                                                     long ldb, double* __restrict__ C, long ldc, int K, int beta,
+                                                     int kchunk, long cz) {
     __shared__ __align__(16) double As[WT * PA > KS * PB ? WT * PA : KS * PB];
     __shared__ __align__(16) double Bs[WT * PA > KS * PB ? WT * PA : KS * PB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, qd = lane & 3;
@@ -86,13 +87,17 @@ __global__ void __launch_bounds__(256) gemm64_kernel(const double* __restrict__ 
             }
         }
     };
-    load_a(0);
-    load_b(0);
-    for (int k0 = 0; k0 < K; k0 += KS) {
+    // split-K: block z multiplies K range [z kchunk, (z+1) kchunk) into its own partial output C + z cz
+    const int kbeg = blockIdx.z * kchunk;
+    const int kend = min(K, kbeg + kchunk);
+    C += (long)blockIdx.z * cz;
+    load_a(kbeg);
+    load_b(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += KS) {
         __syncthreads();  // the previous slab has been consumed
         store_ab();
         __syncthreads();
-        if (k0 + KS < K) {  // prefetch the next slab into registers while this one is multiplied
+        if (k0 + KS < kend) {  // prefetch the next slab into registers while this one is multiplied
             load_a(k0 + KS);
             load_b(k0 + KS);
         }
@@ -128,7 +133,8 @@ __global__ void __launch_bounds__(256) gemm64_kernel(const double* __restrict__ 
 
 struct WideWs {
     int Hp, L, S, Pc;
-    double *Wp, *Wg, *W1p, *wlp, *bias, *Z, *Hh, *D0, *D1, *U, *A64, *XB, *Gb, *Gwl, *G2, *feat;
+    double *Wp, *Wg, *W1p, *wlp, *bias, *Z, *Hh, *D0, *D1, *U, *A64, *XB, *Gb, *Gwl, *G2, *feat, *part;
+    long part_doubles;
 };
 
 struct WideNet {
@@ -382,11 +388,39 @@ inline unsigned blocks_for(long total, int num_sms) {
     return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// C = beta * C + sum_z part[z]  (fixed order => deterministic)
+__global__ void splitk_reduce_kernel(const double* __restrict__ part, int nsplit, long mn, long N, double* __restrict__ C,
+                                     long ldc, int beta) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / N, c = i - r * N;
+        double a = beta ? C[r * ldc + c] : 0.0;
+        for (int z = 0; z < nsplit; ++z) a += part[(long)z * mn + i];
+        C[r * ldc + c] = a;
+    }
+}
+
 template <bool TA, bool TB>
 void gemm(cudaStream_t st, const double* A, long lda, const double* B, long ldb, double* C, long ldc, long M, long N, long K,
-          int beta) {
-    dim3 grid((unsigned)(N / WT), (unsigned)(M / WT));
-    gemm64_kernel<TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, (int)K, beta);
+          int beta, double* part = nullptr, long part_doubles = 0, int num_sms = 148) {
+    dim3 grid((unsigned)(N / WT), (unsigned)(M / WT), 1);
+    const long tiles = (long)grid.x * grid.y;
+    // few output tiles and a long K (the weight-gradient and reduction products): split K over blockIdx.z into partial
+    // outputs, then add them in a fixed order
+    int nsplit = 1;
+    if (part && tiles < num_sms && K >= 1024) {
+        nsplit = (int)((2L * num_sms + tiles - 1) / tiles);
+        if (nsplit > K / 256) nsplit = (int)(K / 256);
+        if ((long)nsplit * M * N > part_doubles) nsplit = (int)(part_doubles / (M * N));
+    }
+    if (nsplit <= 1) {
+        gemm64_kernel<TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, (int)K, beta, (int)K, 0);
+        return;
+    }
+    long kchunk = ((K + nsplit - 1) / nsplit + KS - 1) / KS * KS;
+    nsplit = (int)((K + kchunk - 1) / kchunk);
+    grid.z = nsplit;
+    gemm64_kernel<TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, part, N, (int)K, 0, (int)kchunk, M * N);
+    splitk_reduce_kernel<<<blocks_for(M * N, num_sms), 256, 0, st>>>(part, nsplit, M * N, N, C, ldc, beta);
 }
 
 WideNet wide_net(const qexxc_ctx* c, int xctype) {
@@ -443,6 +477,8 @@ WideWs wide_carve(const qexxc_ctx* c, double* base, size_t* total) {
     w.Gwl = take((size_t)64 * Hp);
     w.G2 = take((size_t)64 * 64);
     w.feat = take((size_t)8 * Pc);
+    w.part_doubles = 8L * Hp * Hp > 64L * 64 * Hp ? 8L * Hp * Hp : 64L * 64 * Hp;  // split-K partial outputs
+    w.part = take((size_t)w.part_doubles);
     *total = off;
     return w;
 }
@@ -539,17 +575,19 @@ int launch_mlp_wide_vjp(qexxc_ctx* c, int xctype, const double* rho, long rho_bs
         QX_TRY(wide_forward(c, n, w, io, 1, st));
         wide_seed_kernel<<<(unsigned)((Pc + 255) / 256), 256, 0, st>>>(n, io, w);
         // b_last_bar = sum u_bar = (A64^T A64)[0][1];  wl_bar = (A64^T [H; Hdot])[0][:]
-        gemm<true, false>(st, w.A64, 64, w.A64, 64, w.G2, 64, 64, 64, 2 * Pc, beta);
-        gemm<true, false>(st, w.A64, 64, w.Hh + (size_t)(L - 1) * 2 * Pc * Hp, Hp, w.Gwl, Hp, 64, Hp, 2 * Pc, beta);
+        gemm<true, false>(st, w.A64, 64, w.A64, 64, w.G2, 64, 64, 64, 2 * Pc, beta, w.part, w.part_doubles, c->num_sms);
+        gemm<true, false>(st, w.A64, 64, w.Hh + (size_t)(L - 1) * 2 * Pc * Hp, Hp, w.Gwl, Hp, 64, Hp, 2 * Pc, beta, w.part,
+                          w.part_doubles, c->num_sms);
         double *D = w.D0, *Dn = w.D1;
         wide_seed2_kernel<<<blocks_for(2 * Pc * Hp, c->num_sms), 256, 0, st>>>(n, w, D);
         for (int l = (int)L - 1; l >= 0; --l) {
             wide_actbwd_kernel<<<blocks_for(Pc * Hp, c->num_sms), 256, 0, st>>>(n, w, l, D);
             // rows of A64^T [z_bar; zdot_bar]: 1 = bias gradient, (l == 0) 2, 3 = first-Dense weight gradients
-            gemm<true, false>(st, w.A64, 64, D, Hp, w.Gb + (size_t)l * 64 * Hp, Hp, 64, Hp, 2 * Pc, beta);
+            gemm<true, false>(st, w.A64, 64, D, Hp, w.Gb + (size_t)l * 64 * Hp, Hp, 64, Hp, 2 * Pc, beta, w.part, w.part_doubles,
+                              c->num_sms);
             if (l > 0) {
                 gemm<true, false>(st, w.Hh + (size_t)(l - 1) * 2 * Pc * Hp, Hp, D, Hp, w.Wg + (size_t)(l - 1) * Hp * Hp, Hp, Hp,
-                                  Hp, 2 * Pc, beta);
+                                  Hp, 2 * Pc, beta, w.part, w.part_doubles, c->num_sms);
                 gemm<false, true>(st, D, Hp, w.Wp + (size_t)(l - 1) * Hp * Hp, Hp, Dn, Hp, 2 * Pc, Hp, Hp, 0);
                 double* t = D;
                 D = Dn;

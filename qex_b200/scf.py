@@ -428,7 +428,9 @@ def scf_loop_batched(xc, theta, dm, eri, s1e, h1e, energy_nuc, nelectron, xctype
 # no mask at all (padded entries contribute exact zeros); the mask matters in the eigensolver, the occupations and the
 # density-matrix build.  Mirrors scf_functions_masked.py:244-309,546-588,917-967 and
 # generalized_eigensolver_masked.py:19-89.  The reference's "stable" get_veff pads with eps = 1e-12 instead of 0 and
-# adds eps to rho (scf_functions_masked.py:567-579); that perturbs energies at the 1e-11 Ha level and is not reproduced.
+# adds eps to rho at every grid point (scf_functions_masked.py:567-579); over a grid that reaches ~100 Bohr that moves
+# E_xc by ~1e-6 Ha (measured with the oracle, tests/test_scf_masked.py) -- a prototype artefact, not reproduced: this
+# loop equals the unpadded one to 1e-10 Ha.
 def pad_stack(mats, n: int | None = None):
     """List of square [N_b, N_b] (or [N_b]^4) tensors -> zero-padded stack [B, n, n(, n, n)] and mask [B, n]."""
     n = n or max(int(m.shape[0]) for m in mats)

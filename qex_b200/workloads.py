@@ -67,7 +67,17 @@ def _cotangents(N, seed):
 
 
 def make(config: str = "c5", ngrids: int | None = None, seed: int = 0) -> Workload:
-    """config in {"c1", "c2", "c3", "c4", "c5", "c5gga"}; `ngrids` overrides the grid size (tests, CPU samples)."""
+    """config in {"c1", "c2", "c3", "c4", "c5", "c5gga", "c5w512"}; `ngrids` overrides the grid size (tests, CPU samples)."""
+    if config == "c5w512":
+        # the c5 system with the 3D trainer's DEFAULT network: flax MLP features [512, 512, 1], gelu, output
+        # -scale * swish(u), applied per grid point (trainer_legacy_no_jit.py:96-107,136-140); layer-by-layer path
+        wl = make("c5", ngrids=ngrids, seed=seed)
+        wl.name = "c5w512"
+        wl.describe = (f"synthetic large system: {wl.nao} AOs x {wl.ngrids} grid points, LocalMLP rho->512->512->1 gelu, "
+                       "-scale*swish output (the 3D trainer's default network), fwd+VJP")
+        wl.net = dict(kind="local_mlp", n_features=1, n_hidden=2, width=512, activation="gelu", out_transform=1)
+        wl.theta = _mlp_theta([1, 512, 512, 1], seed)
+        return wl
     if config == "c5" or config == "c5gga":
         # ~1000 AOs x 1M grid points, LocalMLP (BASELINE.json configs[4])
         mol = gto.synthetic_molecule(50, (4, 2, 2), seed=seed)  # 50 atoms x (4s 2p 2d = 20 AOs) = 1000

@@ -450,9 +450,13 @@ def test_errors_are_loud():
     ctx = _ctx(nao=4, ngrids_max=128, net=_mlp_net())
     with pytest.raises(_lib.QexxcError):
         ctx.nr_rks_fwd(np.eye(4), np.zeros(ctx.n_params), "NN")  # no grid / AO yet
+    # any width / depth is served (csrc/xc_mlp_wide.cu beyond 64 x 3); what the kernels do not have is more than the
+    # two input features (rho, sigma) the reference's local functionals use
     with pytest.raises(NotImplementedError):
-        _ctx(nao=4, ngrids_max=128, net=_mlp_net(H=100)).set_grid(None, np.ones(128)).xc_fwd(
-            np.ones(128), np.zeros(100 * 1 + 100 + 2 * (100 * 100 + 100) + 101), "NN")
+        _ctx(nao=4, ngrids_max=128, ncomp=4, net=_mlp_net(F=3)).set_grid(None, np.ones(128)).xc_fwd(
+            np.ones((4, 128)), np.zeros(3 * 64 + 64 + 2 * (64 * 64 + 64) + 65), "GGA")
+    with pytest.raises(NotImplementedError):
+        _ctx(nao=4, ngrids_max=128, net=_mlp_net(F=3, H=100))
 
 
 def test_empty_grid_and_zero_density_edge_cases():
