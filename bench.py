@@ -413,7 +413,12 @@ def measure(env: Env, args, cfg: str, precision: str, steps: int, warmup: int, h
     # collective times of one step (events on the streams the collectives run on), max over ranks
     coll = None
     if world > 1 and not batch:
-        step(record=True)
+        # ranks leave the timed region skewed (rank 0 reads the profile tables): line them up and take the second of
+        # two recorded steps, otherwise the events time the wait for the slowest rank, not the collective
+        for _ in range(2):
+            torch.cuda.synchronize()
+            env.tdist.barrier()
+            step(record=True)
         f_ms, v_ms = sx.collective_ms()
         t = torch.tensor([f_ms, v_ms], dtype=torch.float64, device="cuda")
         env.tdist.all_reduce(t, op=env.tdist.ReduceOp.MAX)

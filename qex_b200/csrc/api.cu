@@ -289,6 +289,7 @@ int qexxc_create_ex(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngri
     QX_A(c->vgammab, B * Gp);
     if (C == 4) QX_A(c->aow, B * Gp * Np);
     QX_A(c->rq_part, (size_t)((c->Nc + 31) / 32) * 4 * c->num_sms * 128);
+    if (B == 1 && (size_t)c->Npad * 128 * 8 * c->num_sms >= ((size_t)96 << 20)) QX_A(c->rq_pair, (size_t)8 * Gp);
     {
         size_t part_doubles = 0;
         wsyrk_workspace(c->num_sms, c->Nc, c->GpadMax, c->B, C == 4, &part_doubles, &c->ws_items_bytes,

@@ -112,6 +112,7 @@ struct qexxc_ctx {
     double* vgammab = nullptr;  // [B][GpadMax]
     double* aow = nullptr;      // [B][GpadMax][Npad] (C == 4 only)
     double* rq_part = nullptr;  // rowquad split-tail partials [NT][4][num_sms][128]
+    double* rq_pair = nullptr;  // rowquad pair-mode partials [2][4][GpadMax] (single-molecule contexts with wide N)
     double* part = nullptr;     // wsyrk partial tiles, one compact [BN][BN] slot per (batch, tile, grid chunk)
     void* ws_items[2] = {nullptr, nullptr};  // wsyrk static schedules (general, symmetric)
     int* ws_start[2] = {nullptr, nullptr};

@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, double* __restrict__ q,
                int Npad, int Nc, long ao_cstride, long ao_bstride, long S_bstride, long q_cstride,
                long q_bstride, int ncomp, int tri, double f0, double f1, double f2, double f3, int ldS, int Sc,
-               const double* __restrict__ sgn, int nbulk, int ntail, double* __restrict__ qpart) {
+               const double* __restrict__ sgn, int nbulk, int ntail, double* __restrict__ qpart, int npair,
+               unsigned mask0, unsigned mask1, double* __restrict__ qpair) {
     // tri != 0: S holds only its upper triangle (diagonal halved); the caller folds the factor 2
     // into f0.  Npad = storage pitch (multiple of 32, pad columns are zeros), Nc = compute extent
     // (multiple of 8): slabs are always full, column blocks beyond Nc are never issued.
@@ -195,13 +196,24 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int NT = (Sc + BN - 1) / BN;
-    int tile = blockIdx.x, nt_lo = 0, nt_hi = NT;
-    const bool split = (int)blockIdx.x >= nbulk;
+    // Pair mode (npair != 0, wide N): every bulk row tile is shared by TWO adjacent blocks that take complementary,
+    // equally heavy sets of column tiles (mask0 / mask1).  A block then re-streams its 128 ao rows half as often and,
+    // more to the point, only num_sms / 2 distinct row tiles are in flight, so the rows (8 KB each at N = 1000) stay
+    // in L2 between the sweeps instead of being re-read from HBM; the two partial row sums are added in a fixed
+    // order by rowquad_pair_kernel.
+    int tile = blockIdx.x, nt_lo = 0, nt_hi = NT, half = -1;
+    unsigned mask = 0xffffffffu;
+    const int nb2 = npair ? 2 * nbulk : nbulk;
+    const bool split = (int)blockIdx.x >= nb2;
     if (split) {
-        const int idx = blockIdx.x - nbulk;
+        const int idx = blockIdx.x - nb2;
         nt_lo = NT - 1 - idx / ntail;
         nt_hi = nt_lo + 1;
         tile = nbulk + idx % ntail;
+    } else if (npair) {
+        tile = blockIdx.x >> 1;
+        half = blockIdx.x & 1;
+        mask = half ? mask1 : mask0;
     }
     const long g0 = (long)tile * BM;
     const double* ao_b = ao + (long)b * ao_bstride;
@@ -226,6 +238,7 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
         const int pw = warp - NCONS;
         int it = 0;
         for (int nt = nt_lo; nt < nt_hi; ++nt) {
+            if (!((mask >> nt) & 1u)) continue;
             const int nw = imin(BN, ldS - nt * BN);  // copy width: storage columns (zeros beyond Sc)
             const int kend = rq_kend(tri, Nc, BN, nt);
             for (int kb = 0; kb < kend; ++kb, ++it) {
@@ -260,6 +273,7 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
     const int aoff = (wm * 32 + g) * Cfg::LDA + qd;
     const int boff = qd * Cfg::LDB + wn * 8 + g;  // this warp's blocks are 2*j + wn: 16 doubles apart
     for (int nt = nt_lo; nt < nt_hi; ++nt) {
+        if (!((mask >> nt) & 1u)) continue;
         const int nw = imin(BN, Sc - nt * BN);
         const int kend = rq_kend(tri, Nc, BN, nt);
         const int nbv = nw >> 3;                             // valid n8 blocks of this tile
@@ -340,9 +354,19 @@ rowquad_kernel(const double* __restrict__ ao, const double* __restrict__ S, doub
             if (c < ncomp) {
                 const double v = fac[c] * (red[(c * 2 + 0) * BM + threadIdx.x] + red[(c * 2 + 1) * BM + threadIdx.x]);
                 if (split) qpart[((long)(nt_lo * 4 + c) * ntail + (tile - nbulk)) * BM + threadIdx.x] = v;
+                else if (half >= 0) qpair[((long)(half * 4 + c) * nbulk + tile) * BM + threadIdx.x] = v;
                 else q[(long)b * q_bstride + (long)c * q_cstride + g0 + threadIdx.x] = v;
             }
     }
+}
+
+// q[c][row] = half 0 + half 1 of the paired bulk tiles
+__global__ void rowquad_pair_kernel(const double* __restrict__ qpair, double* __restrict__ q, long q_cstride, int ncomp,
+                                    int nbulk) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (long)nbulk * BM) return;
+    for (int c = 0; c < ncomp; ++c)
+        q[(long)c * q_cstride + r] = qpair[(long)c * nbulk * BM + r] + qpair[(long)(4 + c) * nbulk * BM + r];
 }
 
 // q[c][row] = sum over the column tiles (in order) of the split tail tiles' partial results
@@ -705,8 +729,11 @@ void ws_shape(int num_sms, int Nc, int Gpad, int B, bool sym, WsPlan& p) {
     p.BN = pick_bn(Nc);
     p.NT = (Nc + p.BN - 1) / p.BN;
     p.ntile = sym ? p.NT * (p.NT + 1) / 2 : p.NT * p.NT;
-    // ~16 items per CTA keeps greedy scheduling within a few percent of perfect balance
-    static const long per_cta = getenv("QEXXC_WS_ITEMS") ? atol(getenv("QEXXC_WS_ITEMS")) : 16L;
+    // items per CTA: >= 16 keeps greedy scheduling within a few percent of perfect balance; 64 makes the grid chunks
+    // small enough (15 MB of ao rows at c5) that the ~4 chunks in flight stay in L2 while their 36 tile pairs re-read
+    // them: measured DRAM traffic per launch 25.0 -> 11.0 GB (8.2 algorithmic) at unchanged kernel time
+    // (profiles/r02/ws_items_sweep.log); the price is 0.9 GB more partial-tile workspace at c5
+    static const long per_cta = getenv("QEXXC_WS_ITEMS") ? atol(getenv("QEXXC_WS_ITEMS")) : 64L;
     long rows = ((long)Gpad * p.ntile * B + per_cta * num_sms - 1) / (per_cta * num_sms);
     rows = ((rows + 255) / 256) * 256;
     if (rows < 256) rows = 256;
@@ -926,7 +953,7 @@ int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const doub
         QX_TRY(set_smem(rowquad_kernel<BNV>, RowquadCfg<BNV>::SMEM));                            \
         rowquad_kernel<BNV><<<grid, NTHREADS, RowquadCfg<BNV>::SMEM, st>>>(                      \
             c->ao, L, q, c->Npad, c->Nc, ao_cs, ao_bs, L_bs, 0, q_bstride, 1, 0, 1.0, 0.0, 0.0,  \
-            0.0, ldL, Sc, sgn, (int)grid.x, 0, nullptr);                                         \
+            0.0, ldL, Sc, sgn, (int)grid.x, 0, nullptr, 0, 0u, 0u, nullptr);                     \
     } while (0)
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
     if (BN == 128) QX_RQM(128);
@@ -948,11 +975,34 @@ int rowquad_tail_tiles(const qexxc_ctx* c, int tri) {
     return ((double)rem / c->num_sms + heaviest < 0.95) ? rem : 0;
 }
 
+// Pair mode pays when the 128-row ao tiles of all resident blocks no longer fit in L2 (wide N) and there are enough row
+// tiles to keep every SM busy with half-tiles; masks: column tiles dealt heaviest-first to the lighter half.
+static bool rowquad_pair_masks(const qexxc_ctx* c, int tri, int nbulk, unsigned* m0, unsigned* m1) {
+    const int BN = pick_bn(c->Nc), NT = (c->Nc + BN - 1) / BN;
+    if (c->B != 1 || c->rq_pair == nullptr || NT < 2 || NT > 32 || getenv("QEXXC_NO_PAIR")) return false;
+    if ((long)c->Npad * BM * 8 * c->num_sms < (96L << 20) || nbulk < 2 * c->num_sms) return false;
+    long w0 = 0, w1 = 0;
+    *m0 = *m1 = 0;
+    for (int nt = NT - 1; nt >= 0; --nt) {  // rq_kend is non-decreasing in nt: this is heaviest first
+        const long w = rq_kend(tri, c->Nc, BN, nt) + 1;
+        if (w0 <= w1) {
+            *m0 |= 1u << nt;
+            w0 += w;
+        } else {
+            *m1 |= 1u << nt;
+            w1 += w;
+        }
+    }
+    return true;
+}
+
 int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride,
                    long q_cstride, cudaStream_t st) {
     const int BN = pick_bn(c->Nc), NT = (c->Nc + BN - 1) / BN, T = c->Gpad / BM;
     const int ntail = rowquad_tail_tiles(c, tri), nbulk = T - ntail;
-    dim3 grid(nbulk + ntail * NT, c->B);
+    unsigned m0 = 0, m1 = 0;
+    const int npair = rowquad_pair_masks(c, tri, nbulk, &m0, &m1) ? 1 : 0;
+    dim3 grid((npair ? 2 * nbulk : nbulk) + ntail * NT, c->B);
     const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = c->ao_shared ? 0 : ao_cs * c->C, S_bs = (long)c->Npad * c->Npad;
 #define QX_RQ(BNV)                                                                               \
     do {                                                                                         \
@@ -960,7 +1010,7 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double*
         rowquad_kernel<BNV><<<grid, NTHREADS, RowquadCfg<BNV>::SMEM, st>>>(                      \
             c->ao, c->S, q, c->Npad, c->Nc, ao_cs, ao_bs, S_bs, q_cstride, q_bstride, ncomp, tri, \
             (tri ? 2.0 : 1.0) * fac4[0], fac4[1], fac4[2], fac4[3], c->Npad, c->Nc, nullptr,     \
-            nbulk, ntail, c->rq_part);                                                           \
+            nbulk, ntail, c->rq_part, npair, m0, m1, c->rq_pair);                                \
     } while (0)
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
     if (BN == 128) QX_RQ(128);
@@ -968,6 +1018,10 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double*
     else QX_RQ(32);
 #undef QX_RQ
     QX_LAUNCH_CHECK(c);
+    if (npair) {
+        rowquad_pair_kernel<<<(unsigned)(((long)nbulk * BM + 255) / 256), 256, 0, st>>>(c->rq_pair, q, q_cstride, ncomp, nbulk);
+        QX_LAUNCH_CHECK(c);
+    }
     if (ntail > 0) {
         rowquad_tail_kernel<<<(ntail * BM + 255) / 256, 256, 0, st>>>(c->rq_part, q, q_cstride, ncomp, NT, nbulk, ntail);
         QX_LAUNCH_CHECK(c);

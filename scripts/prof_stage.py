@@ -1,4 +1,5 @@
-"""Run one stage of the hot path a few times (for ncu captures):  python scripts/prof_stage.py ao|fwd|vjp [ngrids]"""
+"""Run one stage of the hot path a few times (for ncu captures):
+    python scripts/prof_stage.py ao|fwd|vjp [ngrids] [config] [f64|f32]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,8 +9,9 @@ from qex_b200.engine import XCContext
 what = sys.argv[1] if len(sys.argv) > 1 else "ao"
 G = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 cfg = sys.argv[3] if len(sys.argv) > 3 else "c5"
+prec = sys.argv[4] if len(sys.argv) > 4 else "f64"
 wl = workloads.make(cfg, ngrids=G)
-ctx = XCContext(nao=wl.nao, ngrids_max=G, ncomp=wl.ncomp, net=workloads.net_spec(wl))
+ctx = XCContext(nao=wl.nao, ngrids_max=G, ncomp=wl.ncomp, net=workloads.net_spec(wl, prec))
 ctx.set_basis(wl.mol._atm, wl.mol._bas, wl.mol._env).set_grid(wl.coords, wl.weights)
 deriv = 1 if wl.ncomp == 4 else 0
 ctx.eval_ao(deriv)
