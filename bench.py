@@ -656,8 +656,9 @@ def run_ours(args):
                             "note": "SURVEY 8d's 2*G*N^2 per launch; exceeds the pipe fraction because symmetric operands "
                                     "let the kernels skip the lower-triangular blocks"},
             "executed_flop_per_launch": ex[dom],
-            "traffic_note": "dram read+write bytes per launch from the committed ncu --set full capture of this shape "
-                            "(profiles/ncu_traffic.json); algorithmic bytes = the AO tensor read once = "
+            "traffic_note": "dram read+write bytes per launch of THIS kernel at this shape, from the committed ncu capture "
+                            "(profiles/ncu_traffic.json, profiles/r02/pair_mode_and_traffic.log; not measurable inside a "
+                            "timed run); algorithmic bytes = the AO tensor read once = "
                             f"{8.0 * res['npad'] * res['Gl'] / 1e9:.2f} GB",
             "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, sustained (MEASURED_PEAKS.json has no FP64 figure); "
                            f"burst {peak_burst:.1f} TFLOP/s",

@@ -285,8 +285,8 @@ __device__ __forceinline__ void radial_phase(const ShellDev* __restrict__ shells
     }
 }
 
-template <bool DERIV>
-__global__ void __launch_bounds__(512, 2)
+template <bool DERIV, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 2)
 eval_ao_tiled_kernel(const double* __restrict__ coords, const ShellDev* __restrict__ shells,
                      const int* __restrict__ shell_atom, const int* __restrict__ atom_coord,
                      const AoMeta* __restrict__ meta, int nshell, int natm, int nrad, int lmax,
@@ -459,6 +459,12 @@ int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
     int P = (int)((110 * 1024) / (per_pt ? per_pt : 1));
     if (P > 16) P = 16;
     if (P >= 4) P &= ~3;  // radial sums run four points at a time
+    const bool reg85 = getenv("QEXXC_AO_REG85") && atoi(getenv("QEXXC_AO_REG85")) != 0;
+    if (reg85) {  // three CTAs per SM: up to ~72 KB of tables each
+        P = (int)((72 * 1024) / (per_pt ? per_pt : 1));
+        if (P > 16) P = 16;
+        if (P >= 4) P &= ~3;
+    }
     if (getenv("QEXXC_AO_P")) P = atoi(getenv("QEXXC_AO_P"));
     if (P >= 1) {
         const size_t smem = ((size_t)nrow * (((size_t)P * c->natm) | 1) + (size_t)P * c->nrad * (deriv ? 2 : 1) + 64) * 8;
@@ -467,17 +473,21 @@ int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st) {
         // resident warps (the kernel is latency-bound, not pipe-bound); small molecules keep 256 threads
         int nthr = ((long)P * c->natm >= 256 || c->Npad >= 512) ? 512 : 256;
         if (getenv("QEXXC_AO_THREADS")) nthr = atoi(getenv("QEXXC_AO_THREADS"));
-        if (deriv) {
-            QX_CUDA(cudaFuncSetAttribute(eval_ao_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            eval_ao_tiled_kernel<true><<<tgrid, nthr, smem, st>>>(c->coords, c->shells, c->shell_atom, c->atom_coord,
-                c->ao_meta, c->nshell, c->natm, c->nrad, c->lmax, c->env, c->nenv, c->ao, c->G, c->Gpad, c->GpadMax,
-                c->N, c->Npad, c->C, P);
+        if (reg85) nthr = 256;
+#define QX_AO(D, T)                                                                                              \
+    do {                                                                                                         \
+        QX_CUDA(cudaFuncSetAttribute(eval_ao_tiled_kernel<D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        eval_ao_tiled_kernel<D, T><<<tgrid, nthr, smem, st>>>(c->coords, c->shells, c->shell_atom, c->atom_coord, c->ao_meta, \
+            c->nshell, c->natm, c->nrad, c->lmax, c->env, c->nenv, c->ao, c->G, c->Gpad, c->GpadMax, c->N, c->Npad, c->C, P); \
+    } while (0)
+        if (reg85) {  // 256-thread CTAs, three per SM, up to 85 registers per thread
+            if (deriv) QX_AO(true, 256);
+            else QX_AO(false, 256);
         } else {
-            QX_CUDA(cudaFuncSetAttribute(eval_ao_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            eval_ao_tiled_kernel<false><<<tgrid, nthr, smem, st>>>(c->coords, c->shells, c->shell_atom, c->atom_coord,
-                c->ao_meta, c->nshell, c->natm, c->nrad, c->lmax, c->env, c->nenv, c->ao, c->G, c->Gpad, c->GpadMax,
-                c->N, c->Npad, c->C, P);
+            if (deriv) QX_AO(true, 512);
+            else QX_AO(false, 512);
         }
+#undef QX_AO
         QX_LAUNCH_CHECK(c);
         return QEXXC_OK;
     }
