@@ -1,7 +1,7 @@
 // INT8 tcgen05 throughput probe for the Ozaki-split study: how fast can one SM run
 // kind::i8 MMAs (M = 128, N = 256, K = 32 per instruction, INT32 accumulators in tensor memory) on operands that are
 // already in shared memory?  That is the ceiling of an exact-INT8 emulation of the FP64 contractions; dividing it by
-// the 21 slice products that 1e-10 needs (scripts/ozaki_study.py) gives the FP64-equivalent rate to hold against
+// the 21 slice products that 1e-10 needs (tests/studies/ozaki_study.py) gives the FP64-equivalent rate to hold against
 // the measured 35.5 TFLOP/s of the DMMA path.  Also checks one accumulator against the CPU.
 #include <cstdio>
 #include <cstdlib>

@@ -6,15 +6,15 @@ the stage-2 product T = ao . S and the row-dot rho = rowsum(T * ao):
     a[g,:] = 2^ea[g] * sum_s A_s[g,:] 2^(-7(s+1)),   S[:,j] = 2^eb[j] * sum_t B_t[:,j] 2^(-7(t+1)),  A_s, B_t in [-64, 63]
     T ~= 2^(ea+eb) * sum_{s+t<ns} A_s B_t 2^(-7(s+t+2))      (every A_s B_t exact: 12 bits + log2(N=1000) = 22 < 31)
 Prints, per slice count, the number of INT8 GEMMs and the max-norm error of T and rho.
-    python scripts/ozaki_study.py [ngrids]"""
+    python tests/studies/ozaki_study.py [ngrids]   (lives under tests/ because it uses the oracle's AO values)"""
 import json
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import gto_ref  # noqa: E402  (test infrastructure: this is a study script, not the product path)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import gto_ref  # noqa: E402
 from qex_b200 import workloads  # noqa: E402
 
 
@@ -63,5 +63,5 @@ def main():
 
 if __name__ == "__main__":
     res = main()
-    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02", "ozaki_slices.json")
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "profiles", "r02", "ozaki_slices.json")
     json.dump(res, open(out, "w"), indent=1)
