@@ -46,6 +46,9 @@ def build(force: bool = False, verbose: bool = True) -> Path:
     stamp = BUILD / "stamp"
     dig = _digest(deps)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
+        if verbose:
+            print(f"build: {LIB.name} is up to date (source digest {dig[:12]} matches {stamp}); "
+                  f"`python -m qex_b200.build --force` recompiles")
         return LIB
     nvcc = _nvcc()
 
@@ -65,8 +68,15 @@ def build(force: bool = False, verbose: bool = True) -> Path:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
     stamp.write_text(dig)
+    # what was built, for the record (the .so itself is git-ignored and travels to the GPU box with the snapshot)
+    import json
+    import time
+    ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    (BUILD / "build_info.json").write_text(json.dumps({
+        "library": LIB.name, "sources": SOURCES, "nvcc": ver, "flags": NVCC_FLAGS, "source_digest": dig,
+        "built_at": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "bytes": LIB.stat().st_size}, indent=1))
     if verbose:
-        print(f"built {LIB}")
+        print(f"built {LIB} ({len(SOURCES)} translation units, {ver})")
     return LIB
 
 
