@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 BUILD = HERE / "_build"
 LIB = HERE / "libqexxc.so"
-SOURCES = ["api.cu", "contract.cu", "ao.cu", "pointwise.cu", "xc_mlp.cu", "xc_mlp_tc.cu", "xc_mlp_wide.cu", "xc_global.cu", "xc_qnn.cu", "jk.cu", "eigh.cu", "grid.cu", "xc_lda.cu", "comm.cu"]
+SOURCES = ["api.cu", "contract.cu", "contract_i8.cu", "ao.cu", "pointwise.cu", "xc_mlp.cu", "xc_mlp_tc.cu", "xc_mlp_wide.cu", "xc_global.cu", "xc_qnn.cu", "jk.cu", "eigh.cu", "grid.cu", "xc_lda.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -363,6 +363,7 @@ int qexxc_set_grid(qexxc_ctx* c, const double* coords_dev, const double* weights
     c->G = ngrids;
     c->Gpad = round_up(ngrids > 0 ? ngrids : 1, kGTile);
     c->ao_ncomp = 0;
+    c->i8_valid = false;
     QX_TRY(launch_set_grid(c, coords_dev, weights_dev, ngrids, (cudaStream_t)stream));
     c->have_grid = true;
     return QEXXC_OK;
@@ -434,6 +435,7 @@ int qexxc_set_basis(qexxc_ctx* c, const int* atm, int natm, const int* bas, int 
     QX_CUDA(cudaMemcpy(c->env, env, sizeof(double) * (size_t)nb * nenv, cudaMemcpyHostToDevice));
     c->have_basis = true;
     c->ao_ncomp = 0;
+    c->i8_valid = false;
     return QEXXC_OK;
 }
 
@@ -454,6 +456,7 @@ int qexxc_eval_ao(qexxc_ctx* c, int deriv, void* stream) {
     QX_CUDA(cudaSetDevice(c->device));
     QX_TRY(launch_eval_ao(c, deriv, (cudaStream_t)stream));
     c->ao_ncomp = deriv ? 4 : 1;
+    c->i8_valid = false;
     return QEXXC_OK;
 }
 
@@ -468,6 +471,7 @@ int qexxc_set_ao(qexxc_ctx* c, const double* ao_dev, int ncomp, int ngrids, void
     QX_CUDA(cudaSetDevice(c->device));
     QX_TRY(launch_pack_ao(c, ao_dev, ncomp, ngrids, (cudaStream_t)stream));
     c->ao_ncomp = ncomp;
+    c->i8_valid = false;
     return QEXXC_OK;
 }
 

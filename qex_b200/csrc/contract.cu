@@ -998,6 +998,7 @@ static bool rowquad_pair_masks(const qexxc_ctx* c, int tri, int nbulk, unsigned*
 
 int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride,
                    long q_cstride, cudaStream_t st) {
+    if (rowquad_i8_enabled(c)) return launch_rowquad_i8(c, ncomp, tri, fac4, q, q_cstride, st);
     const int BN = pick_bn(c->Nc), NT = (c->Nc + BN - 1) / BN, T = c->Gpad / BM;
     const int ntail = rowquad_tail_tiles(c, tri), nbulk = T - ntail;
     unsigned m0 = 0, m1 = 0;
