@@ -2,14 +2,20 @@
 //     q_c[g] = fac_c * sum_ij ao_c[g,i] S[i,j] ao_0[g,j]                      (rowquad of contract.cu)
 // The FP64 DMMA path saturates the FP64 pipe (0.99 of cuBLAS DGEMM); this path does not use it for the N^2 work:
 //
-//   ao_0[g,:] = 2^(ea[g]-42) * sum_k A_k[g,:] 128^k,   S[:,j] = 2^(eb[j]-42) * sum_l B_l[:,j] 128^l,   A_k, B_l in [-64, 63]
-//   (ao_0 S)[g,j] ~= 2^(ea[g]+eb[j]-49) * sum_{d=0..5} 128^(5-d) * sum_{s+t=d} (A^(s) B^(t))[g,j]     (s = 5-k, t = 5-l)
+//   ao_0[g,:] = 2^(ea[g]-48) * sum_k A_k[g,:] 256^k,   S[:,j] = 2^(eb[j]-48) * sum_l B_l[:,j] 256^l,   A_k, B_l in [-128, 127]
+//   (ao_0 S)[g,j] ~= 2^(ea[g]+eb[j]-56) * sum_{d=0..5} 256^(5-d) * sum_{s+t=d} (A^(s) B^(t))[g,j]     (s = 5-k, t = 5-l)
 //
-// six balanced 7-bit digits per operand (42 bits relative to the row / column maximum), the 21 digit products with
-// s + t <= 5, each an exact INT8 x INT8 -> INT32 GEMM on tcgen05 (kind::i8): 12 bits per product + log2(N) and at most
-// six products per diagonal stay below 2^31.  Measured on the c5 operands (tests/studies/ozaki_study.py): rho to 1.6e-11 of its
+// six balanced 8-bit digits per operand (46 bits relative to the row / column maximum), the 21 digit products with
+// s + t <= 5, each an exact INT8 x INT8 -> INT32 GEMM on tcgen05 (kind::i8): 14 bits per product + log2(N <= 1024) and at
+// most six products per diagonal stay below 2^27.  Measured on the c5 operands (tests/studies/ozaki_study.py): rho to 1.6e-11 of its
 // largest element, i.e. inside the 1e-10 bar of the FP64 path; the digits of a diagonal share one TMEM accumulator, the
-// six accumulators are combined in 64-bit integers (exact) and converted to FP64 once per element.
+// six accumulators are combined in 64-bit integers (exact) and converted to FP64 twice per element (high / low half).
+//
+// tcgen05.mma has a floor of ~105 cycles per instruction for N <= 128 (scripts/probe/i8_rate.cu: N = 64 runs at a third of
+// the N = 256 rate), so the products of one A digit plane with ALL the B planes it meets are ONE instruction: the B
+// planes of a k-chunk sit in shared memory as a single [6 x 64 rows] K-major tile and the accumulators of consecutive
+// diagonals are adjacent TMEM column ranges, so A^(s) x [B^(0); ...; B^(5-s)] lands in accumulators s ... 5 (N = 64 (6 - s),
+// split at 256): 8 instructions per k-step instead of 21.
 //
 // Pipeline (one CTA per 128 grid rows, 6 warps): warp 0 streams digit tiles with 1-D bulk copies (the slicing kernels
 // write them in the 128-byte-swizzled K-major tile layout, so no tensor maps are needed) -- the six B tiles of a
@@ -31,24 +37,25 @@ constexpr int KC = 128;          // k-chunk: 128 int8 = one 128-byte swizzled ro
 constexpr uint32_t ATILE = IM * KC;  // 16 KB
 constexpr uint32_t BTILE = IN * KC;  // 8 KB
 constexpr int NA = 4;            // A-tile ring depth
-constexpr int I8_THREADS = 192;
+constexpr int NEW = 8;           // epilogue warps: 4 TMEM lane quadrants x 2 column halves
+constexpr int I8_THREADS = 64 + 32 * NEW;
 
 __device__ __forceinline__ uint32_t tile_off(int r, int c) {  // byte offset of (row r, k c) inside a swizzled tile
     return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((((c >> 4) ^ (r & 7)) << 4) | (c & 15));
 }
 
-// balanced base-128 digits of v (|v| < 2^41), least significant first
+// balanced base-256 digits of v (|v| < 2^46), least significant first
 __device__ __forceinline__ void digits6(long long v, int (&d)[ND]) {
 #pragma unroll
     for (int k = 0; k < ND; ++k) {
-        const int low = (int)(((v + 64) & 127) - 64);
+        const int low = (int)(((v + 128) & 255) - 128);
         d[k] = low;
-        v = (v - low) >> 7;
+        v = (v - low) >> 8;
     }
 }
 
 // ---- slicing kernels ----------------------------------------------------------------------------------------------
-// A8[s][row tile][k-chunk][16 KB tile], s = 0 most significant; ea[g]: x = 2^(ea-42) * sum digits.  One warp per row.
+// A8[s][row tile][k-chunk][16 KB tile], s = 0 most significant; ea[g]: x = 2^(ea-48) * sum digits.  One warp per row.
 __global__ void __launch_bounds__(256) slice_ao_kernel(const double* __restrict__ ao, int Npad, int nkc, long Gpad,
                                                        signed char* __restrict__ A8, float* __restrict__ sa) {
     const long g = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -69,10 +76,10 @@ __global__ void __launch_bounds__(256) slice_ao_kernel(const double* __restrict_
     int e = 0;
     if (mx > 0.0) {
         (void)frexp(mx, &e);  // mx = m 2^e, m in [0.5, 1)
-        e += 2;               // |x| / 2^e < 0.25: the top balanced digit stays below 33 after carries
+        e += 2;               // |x| / 2^e < 0.25: the top balanced digit stays below 65 after carries
     }
     if (lane == 0) sa[g] = (float)e;
-    const double scale = ldexp(1.0, 42 - e);
+    const double scale = ldexp(1.0, 48 - e);
     // pass 2: lane owns 16 consecutive columns (one 16-byte chunk) per step
     for (int c0 = lane * 16; c0 < nkc * KC; c0 += 512) {
         unsigned w[ND][4];
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(256) slice_ao_kernel(const double* __restrict_
     }
 }
 
-// B8[t][column tile (64)][k-chunk][8 KB tile]: B[n = j][k = i] = S[i][j]; sb[j] = 2^(eb[j]-49).  One block per column j.
+// B8[t][column tile (64)][k-chunk][8 KB tile]: B[n = j][k = i] = S[i][j]; sb[j] = 2^(eb[j]-56).  One block per column j.
 __global__ void __launch_bounds__(256) slice_s_kernel(const double* __restrict__ S, int ldS, int Nc, int nkc, int nct,
                                                       signed char* __restrict__ B8, double* __restrict__ sb) {
     const int j = blockIdx.x;
@@ -116,8 +123,8 @@ __global__ void __launch_bounds__(256) slice_s_kernel(const double* __restrict__
         (void)frexp(mx, &e);
         e += 2;
     }
-    if (threadIdx.x == 0) sb[j] = ldexp(1.0, e - 49);
-    const double scale = ldexp(1.0, 42 - e);
+    if (threadIdx.x == 0) sb[j] = ldexp(1.0, e - 56);
+    const double scale = ldexp(1.0, 48 - e);
     const int ct = j / IN, r = j % IN;
     for (int i = threadIdx.x; i < nkc * KC; i += blockDim.x) {
         const double x = (j < Nc && i < Nc) ? S[(long)i * ldS + j] : 0.0;
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const I8Args 
             mbar_init(emptyA + i, 1);
         }
         mbar_init(tfull, 1);
-        mbar_init(tempty, 4);  // one arrival per epilogue warp
+        mbar_init(tempty, NEW);  // one arrival per epilogue warp
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tslot, 512);
@@ -207,7 +214,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const I8Args 
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            constexpr uint32_t id = idesc_i8(IM, IN);
             const uint32_t sA = smem_u32(As), sB = smem_u32(Bs);
             int itB = 0, itA = 0;
             for (int ct = 0; ct < a.nct; ++ct) {
@@ -221,13 +227,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const I8Args 
                         const int sl = itA % NA;
                         mbar_wait(fullA + sl, (itA / NA) & 1);
                         tc_fence_after();
-                        for (int t = 0; t + s < ND; ++t) {
-                            const uint32_t d = tm + (uint32_t)(s + t) * IN;
+                        // A^(s) x [B^(0); ...; B^(5-s)] -> accumulators s ... 5 (adjacent TMEM columns), N <= 256 per instruction
+                        const int ntot = (ND - s) * IN;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                mma_i8(d, smem_desc(sA + sl * ATILE + k * 32, 16, 1024),
-                                       smem_desc(sB + (kb * ND + t) * BTILE + k * 32, 16, 1024), id,
-                                       (uint32_t)(kc != 0 || s != 0 || k != 0));
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t acc = (uint32_t)(kc != 0 || s != 0 || k != 0);
+                            const uint64_t da = smem_desc(sA + sl * ATILE + k * 32, 16, 1024);
+                            const int n0 = ntot > 256 ? 256 : ntot;
+                            mma_i8(tm + (uint32_t)s * IN, da, smem_desc(sB + kb * ND * BTILE + k * 32, 16, 1024), idesc_i8(IM, n0), acc);
+                            if (ntot > 256)
+                                mma_i8(tm + (uint32_t)s * IN + 256, da, smem_desc(sB + kb * ND * BTILE + 4 * BTILE + k * 32, 16, 1024),
+                                       idesc_i8(IM, ntot - 256), acc);
                         }
                         mma_commit(emptyA + sl);  // the slot is free once these MMAs have read it
                     }
@@ -237,35 +247,40 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const I8Args 
             }
         }
     } else {
-        // ---------------- epilogue: 4 warps, thread = one grid row ----------------
-        const int qd = warp & 3;  // TMEM lane quadrant of this warp
+        // ---------------- epilogue: 8 warps; thread = one grid row x one half of the tile's columns ----------------
+        const int qd = warp & 3;           // TMEM lane quadrant of this warp
+        const int half = (warp - 2) >> 2;  // columns [32 half, 32 half + 32) of every 64-column tile
         const int r = qd * 32 + lane;
         const long g = tile * IM + r;
-        const double rs = ldexp(1.0, (int)a.sa[g]);
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         for (int ct = 0; ct < a.nct; ++ct) {
             mbar_wait(tfull, ct & 1);
             __syncwarp();
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < IN; c0 += 16) {
-                long long tot[16];
+            for (int c0 = 32 * half; c0 < 32 * half + 32; c0 += 16) {
+                long long hi[16], lo[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) tot[j] = 0;
+                for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0;
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
                     float v[16];
                     tmem_ld16(tmem_addr(tm, 32 * qd, d * IN + c0), v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) tot[j] += (long long)__float_as_int(v[j]) << (7 * (ND - 1 - d));
+                    for (int j = 0; j < 16; ++j) {
+                        const long long p = (long long)__float_as_int(v[j]);
+                        if (d < 3) hi[j] += p << (8 * (2 - d));
+                        else lo[j] += p << (8 * (5 - d));
+                    }
                 }
                 const int col = ct * IN + c0;
                 if (col < a.Nc) {
                     const double* sbp = a.sb + col;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const double t = (double)tot[j] * sbp[j];  // columns beyond Nc carry zero digits
+                        // sum_d P_d 256^(5-d) = hi 2^24 + lo, each half exact in FP64 (< 2^45); columns beyond Nc carry zero digits
+                        const double t = fma((double)hi[j], 16777216.0, (double)lo[j]) * sbp[j];
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             if (c < a.ncomp) acc[c] = fma(t, a.ao[(long)c * a.ao_cstride + g * a.Npad + col + j], acc[c]);
@@ -276,9 +291,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const I8Args 
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty);
         }
+        // the two column halves of a row: fixed-order sum through shared memory (the B tiles are free now)
+        double* part = reinterpret_cast<double*>(Bs);
+        if (half == 1) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c < a.ncomp) a.q[(long)c * a.q_cstride + g] = a.f[c] * rs * acc[c];
+            for (int c = 0; c < 4; ++c) part[c * IM + r] = acc[c];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * NEW) : "memory");
+        if (half == 0) {
+            const double rs = ldexp(1.0, (int)a.sa[g]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < a.ncomp) a.q[(long)c * a.q_cstride + g] = a.f[c] * rs * (acc[c] + part[c * IM + r]);
+        }
     }
     tc_fence_before();
     __syncthreads();

@@ -9,7 +9,7 @@
 #include "../../qex_b200/csrc/tc05.cuh"
 using namespace qexxc::tc05;
 
-__global__ void __launch_bounds__(128, 1) i8_kernel(const signed char* A, const signed char* B, int* D, int iters, int nkind) {
+__global__ void __launch_bounds__(128, 1) i8_kernel(const signed char* A, const signed char* B, int* D, int iters, int nkind, int N) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
     unsigned char* As = base;              // [128 rows][128 bytes] K-major, SWIZZLE_128B
@@ -39,10 +39,10 @@ __global__ void __launch_bounds__(128, 1) i8_kernel(const signed char* A, const 
             // 4 k-steps of 32 bytes = one 128-byte row; alternate two accumulators like a pipelined tile loop would
             const uint32_t d = tm + (it & 1) * 256;
             if (nkind == 0) {
-                const uint32_t id = idesc_i8(128, 256);
+                const uint32_t id = idesc_i8(128, N);
                 for (int k = 0; k < 4; ++k) mma_i8(d, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), id, (it > 1) | (k > 0));
             } else {
-                const uint32_t id = idesc_bf16(128, 256, 0, 0);
+                const uint32_t id = idesc_bf16(128, N, 0, 0);
                 for (int k = 0; k < 4; ++k) mma_bf16(d, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), id, (it > 1) | (k > 0));
             }
             if ((it & 63) == 63 || it == iters - 1) {  // bound the number of MMAs in flight
@@ -77,7 +77,7 @@ int main() {
     const int smem = 128 * 128 + 256 * 128 + 1024;
     cudaFuncSetAttribute(i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     // correctness: one K = 128 product
-    i8_kernel<<<1, 128, smem>>>(dA, dB, dD, 1, 0);
+    i8_kernel<<<1, 128, smem>>>(dA, dB, dD, 1, 0, 256);
     if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
     std::vector<int> D(128 * 16);
     cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
@@ -90,18 +90,19 @@ int main() {
     printf("i8 check: %d mismatches of 2048 (D[0][0] = %d)\n", bad, D[0]);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     int nsm = 0; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+    for (int N = 256; N >= 32; N >>= 1)
     for (int kind = 0; kind < 2; ++kind) {
         const int iters = 20000;
-        i8_kernel<<<nsm, 128, smem>>>(dA, dB, dD, 2000, kind);
+        i8_kernel<<<nsm, 128, smem>>>(dA, dB, dD, 2000, kind, N);
         cudaEventRecord(e0);
-        i8_kernel<<<nsm, 128, smem>>>(dA, dB, dD, iters, kind);
+        i8_kernel<<<nsm, 128, smem>>>(dA, dB, dD, iters, kind, N);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         const double kk = kind == 0 ? 128.0 : 64.0;  // K elements per 4 k-steps
-        const double mac = (double)nsm * iters * 128.0 * 256.0 * kk;
-        printf("{\"kind\": \"%s\", \"sms\": %d, \"ms\": %.3f, \"tera_mac_per_s\": %.1f, \"tera_ops_per_s\": %.1f}\n", kind == 0 ? "i8" : "bf16", nsm, ms,
-               mac / ms / 1e9, 2 * mac / ms / 1e9);
+        const double mac = (double)nsm * iters * 128.0 * N * kk;
+        printf("{\"kind\": \"%s\", \"N\": %d, \"sms\": %d, \"ms\": %.3f, \"tera_ops_per_s\": %.1f, \"cycles_per_mma\": %.1f}\n", kind == 0 ? "i8" : "bf16", N, nsm,
+               ms, 2 * mac / ms / 1e9, ms * 1e-3 * 1.965e9 / (iters * 4.0));
     }
     return 0;
 }
