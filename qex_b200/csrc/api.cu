@@ -295,6 +295,7 @@ int qexxc_create_ex(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngri
         wsyrk_workspace(c->num_sms, c->Nc, c->GpadMax, c->B, C == 4, &part_doubles, &c->ws_items_bytes,
                         &c->ws_start_cap);
         QX_A(c->part, part_doubles);
+        c->part_doubles = part_doubles;
         for (int k = 0; k < 2; ++k) {
             unsigned char* p = nullptr;
             if (rc == QEXXC_OK) rc = dev_alloc(c, &p, c->ws_items_bytes);
@@ -347,6 +348,7 @@ int qexxc_destroy(qexxc_ctx* c) {
     if (!c) return QEXXC_OK;
     cudaSetDevice(c->device);
     for (void* p : c->allocs) cudaFree(p);
+    i8_release(c);
     delete c;
     return QEXXC_OK;
 }

@@ -112,12 +112,11 @@ struct qexxc_ctx {
     double* vgammab = nullptr;  // [B][GpadMax]
     double* aow = nullptr;      // [B][GpadMax][Npad] (C == 4 only)
     double* rq_part = nullptr;  // rowquad split-tail partials [NT][4][num_sms][128]
-    void *i8_A = nullptr, *i8_B = nullptr;  // INT8 digit tiles of ao_0 / S (contract_i8.cu, opt-in QEXXC_I8=1)
-    float* i8_sa = nullptr;
-    double* i8_sb = nullptr;
-    bool i8_valid = false;
+    void* i8ws = nullptr;       // INT8 (Ozaki) contraction workspace: digit planes of ao_0 / S / the weighted operand (contract_i8.cu)
+    bool i8_valid = false;      // the geometry-dependent digit planes match the current ao
     double* rq_pair = nullptr;  // rowquad pair-mode partials [2][4][GpadMax] (single-molecule contexts with wide N)
     double* part = nullptr;     // wsyrk partial tiles, one compact [BN][BN] slot per (batch, tile, grid chunk)
+    size_t part_doubles = 0;
     void* ws_items[2] = {nullptr, nullptr};  // wsyrk static schedules (general, symmetric)
     int* ws_start[2] = {nullptr, nullptr};
     long ws_key[2] = {-1, -1};
@@ -182,9 +181,11 @@ int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const doub
 // aow[b][g][n] = sum_c f[c] wv[b][c][g] ao[b][c][g][n]
 int launch_build_aow(qexxc_ctx* c, const double* wv, long wv_bstride, long wv_cstride, const double* fac4,
                      cudaStream_t st);
-// contract_i8.cu: exact INT8 (Ozaki) form of rowquad on tcgen05, opt-in
-bool rowquad_i8_enabled(const qexxc_ctx* c);
+// contract_i8.cu: exact INT8 (Ozaki) form of rowquad / wsyrk on tcgen05 (QEXXC_I8=0/1; default: nao >= 256, single molecule)
+bool i8_enabled(const qexxc_ctx* c);
+void i8_release(qexxc_ctx* c);
 int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_cstride, cudaStream_t st);
+int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st);
 // ao.cu
 int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st);
 int launch_pack_ao(qexxc_ctx* c, const double* src, int ncomp, int G, cudaStream_t st);

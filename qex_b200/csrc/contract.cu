@@ -998,7 +998,7 @@ static bool rowquad_pair_masks(const qexxc_ctx* c, int tri, int nbulk, unsigned*
 
 int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride,
                    long q_cstride, cudaStream_t st) {
-    if (rowquad_i8_enabled(c)) return launch_rowquad_i8(c, ncomp, tri, fac4, q, q_cstride, st);
+    if (i8_enabled(c)) return launch_rowquad_i8(c, ncomp, tri, fac4, q, q_cstride, st);
     const int BN = pick_bn(c->Nc), NT = (c->Nc + BN - 1) / BN, T = c->Gpad / BM;
     const int ntail = rowquad_tail_tiles(c, tri), nbulk = T - ntail;
     unsigned m0 = 0, m1 = 0;
@@ -1032,6 +1032,7 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double*
 
 int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bsrc, double scale, int tadd,
                  double* out, long out_bstride, cudaStream_t st) {
+    if (i8_enabled(c)) return launch_wsyrk_i8(c, s, Bsrc, scale, tadd, out, st);
     const bool sym = (Bsrc == nullptr);
     WsPlan plan;
     QX_TRY(ws_schedule(c, sym, plan, st));

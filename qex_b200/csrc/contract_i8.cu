@@ -1,28 +1,33 @@
-// Stage 2 / 4-transposed on the INT8 tensor cores: an EXACT integer split (Ozaki scheme) of the FP64 product
-//     q_c[g] = fac_c * sum_ij ao_c[g,i] S[i,j] ao_0[g,j]                      (rowquad of contract.cu)
-// The FP64 DMMA path saturates the FP64 pipe (0.99 of cuBLAS DGEMM); this path does not use it for the N^2 work:
+// Stages 2 and 4 on the INT8 tensor cores: an EXACT integer split (Ozaki scheme) of the two FP64 contractions
+//     rowquad:  q_c[g]  = fac_c * sum_ij ao_c[g,i] S[i,j] ao_0[g,j]                (numint_legacy.py:351-410, eval_rho)
+//     wsyrk:    H[i,j]  = sum_g ao_0[g,i] s[g] ao_0[g,j]   or   sum_g ao_0[g,i] B[g,j] (numint_legacy.py:432-456, V_xc)
+// The FP64 DMMA kernels of contract.cu run at 0.96-0.99 of the FP64 tensor pipe; this path does not use that pipe for
+// the N^2 G work.  Both operands of a product are written in fixed point relative to a per-row / per-column power of
+// two and cut into six balanced base-256 digits,
 //
-//   ao_0[g,:] = 2^(ea[g]-48) * sum_k A_k[g,:] 256^k,   S[:,j] = 2^(eb[j]-48) * sum_l B_l[:,j] 256^l,   A_k, B_l in [-128, 127]
-//   (ao_0 S)[g,j] ~= 2^(ea[g]+eb[j]-56) * sum_{d=0..5} 256^(5-d) * sum_{s+t=d} (A^(s) B^(t))[g,j]     (s = 5-k, t = 5-l)
+//   x[m,k] = 2^(ea[m]-46) * sum_s A^(s)[m,k] 256^(5-s),   y[n,k] = 2^(eb[n]-46) * sum_t B^(t)[n,k] 256^(5-t),   digits in [-128, 127]
+//   (x y^T)[m,n] ~= 2^(ea[m]+eb[n]-52) * sum_{d=0..5} 256^(5-d) * sum_{s+t=d} (A^(s) B^(t)^T)[m,n]
 //
-// six balanced 8-bit digits per operand (46 bits relative to the row / column maximum), the 21 digit products with
-// s + t <= 5, each an exact INT8 x INT8 -> INT32 GEMM on tcgen05 (kind::i8): 14 bits per product + log2(N <= 1024) and at
-// most six products per diagonal stay below 2^27.  Measured on the c5 operands (tests/studies/ozaki_study.py): rho to 1.6e-11 of its
-// largest element, i.e. inside the 1e-10 bar of the FP64 path; the digits of a diagonal share one TMEM accumulator, the
-// six accumulators are combined in 64-bit integers (exact) and converted to FP64 twice per element (high / low half).
+// the 21 digit products with s + t <= 5 are exact INT8 x INT8 -> INT32 GEMMs on tcgen05 (kind::i8); the digits of one
+// diagonal d share a TMEM accumulator, the six accumulators are recombined exactly in 64-bit integers and rounded to FP64
+// once.  What is dropped (s + t >= 6) is below 2^-45 of (row maximum) x (column maximum).
 //
-// tcgen05.mma has a floor of ~105 cycles per instruction for N <= 128 (scripts/probe/i8_rate.cu: N = 64 runs at a third of
-// the N = 256 rate), so the products of one A digit plane with ALL the B planes it meets are ONE instruction: the B
-// planes of a k-chunk sit in shared memory as a single [6 x 64 rows] K-major tile and the accumulators of consecutive
-// diagonals are adjacent TMEM column ranges, so A^(s) x [B^(0); ...; B^(5-s)] lands in accumulators s ... 5 (N = 64 (6 - s),
-// split at 256): 8 instructions per k-step instead of 21.
+// tcgen05.mma has a floor of ~105 cycles per instruction for N <= 128 (scripts/probe/i8_rate.cu), so the products of one
+// A digit plane with ALL the B planes it meets are ONE instruction: the B planes of a k-chunk sit in shared memory as a
+// single [6 x 64 rows] K-major tile and the accumulators of consecutive diagonals are adjacent TMEM column ranges, so
+// A^(s) x [B^(0); ...; B^(5-s)] lands in accumulators s ... 5 (N = 64 (6 - s), split at 256).
 //
-// Pipeline (one CTA per 128 grid rows, 6 warps): warp 0 streams digit tiles with 1-D bulk copies (the slicing kernels
-// write them in the 128-byte-swizzled K-major tile layout, so no tensor maps are needed) -- the six B tiles of a
-// 128-wide k-chunk once, the six A tiles through a 4-deep ring; warp 1 issues the tcgen05.mma stream; warps 2..5 drain
-// the accumulators (tcgen05.ld), recombine, scale and row-dot with the FP64 ao rows.
+// One pipeline serves both contractions (one CTA = one 128 x 64 output tile, 10 warps): warp 0 streams digit tiles with
+// 1-D bulk copies (the slicing kernels write them in the 128-byte-swizzled K-major tile layout, so no tensor maps are
+// needed), warp 1 issues the tcgen05.mma stream, warps 2..9 drain the accumulators (tcgen05.ld).
+//   rowquad: M = 128 grid rows (row-scaled digits of ao_0), N = 64 columns of S, K = AO index; the epilogue row-dots the
+//            recombined (ao_0 S) tile with the FP64 ao_c rows.
+//   wsyrk:   M = 128 AO rows i, N = 64 AO columns j, K = grid index.  The fixed-point exponents are per COLUMN of ao and
+//            per block of 4096 grid rows (block floating point along K); the INT32 accumulators are drained into FP64
+//            registers at every block boundary, where the block's scales are applied.
 //
-// Opt-in (QEXXC_I8=1): the slices cost 6 bytes per AO value of extra memory and one pass over the AO tensor per geometry.
+// Policy: QEXXC_I8=1 forces this path, QEXXC_I8=0 the FP64 DMMA path; unset = this path when nao >= 256 (single-molecule
+// contexts).  Cost: 18 bytes of digit planes per AO value of component 0.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -31,79 +36,96 @@ namespace {
 using namespace tc05;
 
 constexpr int ND = 6;            // digits per operand
-constexpr int IM = 128;          // grid rows per CTA
-constexpr int IN = 64;           // columns per tile (6 accumulators x 64 columns = 384 of the 512 TMEM columns)
+constexpr int IM = 128;          // output rows per CTA
+constexpr int IN = 64;           // output columns per CTA (6 accumulators x 64 columns = 384 of the 512 TMEM columns)
 constexpr int KC = 128;          // k-chunk: 128 int8 = one 128-byte swizzled row
 constexpr uint32_t ATILE = IM * KC;  // 16 KB
 constexpr uint32_t BTILE = IN * KC;  // 8 KB
-constexpr int NA = 4;            // A-tile ring depth
-constexpr int NEW = 8;           // epilogue warps: 4 TMEM lane quadrants x 2 column halves
+constexpr int NA = 6;            // A-tile ring depth = one slot per digit plane (slot index is a compile-time constant)
+constexpr int NEW = 16;          // epilogue warps: 4 TMEM lane quadrants x 4 column groups
+constexpr int CW = IN / (NEW / 4);  // columns of a tile per epilogue warp
 constexpr int I8_THREADS = 64 + 32 * NEW;
+constexpr int KDC = 32;          // wsyrk: k-chunks per exponent block (4096 grid rows between accumulator drains; INT32 is safe to 16384)
+
+// x * scale rounded to an integer v (|v| <= 2^46), returned as w = v + 0x808080808080: byte k of w, XOR 0x80, is the
+// balanced base-256 digit k of v (least significant first)
+__device__ __forceinline__ void to_w48(double x, double scale, uint32_t& lo, uint32_t& hi) {
+    const double d = fma(x, scale, 6755399441055744.0);  // 1.5 * 2^52: the integer sits in the low mantissa bits
+    const unsigned long long w = (unsigned long long)__double_as_longlong(d) + (0x0000808080808080ull - 0x4338000000000000ull);
+    lo = (uint32_t)w;
+    hi = (uint32_t)(w >> 32);
+}
+// byte b (0..3) of four words -> one word
+__device__ __forceinline__ uint32_t pack_byte(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int b) {
+    const uint32_t sel = (uint32_t)b | ((uint32_t)(4 + b) << 4);
+    return __byte_perm(__byte_perm(a0, a1, sel), __byte_perm(a2, a3, sel), 0x5410);
+}
+// digit plane s (0 = most significant) of four consecutive values
+__device__ __forceinline__ uint32_t plane_word(const uint32_t (&lo)[4], const uint32_t (&hi)[4], int s) {
+    const int b = ND - 1 - s;
+    const uint32_t w = b < 4 ? pack_byte(lo[0], lo[1], lo[2], lo[3], b) : pack_byte(hi[0], hi[1], hi[2], hi[3], b - 4);
+    return w ^ 0x80808080u;
+}
+__device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
 
 __device__ __forceinline__ uint32_t tile_off(int r, int c) {  // byte offset of (row r, k c) inside a swizzled tile
     return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((((c >> 4) ^ (r & 7)) << 4) | (c & 15));
 }
 
-// balanced base-256 digits of v (|v| < 2^46), least significant first
-__device__ __forceinline__ void digits6(long long v, int (&d)[ND]) {
-#pragma unroll
-    for (int k = 0; k < ND; ++k) {
-        const int low = (int)(((v + 128) & 255) - 128);
-        d[k] = low;
-        v = (v - low) >> 8;
-    }
-}
-
 // ---- slicing kernels ----------------------------------------------------------------------------------------------
-// A8[s][row tile][k-chunk][16 KB tile], s = 0 most significant; ea[g]: x = 2^(ea-48) * sum digits.  One warp per row.
-__global__ void __launch_bounds__(256) slice_ao_kernel(const double* __restrict__ ao, int Npad, int nkc, long Gpad,
-                                                       signed char* __restrict__ A8, float* __restrict__ sa) {
-    const long g = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+// Row-scaled planes of ao_0 (rowquad A operand): A8[s][row tile][k-chunk][16 KB tile]; sa[g] = exponent e, |ao[g,:]| < 2^e.
+// One warp per grid row; NKC k-chunks of the row live in registers between the maximum and the digit pass.
+template <int NKC>
+__global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ ao, int Npad, int nkc, long Gpad,
+                                                         signed char* __restrict__ A8, float* __restrict__ sa) {
+    __shared__ __align__(16) uint32_t stage[8][ND][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long g = (long)blockIdx.x * 8 + warp;
     if (g >= Gpad) return;
     const double* row = ao + g * Npad;
-    const long tile = g >> 7;
+    const long tile = g >> 7, nt = Gpad >> 7;
     const int r = (int)(g & 127);
-    const long nt = Gpad >> 7;
-    // pass 1: row maximum
+    double x[NKC][4];
     double mx = 0.0;
-    for (int c = lane * 2; c < Npad; c += 64) {
-        const double2 v = *reinterpret_cast<const double2*>(row + c);
-        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+#pragma unroll
+    for (int kc = 0; kc < NKC; ++kc) {
+        const int c = kc * KC + lane * 4;
+        if (c < Npad) {  // Npad is a multiple of 32: the four columns are inside or outside together
+            const double2 u = *reinterpret_cast<const double2*>(row + c), v = *reinterpret_cast<const double2*>(row + c + 2);
+            x[kc][0] = u.x, x[kc][1] = u.y, x[kc][2] = v.x, x[kc][3] = v.y;
+        } else {
+            x[kc][0] = x[kc][1] = x[kc][2] = x[kc][3] = 0.0;
+        }
+        mx = fmax(fmax(mx, fmax(fabs(x[kc][0]), fabs(x[kc][1]))), fmax(fabs(x[kc][2]), fabs(x[kc][3])));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     int e = 0;
-    if (mx > 0.0) {
-        (void)frexp(mx, &e);  // mx = m 2^e, m in [0.5, 1)
-        e += 2;               // |x| / 2^e < 0.25: the top balanced digit stays below 65 after carries
-    }
+    if (mx > 0.0) (void)frexp(mx, &e);  // mx = m 2^e, m in [0.5, 1)
+    if (e < -900) e = -900;
     if (lane == 0) sa[g] = (float)e;
-    const double scale = ldexp(1.0, 48 - e);
-    // pass 2: lane owns 16 consecutive columns (one 16-byte chunk) per step
-    for (int c0 = lane * 16; c0 < nkc * KC; c0 += 512) {
-        unsigned w[ND][4];
+    const double scale = pow2(46 - e);
 #pragma unroll
-        for (int s = 0; s < ND; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+    for (int kc = 0; kc < NKC; ++kc) {
+        if (kc >= nkc) break;
+        uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int c = c0 + j;
-            const double x = c < Npad ? row[c] : 0.0;
-            int d[ND];
-            digits6(__double2ll_rn(x * scale), d);
+        for (int j = 0; j < 4; ++j) to_w48(x[kc][j], scale, lo[j], hi[j]);
 #pragma unroll
-            for (int s = 0; s < ND; ++s) w[s][j >> 2] |= (unsigned)(d[ND - 1 - s] & 0xff) << (8 * (j & 3));
+        for (int s = 0; s < ND; ++s) stage[warp][s][(((lane >> 2) ^ (r & 7)) << 2) | (lane & 3)] = plane_word(lo, hi, s);
+        __syncwarp();
+        for (int idx = lane; idx < ND * 8; idx += 32) {
+            const int s = idx >> 3, ch = idx & 7;
+            const uint4 v = *reinterpret_cast<const uint4*>(&stage[warp][s][ch * 4]);
+            signed char* t = A8 + (((long)s * nt + tile) * nkc + kc) * ATILE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + ch * 16;
+            *reinterpret_cast<uint4*>(t) = v;
         }
-        const int kc = c0 >> 7, cc = c0 & 127;
-#pragma unroll
-        for (int s = 0; s < ND; ++s) {
-            signed char* t = A8 + (((long)s * nt + tile) * nkc + kc) * ATILE + tile_off(r, cc);
-            *reinterpret_cast<uint4*>(t) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
-        }
+        __syncwarp();
     }
 }
 
-// B8[t][column tile (64)][k-chunk][8 KB tile]: B[n = j][k = i] = S[i][j]; sb[j] = 2^(eb[j]-56).  One block per column j.
+// Column-scaled planes of S (rowquad B operand): B8[t][column tile (64)][k-chunk][8 KB tile], B[n = j][k = i] = S[i][j];
+// sb[j] = 2^(eb[j]-52).  One block per column j.
 __global__ void __launch_bounds__(256) slice_s_kernel(const double* __restrict__ S, int ldS, int Nc, int nkc, int nct,
                                                       signed char* __restrict__ B8, double* __restrict__ sb) {
     const int j = blockIdx.x;
@@ -119,69 +141,287 @@ __global__ void __launch_bounds__(256) slice_s_kernel(const double* __restrict__
     }
     mx = red[0];
     int e = 0;
-    if (mx > 0.0) {
-        (void)frexp(mx, &e);
-        e += 2;
-    }
-    if (threadIdx.x == 0) sb[j] = ldexp(1.0, e - 56);
-    const double scale = ldexp(1.0, 48 - e);
+    if (mx > 0.0) (void)frexp(mx, &e);
+    if (e < -900) e = -900;
+    if (threadIdx.x == 0) sb[j] = pow2(e - 52);
+    const double scale = pow2(46 - e);
     const int ct = j / IN, r = j % IN;
     for (int i = threadIdx.x; i < nkc * KC; i += blockDim.x) {
         const double x = (j < Nc && i < Nc) ? S[(long)i * ldS + j] : 0.0;
-        int d[ND];
-        digits6(__double2ll_rn(x * scale), d);
+        uint32_t lo, hi;
+        to_w48(x, scale, lo, hi);
+        const unsigned long long w = (((unsigned long long)hi << 32) | lo) ^ 0x0000808080808080ull;
         const int kc = i >> 7, c = i & 127;
 #pragma unroll
         for (int t = 0; t < ND; ++t)
-            B8[(((long)t * nct + ct) * nkc + kc) * BTILE + tile_off(r, c)] = (signed char)d[ND - 1 - t];
+            B8[(((long)t * nct + ct) * nkc + kc) * BTILE + tile_off(r, c)] = (signed char)(w >> (8 * (ND - 1 - t)));
     }
 }
 
-// ---- the contraction ----------------------------------------------------------------------------------------------
-struct I8Args {
-    const signed char* A8;
-    const signed char* B8;
-    const float* sa;
-    const double* sb;
+// cmax[sub][col] >= max over the 128 grid rows of sub-block `sub` of |x[g][col]| (rounded up to float)
+__global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ x, int ld, int NpadK, float* __restrict__ cmax) {
+    const long g0 = (long)blockIdx.x * 128;
+    for (int c = 4 * threadIdx.x; c < NpadK; c += 1024) {
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+        if (c < ld) {
+            const double* p = x + g0 * ld + c;
+#pragma unroll 8
+            for (int r = 0; r < 128; ++r) {
+                const double2 u = *reinterpret_cast<const double2*>(p + (long)r * ld), v = *reinterpret_cast<const double2*>(p + (long)r * ld + 2);
+                m0 = fmax(m0, fabs(u.x)), m1 = fmax(m1, fabs(u.y)), m2 = fmax(m2, fabs(v.x)), m3 = fmax(m3, fabs(v.y));
+            }
+        }
+        *reinterpret_cast<float4*>(cmax + (long)blockIdx.x * NpadK + c) =
+            make_float4(__double2float_ru(m0), __double2float_ru(m1), __double2float_ru(m2), __double2float_ru(m3));
+    }
+}
+
+// Block exponents of the wsyrk operands: eexp[blk][col] = e with |s[g] x[g][col]| < 2^e for the (up to) 4096 grid rows of
+// block blk.  Exact for s == nullptr; with weights it is the bound  max_sub (max_{g in sub} |s[g]|) * cmax[sub][col]  over
+// the block's 128-row sub-blocks (tight up to the variation of s inside 128 consecutive grid points).
+__global__ void __launch_bounds__(256) blk_exp_kernel(const float* __restrict__ cmax, const double* __restrict__ s, int ngc, int NpadK,
+                                                      int* __restrict__ eexp) {
+    __shared__ float smax[KDC];
+    const int blk = blockIdx.x, gc0 = blk * KDC, nsub = min(KDC, ngc - gc0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int sub = warp; sub < nsub; sub += 8) {
+        float m = 1.0f;
+        if (s) {
+            const double* p = s + ((long)(gc0 + sub) * 128) + lane * 4;
+            double d = fmax(fmax(fabs(p[0]), fabs(p[1])), fmax(fabs(p[2]), fabs(p[3])));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+            m = __double2float_ru(d);
+        }
+        if (lane == 0) smax[sub] = m;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < NpadK; c += 256) {
+        float m = 0.0f;
+        for (int sub = 0; sub < nsub; ++sub) m = fmaxf(m, __fmul_ru(smax[sub], cmax[(long)(gc0 + sub) * NpadK + c]));
+        int e = 0;
+        if (m > 0.0f) (void)frexpf(m, &e);
+        if (m > 3.0e38f) e = 129;  // overflowed bound (inf): keep the shift finite
+        eexp[(long)blk * NpadK + c] = e;
+    }
+}
+
+// Column-scaled planes of x[g][col] (* s[g]) for wsyrk, K = grid index:  P[plane][g-chunk][column tile (64)][8 KB tile],
+// tile row = column, tile byte = grid row inside the 128-row chunk.  One CTA per (g-chunk, 128 columns); a thread owns
+// one column and 16 consecutive grid rows = one 16-byte chunk per plane, staged in shared memory in the final layout.
+__global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restrict__ x, int ld, const double* __restrict__ s,
+                                                         const int* __restrict__ eexp, int NpadK, int njt, long plane_stride,
+                                                         signed char* __restrict__ P) {
+    extern __shared__ __align__(1024) unsigned char stage[];  // [ND][128 columns][128 bytes]
+    const int gc = blockIdx.x, cg = blockIdx.y, blk = gc / KDC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long g0 = (long)gc * 128 + 16 * warp;
+    double sv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sv[k] = s ? s[g0 + k] : 1.0;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        const int r = q * 32 + lane, col = cg * 128 + r;
+        const double scale = pow2(46 - eexp[(long)blk * NpadK + col]);
+        double v[16];
+        if (col < ld) {
+            const double* p = x + g0 * ld + col;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = p[(long)k * ld];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = 0.0;
+        }
+        uint32_t lo[16], hi[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) to_w48(v[k] * sv[k], scale, lo[k], hi[k]);
+#pragma unroll
+        for (int pl = 0; pl < ND; ++pl) {
+            uint4 w;
+            {
+                const uint32_t l0[4] = {lo[0], lo[1], lo[2], lo[3]}, h0[4] = {hi[0], hi[1], hi[2], hi[3]};
+                w.x = plane_word(l0, h0, pl);
+                const uint32_t l1[4] = {lo[4], lo[5], lo[6], lo[7]}, h1[4] = {hi[4], hi[5], hi[6], hi[7]};
+                w.y = plane_word(l1, h1, pl);
+                const uint32_t l2[4] = {lo[8], lo[9], lo[10], lo[11]}, h2[4] = {hi[8], hi[9], hi[10], hi[11]};
+                w.z = plane_word(l2, h2, pl);
+                const uint32_t l3[4] = {lo[12], lo[13], lo[14], lo[15]}, h3[4] = {hi[12], hi[13], hi[14], hi[15]};
+                w.w = plane_word(l3, h3, pl);
+            }
+            *reinterpret_cast<uint4*>(stage + pl * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((warp ^ (r & 7)) << 4)) = w;
+        }
+    }
+    __syncthreads();
+    // 128 columns = two consecutive 8 KB column tiles = 16 KB contiguous per plane
+    for (int pl = 0; pl < ND; ++pl) {
+        uint4* dst = reinterpret_cast<uint4*>(P + pl * plane_stride + ((long)gc * njt + cg * 2) * BTILE);
+        const uint4* src = reinterpret_cast<const uint4*>(stage + pl * 16384);
+        for (int i = threadIdx.x; i < 1024; i += 256) dst[i] = src[i];
+    }
+}
+
+// ---- the shared pipeline --------------------------------------------------------------------------------------------
+struct Pipe {
+    unsigned char *As, *Bs;
+    uint64_t *fullB, *emptyB, *fullA, *emptyA, *tfull, *tempty;
+};
+
+// A "schedule" names the output units of a CTA (column tiles of a row tile / exponent blocks of an output tile) and,
+// per unit, the k-chunk range and where its digit tiles are.
+struct RqSched {
+    const signed char *A, *B;
+    long a_plane, b_plane, tile;
+    int nkc, nct, Nc, tri, dbg;
+    __device__ int nunits() const { return nct; }
+    __device__ int kbeg(int) const { return 0; }
+    __device__ int kend(int ct) const {
+        if (!tri) return (Nc + KC - 1) / KC;
+        const int last = min(Nc, (ct + 1) * IN);  // S is upper triangular: rows i <= last column only
+        return (last + KC - 1) / KC;
+    }
+    __device__ long aoff(int, int kc) const { return (tile * nkc + kc) * (long)ATILE; }
+    __device__ long boff(int ct, int kc) const { return ((long)ct * nkc + kc) * (long)BTILE; }
+};
+struct WsSched {
+    const signed char *A, *B;
+    long a_plane, b_plane;
+    int it, jt, njt, ngc, blk0, blk1, dbg;
+    __device__ int nunits() const { return blk1 - blk0; }
+    __device__ int kbeg(int u) const { return (blk0 + u) * KDC; }
+    __device__ int kend(int u) const { return min(ngc, (blk0 + u + 1) * KDC); }
+    __device__ long aoff(int, int gc) const { return ((long)gc * njt + 2 * it) * (long)BTILE; }
+    __device__ long boff(int, int gc) const { return ((long)gc * njt + jt) * (long)BTILE; }
+};
+
+__device__ __forceinline__ Pipe pipe_setup(unsigned char* smem_raw, uint32_t** tslot) {
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    Pipe p;
+    p.Bs = base;                   // [2][ND][BTILE]
+    p.As = base + 2 * ND * BTILE;  // [NA][ATILE]
+    uint64_t* bars = (uint64_t*)(p.As + NA * ATILE);
+    p.fullB = bars, p.emptyB = bars + 2, p.fullA = bars + 4, p.emptyA = bars + 4 + NA, p.tfull = bars + 4 + 2 * NA,
+    p.tempty = bars + 5 + 2 * NA;
+    *tslot = (uint32_t*)(bars + 6 + 2 * NA);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(p.fullB + i, 1);
+            mbar_init(p.emptyB + i, 1);
+        }
+        for (int i = 0; i < NA; ++i) {
+            mbar_init(p.fullA + i, 1);
+            mbar_init(p.emptyA + i, 1);
+        }
+        mbar_init(p.tfull, 1);
+        mbar_init(p.tempty, NEW);  // one arrival per epilogue warp
+        mbar_fence_init();
+    }
+    return p;
+}
+
+template <class S>
+__device__ __forceinline__ void i8_produce(const S& sc, const Pipe& p) {
+    int itB = 0;
+    const int nu = sc.nunits();
+    for (int u = 0; u < nu; ++u) {
+        const int k1 = sc.kend(u);
+        for (int kc = sc.kbeg(u); kc < k1; ++kc, ++itB) {
+            const int kb = itB & 1;
+            mbar_wait(p.emptyB + kb, ((itB >> 1) & 1) ^ 1);
+            const signed char* bsrc = sc.B + sc.boff(u, kc);
+            mbar_expect_tx(p.fullB + kb, ND * BTILE);
+            for (int t = 0; t < ND; ++t) bulk_g2s(p.Bs + ((size_t)kb * ND + t) * BTILE, bsrc + t * sc.b_plane, BTILE, p.fullB + kb);
+            const signed char* asrc = sc.A + sc.aoff(u, kc);
+            for (int s = 0; s < ND; ++s) {
+                mbar_wait(p.emptyA + s, (itB & 1) ^ 1);
+                mbar_expect_tx(p.fullA + s, ATILE);
+                bulk_g2s(p.As + (size_t)s * ATILE, asrc + s * sc.a_plane, ATILE, p.fullA + s);
+            }
+        }
+    }
+}
+
+// The MMA stream, executed by one whole (converged) warp so that every operand is warp-uniform; the instructions themselves
+// are issued by one elected lane.  Fully unrolled over the six A planes and the four 32-byte k-steps of a k-chunk.
+template <class S>
+__device__ __forceinline__ void i8_issue(const S& sc, const Pipe& p, uint32_t tm) {
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, descriptor version 1, SWIZZLE_128B
+    const uint32_t sA = smem_u32(p.As), sB = smem_u32(p.Bs);
+    const uint32_t alo0 = ((sA >> 4) & 0x3FFFu) | (1u << 16), blo0 = ((sB >> 4) & 0x3FFFu) | (1u << 16);
+    int itB = 0;
+    const int nu = sc.nunits();
+    for (int u = 0; u < nu; ++u) {
+        mbar_wait(p.tempty, (u & 1) ^ 1);  // the epilogue has drained the accumulators of the previous unit
+        tc_fence_after();
+        const int k0 = sc.kbeg(u), k1 = sc.kend(u);
+        for (int kc = k0; kc < k1; ++kc, ++itB) {
+            const int kb = itB & 1;
+            mbar_wait(p.fullB + kb, (itB >> 1) & 1);
+            const uint32_t blo = blo0 + (uint32_t)kb * (ND * BTILE >> 4);
+            const uint32_t first = (uint32_t)(kc != k0);
+#pragma unroll
+            for (int s = 0; s < ND; ++s) {  // A ring slot == plane (NA == ND)
+                mbar_wait(p.fullA + s, itB & 1);
+                tc_fence_after();
+                // A^(s) x [B^(0); ...; B^(5-s)] -> accumulators s ... 5 (adjacent TMEM columns), N <= 256 per instruction
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int ntot = (ND - s) * IN;
+                const int n0 = ntot > 256 ? 256 : ntot;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (s != 0 || k != 0) ? 1u : first;
+                        const uint32_t alo = alo0 + (uint32_t)s * (ATILE >> 4) + (uint32_t)k * 2u;
+                        mma_i8_lohi(tm + (uint32_t)s * IN, alo, blo + (uint32_t)k * 2u, DESC_HI, idesc_i8(IM, n0), acc);
+                        if (ntot > 256)
+                            mma_i8_lohi(tm + (uint32_t)s * IN + 256, alo, blo + (4 * BTILE >> 4) + (uint32_t)k * 2u, DESC_HI,
+                                        idesc_i8(IM, ntot - 256), acc);
+                    }
+                    mma_commit(p.emptyA + s);  // the slot is free once these MMAs have read it
+                    if (s == ND - 1) mma_commit(p.emptyB + kb);
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) mma_commit(p.tfull);
+        __syncwarp();
+    }
+}
+
+// eight columns (c0 ...) of the six diagonal accumulators of this thread's TMEM lane -> T[j] = sum_d P_d 256^(5-d), exact in
+// two 64-bit halves, rounded to FP64 once
+__device__ __forceinline__ void drain8(uint32_t tm, int qd, int c0, double (&T)[8]) {
+    uint32_t v[ND][8];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) tmem_ld8(tmem_addr(tm, 32 * qd, d * IN + c0), v[d]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const long long hi = ((long long)(int)v[0][j] << 16) + ((long long)(int)v[1][j] << 8) + (long long)(int)v[2][j];
+        const long long lo = ((long long)(int)v[3][j] << 16) + ((long long)(int)v[4][j] << 8) + (long long)(int)v[5][j];
+        T[j] = fma((double)hi, 16777216.0, (double)lo);
+    }
+}
+
+// ---- rowquad ----------------------------------------------------------------------------------------------------------
+struct RqArgs {
+    RqSched sc;        // tile filled in by the CTA
+    const float* sa;   // row exponents
+    const double* sb;  // column scales 2^(eb-52)
     const double* ao;  // FP64 ao rows for the row-dot epilogue
     double* q;
     long ao_cstride, q_cstride;
-    int Npad, Nc, nkc, nct, nctB, ncomp, tri;  // nct: column tiles that hold data; nctB: column tiles of the B8 layout
-    long ntiles;
+    int Npad, ncomp;
     double f[4];
 };
 
-__device__ __forceinline__ int i8_kend(const I8Args& a, int ct) {
-    if (!a.tri) return (a.Nc + KC - 1) / KC;
-    const int last = min(a.Nc, (ct + 1) * IN);  // S is upper triangular: rows i <= last column only
-    return (last + KC - 1) / KC;
-}
-
-__global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const I8Args a) {
+__global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* Bs = base;                        // [2][ND][BTILE]
-    unsigned char* As = base + 2 * ND * BTILE;       // [NA][ATILE]
-    uint64_t* bars = (uint64_t*)(As + NA * ATILE);
-    uint64_t *fullB = bars, *emptyB = bars + 2, *fullA = bars + 4, *emptyA = bars + 4 + NA, *tfull = bars + 4 + 2 * NA,
-             *tempty = bars + 5 + 2 * NA;
-    uint32_t* tslot = (uint32_t*)(bars + 6 + 2 * NA);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long tile = blockIdx.x;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(fullB + i, 1);
-            mbar_init(emptyB + i, 1);
-        }
-        for (int i = 0; i < NA; ++i) {
-            mbar_init(fullA + i, 1);
-            mbar_init(emptyA + i, 1);
-        }
-        mbar_init(tfull, 1);
-        mbar_init(tempty, NEW);  // one arrival per epilogue warp
-        mbar_fence_init();
-    }
+    uint32_t* tslot;
+    const Pipe p = pipe_setup(smem_raw, &tslot);
+    const int warp = warp_uniform_idx(), lane = threadIdx.x & 31;
+    RqSched sc = a.sc;
+    sc.tile = blockIdx.x;
     if (warp == 1) tmem_alloc(tslot, 512);
     tc_fence_before();
     __syncthreads();
@@ -189,120 +429,83 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const I8Args 
     const uint32_t tm = *tslot;
 
     if (warp == 0) {
-        // ---------------- producer ----------------
-        if (lane == 0) {
-            int itB = 0, itA = 0;
-            for (int ct = 0; ct < a.nct; ++ct) {
-                const int kend = i8_kend(a, ct);
-                for (int kc = 0; kc < kend; ++kc, ++itB) {
-                    const int kb = itB & 1;
-                    mbar_wait(emptyB + kb, ((itB >> 1) & 1) ^ 1);
-                    mbar_expect_tx(fullB + kb, ND * BTILE);
-                    for (int t = 0; t < ND; ++t)
-                        bulk_g2s(Bs + ((size_t)kb * ND + t) * BTILE, a.B8 + (((long)t * a.nctB + ct) * a.nkc + kc) * BTILE, BTILE,
-                                 fullB + kb);
-                    for (int s = 0; s < ND; ++s, ++itA) {
-                        const int sl = itA % NA;
-                        mbar_wait(emptyA + sl, ((itA / NA) & 1) ^ 1);
-                        mbar_expect_tx(fullA + sl, ATILE);
-                        bulk_g2s(As + (size_t)sl * ATILE, a.A8 + (((long)s * a.ntiles + tile) * a.nkc + kc) * ATILE, ATILE,
-                                 fullA + sl);
-                    }
-                }
-            }
-        }
+        if (lane == 0) i8_produce(sc, p);
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            const uint32_t sA = smem_u32(As), sB = smem_u32(Bs);
-            int itB = 0, itA = 0;
-            for (int ct = 0; ct < a.nct; ++ct) {
-                const int kend = i8_kend(a, ct);
-                mbar_wait(tempty, (ct & 1) ^ 1);  // the epilogue has drained the accumulators of the previous column tile
-                tc_fence_after();
-                for (int kc = 0; kc < kend; ++kc, ++itB) {
-                    const int kb = itB & 1;
-                    mbar_wait(fullB + kb, (itB >> 1) & 1);
-                    for (int s = 0; s < ND; ++s, ++itA) {
-                        const int sl = itA % NA;
-                        mbar_wait(fullA + sl, (itA / NA) & 1);
-                        tc_fence_after();
-                        // A^(s) x [B^(0); ...; B^(5-s)] -> accumulators s ... 5 (adjacent TMEM columns), N <= 256 per instruction
-                        const int ntot = (ND - s) * IN;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t acc = (uint32_t)(kc != 0 || s != 0 || k != 0);
-                            const uint64_t da = smem_desc(sA + sl * ATILE + k * 32, 16, 1024);
-                            const int n0 = ntot > 256 ? 256 : ntot;
-                            mma_i8(tm + (uint32_t)s * IN, da, smem_desc(sB + kb * ND * BTILE + k * 32, 16, 1024), idesc_i8(IM, n0), acc);
-                            if (ntot > 256)
-                                mma_i8(tm + (uint32_t)s * IN + 256, da, smem_desc(sB + kb * ND * BTILE + 4 * BTILE + k * 32, 16, 1024),
-                                       idesc_i8(IM, ntot - 256), acc);
-                        }
-                        mma_commit(emptyA + sl);  // the slot is free once these MMAs have read it
-                    }
-                    mma_commit(emptyB + kb);
-                }
-                mma_commit(tfull);
-            }
-        }
+        i8_issue(sc, p, tm);
     } else {
-        // ---------------- epilogue: 8 warps; thread = one grid row x one half of the tile's columns ----------------
-        const int qd = warp & 3;           // TMEM lane quadrant of this warp
-        const int half = (warp - 2) >> 2;  // columns [32 half, 32 half + 32) of every 64-column tile
+        // epilogue: 16 warps; thread = one grid row x CW of the tile's columns
+        const int qd = warp & 3;         // TMEM lane quadrant of this warp
+        const int cq = (warp - 2) >> 2;  // columns [CW cq, CW cq + CW) of every 64-column tile
         const int r = qd * 32 + lane;
-        const long g = tile * IM + r;
+        const long g = sc.tile * IM + r;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int ct = 0; ct < a.nct; ++ct) {
-            mbar_wait(tfull, ct & 1);
+        for (int ct = 0; ct < sc.nct; ++ct) {
+            const int col = ct * IN + CW * cq;
+            const bool live = col < a.Npad;  // Npad is a multiple of 32 and col of 16; digits of columns >= Nc are zero
+            // the FP64 ao_0 values of this thread's row are fetched before the wait, so that after the drain the row-dot is
+            // arithmetic only and the warp is back in time for the next (possibly short) column tile
+            double2 a0[CW / 2];
+            if (live) {
+                const double2* ap = reinterpret_cast<const double2*>(a.ao + g * a.Npad + col);
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) a0[j] = ap[j];
+            }
+            mbar_wait(p.tfull, ct & 1);
             __syncwarp();
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 32 * half; c0 < 32 * half + 32; c0 += 16) {
-                long long hi[16], lo[16];
+            double T[CW];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0;
+            for (int b = 0; b < CW / 8; ++b) {
+                double t8[8];
+                drain8(tm, qd, CW * cq + 8 * b, t8);
 #pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    float v[16];
-                    tmem_ld16(tmem_addr(tm, 32 * qd, d * IN + c0), v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const long long p = (long long)__float_as_int(v[j]);
-                        if (d < 3) hi[j] += p << (8 * (2 - d));
-                        else lo[j] += p << (8 * (5 - d));
-                    }
-                }
-                const int col = ct * IN + c0;
-                if (col < a.Nc) {
-                    const double* sbp = a.sb + col;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        // sum_d P_d 256^(5-d) = hi 2^24 + lo, each half exact in FP64 (< 2^45); columns beyond Nc carry zero digits
-                        const double t = fma((double)hi[j], 16777216.0, (double)lo[j]) * sbp[j];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (c < a.ncomp) acc[c] = fma(t, a.ao[(long)c * a.ao_cstride + g * a.Npad + col + j], acc[c]);
-                    }
-                }
+                for (int j = 0; j < 8; ++j) T[8 * b + j] = t8[j];
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty);
-        }
-        // the two column halves of a row: fixed-order sum through shared memory (the B tiles are free now)
-        double* part = reinterpret_cast<double*>(Bs);
-        if (half == 1) {
+            if (lane == 0) mbar_arrive(p.tempty);  // the accumulators are free: the next column tile's MMAs overlap the row-dot
+            if (live) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) part[c * IM + r] = acc[c];
+                for (int j = 0; j < CW; ++j) T[j] *= a.sb[col + j];
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) {
+                    s0 = fma(T[2 * j], a0[j].x, s0);
+                    s1 = fma(T[2 * j + 1], a0[j].y, s1);
+                }
+                acc[0] += s0 + s1;
+#pragma unroll
+                for (int c = 1; c < 4; ++c)
+                    if (c < a.ncomp) {
+                        const double2* ap = reinterpret_cast<const double2*>(a.ao + (long)c * a.ao_cstride + g * a.Npad + col);
+                        s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < CW / 2; ++j) {
+                            const double2 v = ap[j];
+                            s0 = fma(T[2 * j], v.x, s0);
+                            s1 = fma(T[2 * j + 1], v.y, s1);
+                        }
+                        acc[c] += s0 + s1;
+                    }
+            }
+        }
+        // the column groups of a row: fixed-order sum through shared memory (every tile has been consumed by now)
+        double* part = reinterpret_cast<double*>(p.Bs);
+        if (cq != 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[((cq - 1) * 4 + c) * IM + r] = acc[c];
         }
         asm volatile("bar.sync 1, %0;" ::"r"(32 * NEW) : "memory");
-        if (half == 0) {
-            const double rs = ldexp(1.0, (int)a.sa[g]);
+        if (cq == 0) {
+            const double rs = pow2((int)a.sa[g]);
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                if (c < a.ncomp) a.q[(long)c * a.q_cstride + g] = a.f[c] * rs * (acc[c] + part[c * IM + r]);
+                if (c < a.ncomp) {
+                    double t = acc[c];
+#pragma unroll
+                    for (int k = 0; k < NEW / 4 - 1; ++k) t += part[(k * 4 + c) * IM + r];
+                    a.q[(long)c * a.q_cstride + g] = a.f[c] * rs * t;
+                }
         }
     }
     tc_fence_before();
@@ -310,72 +513,299 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const I8Args 
     if (warp == 1) tmem_free(tm, 512);
 }
 
-}  // namespace
+// ---- wsyrk ------------------------------------------------------------------------------------------------------------
+struct WsArgs {
+    const signed char *A, *B;   // unweighted / weighted column-scaled planes
+    long plane_stride;
+    const int *eA, *eB;         // block exponents [nblk][NpadK]
+    double* part;               // [nsplit][ntile][128 x 64]
+    int NpadK, njt, njtL, ngc, nblk, ntile, nsplit, sym, dbg;  // njt: column tiles that hold data (tile enumeration); njtL: pitch of the plane layout
+};
 
-bool rowquad_i8_enabled(const qexxc_ctx* c) {
-    const char* e = getenv("QEXXC_I8");
-    return e && atoi(e) != 0 && c->B == 1 && !c->ao_shared;
+__device__ __forceinline__ void ws_tile(const WsArgs& a, int t, int& it, int& jt) {
+    if (!a.sym) {
+        it = t / a.njt;
+        jt = t % a.njt;
+        return;
+    }
+    it = 0;
+    while (t >= a.njt - 2 * it) {  // row tile it holds the column tiles jt >= 2 it (on or above the diagonal)
+        t -= a.njt - 2 * it;
+        ++it;
+    }
+    jt = 2 * it + t;
 }
 
-size_t rowquad_i8_smem() { return 2 * ND * BTILE + NA * ATILE + 32 * 8 + 1024; }
+__global__ void __launch_bounds__(I8_THREADS, 1) wsyrk_i8_kernel(const WsArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    uint32_t* tslot;
+    const Pipe p = pipe_setup(smem_raw, &tslot);
+    const int warp = warp_uniform_idx(), lane = threadIdx.x & 31;
+    const int t = blockIdx.x % a.ntile, sp = blockIdx.x / a.ntile;
+    WsSched sc;
+    sc.A = a.A, sc.B = a.B, sc.a_plane = sc.b_plane = a.plane_stride;
+    ws_tile(a, t, sc.it, sc.jt);
+    sc.njt = a.njtL, sc.ngc = a.ngc;
+    sc.dbg = a.dbg;
+    sc.blk0 = (int)((long)a.nblk * sp / a.nsplit), sc.blk1 = (int)((long)a.nblk * (sp + 1) / a.nsplit);
+    if (warp == 1) tmem_alloc(tslot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tslot;
 
-// (re)build the digit tiles of AO component 0 for the current grid
-int launch_slice_ao(qexxc_ctx* c, cudaStream_t st) {
-    const int nkc = (c->Npad + KC - 1) / KC;
-    const size_t need = (size_t)ND * c->GpadMax * nkc * KC;
-    if (!c->i8_A) {
-        QX_CUDA(cudaMalloc(&c->i8_A, need));
-        QX_CUDA(cudaMalloc(&c->i8_sa, sizeof(float) * c->GpadMax));
-        const int nct = (nkc * KC) / IN;
-        QX_CUDA(cudaMalloc(&c->i8_B, (size_t)ND * nct * nkc * BTILE));
-        QX_CUDA(cudaMalloc(&c->i8_sb, sizeof(double) * nkc * KC));
-        c->allocs.push_back(c->i8_A);
-        c->allocs.push_back(c->i8_sa);
-        c->allocs.push_back(c->i8_B);
-        c->allocs.push_back(c->i8_sb);
-        c->bytes += need + (size_t)ND * nct * nkc * BTILE;
+    if (warp == 0) {
+        if (lane == 0) i8_produce(sc, p);
+    } else if (warp == 1) {
+        i8_issue(sc, p, tm);
+    } else {
+        // epilogue: thread = one output row i x CW of the tile's 64 columns, FP64 accumulators across the exponent blocks
+        const int qd = warp & 3, cq = (warp - 2) >> 2;
+        const int r = qd * 32 + lane;
+        const int i = sc.it * IM + r, j0 = sc.jt * IN + CW * cq;
+        double acc[CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) acc[j] = 0.0;
+        for (int u = 0; u < sc.blk1 - sc.blk0; ++u) {
+            const long eo = (long)(sc.blk0 + u) * a.NpadK;
+            const double si = pow2(a.eA[eo + i] - 26);
+            int eb[CW];  // fetched before the wait: the accumulators are held for as short a time as possible
+            {
+                const int4* ebp = reinterpret_cast<const int4*>(a.eB + eo + j0);
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                    const int4 v = ebp[j];
+                    eb[4 * j] = v.x, eb[4 * j + 1] = v.y, eb[4 * j + 2] = v.z, eb[4 * j + 3] = v.w;
+                }
+            }
+            mbar_wait(p.tfull, u & 1);
+            __syncwarp();
+            tc_fence_after();
+#pragma unroll
+            for (int b = 0; b < CW / 8; ++b) {
+                double t8[8];
+                drain8(tm, qd, CW * cq + 8 * b, t8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[8 * b + j] = fma(t8[j] * si, pow2(eb[8 * b + j] - 26), acc[8 * b + j]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p.tempty);
+        }
+        double2* out = reinterpret_cast<double2*>(a.part + ((long)sp * a.ntile + t) * (IM * IN) + r * IN + CW * cq);
+#pragma unroll
+        for (int j = 0; j < CW / 2; ++j) out[j] = make_double2(acc[2 * j], acc[2 * j + 1]);
     }
-    const long warps = c->Gpad;
-    slice_ao_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(c->ao, c->Npad, nkc, c->Gpad, (signed char*)c->i8_A,
-                                                                          c->i8_sa);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_free(tm, 512);
+}
+
+// out[i][j] = scale * (H[i][j] + (tadd ? H[j][i] : 0)),  H = sum over the grid splits of the partial tiles (fixed order)
+__global__ void __launch_bounds__(256) wsyrk_i8_reduce_kernel(const double* __restrict__ part, double* __restrict__ out, int N, int njt,
+                                                              int ntile, int nsplit, int sym, double scale, int tadd) {
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31), i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (i >= N || j >= N) return;
+    auto H = [&](int r, int c) {
+        const int it = r / IM, jt = c / IN;
+        const int t = sym ? it * njt - it * (it - 1) + (jt - 2 * it) : it * njt + jt;
+        const double* P = part + (long)t * (IM * IN) + (r - it * IM) * IN + (c - jt * IN);
+        double h = 0.0;
+        for (int sp = 0; sp < nsplit; ++sp) h += P[(long)sp * ntile * (IM * IN)];
+        return h;
+    };
+    if (sym) {
+        if (j < i) return;
+        const double v = scale * (tadd ? 2.0 : 1.0) * H(i, j);
+        out[(long)i * N + j] = v;
+        out[(long)j * N + i] = v;
+    } else {
+        out[(long)i * N + j] = scale * (H(i, j) + (tadd ? H(j, i) : 0.0));
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+struct I8Ws {
+    signed char *A = nullptr, *Bs = nullptr;  // rowquad: row-scaled ao planes, S planes
+    float* sa = nullptr;
+    double* sb = nullptr;
+    signed char *T = nullptr, *W = nullptr;   // wsyrk: column-scaled planes of ao_0 (per geometry) and of the weighted operand (per call)
+    float *cmax = nullptr, *cmaxW = nullptr;  // 128-row column maxima of ao_0 / of a general B operand
+    int *eA = nullptr, *eB = nullptr;
+    int nkc = 0, NpadK = 0, njt = 0, ngcMax = 0, nblkMax = 0;
+    long plane_stride = 0;
+};
+
+size_t i8_smem() { return 2 * ND * BTILE + NA * ATILE + 32 * 8 + 1024; }
+
+int i8_alloc(qexxc_ctx* c) {
+    if (c->i8ws) return QEXXC_OK;
+    I8Ws* w = new I8Ws();
+    w->nkc = (c->Npad + KC - 1) / KC;
+    w->NpadK = w->nkc * KC;
+    w->njt = w->NpadK / IN;
+    w->ngcMax = c->GpadMax / 128;
+    w->nblkMax = (w->ngcMax + KDC - 1) / KDC;
+    w->plane_stride = (long)w->ngcMax * w->njt * BTILE;
+    const size_t planes = (size_t)ND * c->GpadMax * w->NpadK;
+    const size_t sbytes = (size_t)ND * w->njt * w->nkc * BTILE;
+    auto A = [&](void** p, size_t bytes) {
+        if (cudaMalloc(p, bytes) != cudaSuccess) return false;
+        c->allocs.push_back(*p);
+        c->bytes += bytes;
+        return true;
+    };
+    bool ok = A((void**)&w->A, planes) && A((void**)&w->T, planes) && A((void**)&w->W, planes) && A((void**)&w->Bs, sbytes) &&
+              A((void**)&w->sa, sizeof(float) * c->GpadMax) && A((void**)&w->sb, sizeof(double) * w->NpadK) &&
+              A((void**)&w->cmax, sizeof(float) * (size_t)w->ngcMax * w->NpadK) &&
+              A((void**)&w->eA, sizeof(int) * (size_t)w->nblkMax * w->NpadK) && A((void**)&w->eB, sizeof(int) * (size_t)w->nblkMax * w->NpadK);
+    if (ok && c->C == 4) ok = A((void**)&w->cmaxW, sizeof(float) * (size_t)w->ngcMax * w->NpadK);
+    c->i8ws = w;  // the buffers are owned by c->allocs; the small struct is released in qexxc_destroy via i8_release
+    if (!ok) {
+        (void)cudaGetLastError();
+        set_error("INT8 contraction workspace: cudaMalloc failed (%.1f GB of digit planes); set QEXXC_I8=0 for the FP64 path",
+                  3.0 * planes / 1e9);
+        return QEXXC_ERR_CUDA;
+    }
+    QX_CUDA(cudaFuncSetAttribute(rowquad_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem()));
+    QX_CUDA(cudaFuncSetAttribute(wsyrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem()));
+    QX_CUDA(cudaFuncSetAttribute(slice_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ND * 16384));
+    return QEXXC_OK;
+}
+
+// digit planes that depend on the geometry only: row-scaled (rowquad) and column-scaled (wsyrk) planes of ao_0
+int i8_prepare(qexxc_ctx* c, cudaStream_t st) {
+    QX_TRY(i8_alloc(c));
+    if (c->i8_valid) return QEXXC_OK;
+    I8Ws* w = (I8Ws*)c->i8ws;
+    ProfScope prof(c, QEXXC_PROF_EVAL_AO, st);
+    const unsigned nb = (unsigned)((c->Gpad + 7) / 8);
+    switch (w->nkc) {
+#define QX_SR(K)                                                                                   \
+    case K:                                                                                        \
+        slice_rows_kernel<K><<<nb, 256, 0, st>>>(c->ao, c->Npad, w->nkc, c->Gpad, w->A, w->sa);   \
+        break
+        QX_SR(1); QX_SR(2); QX_SR(3); QX_SR(4); QX_SR(5); QX_SR(6); QX_SR(7); QX_SR(8);
+        QX_SR(9); QX_SR(10); QX_SR(11); QX_SR(12); QX_SR(13); QX_SR(14); QX_SR(15); QX_SR(16);
+#undef QX_SR
+        default:
+            set_error("INT8 contractions support nao <= 2048 (got %d)", c->N);
+            return QEXXC_ERR_UNSUPPORTED;
+    }
+    QX_LAUNCH_CHECK(c);
+    const int ngc = c->Gpad / 128, nblk = (ngc + KDC - 1) / KDC;
+    colmax_kernel<<<ngc, 256, 0, st>>>(c->ao, c->Npad, w->NpadK, w->cmax);
+    QX_LAUNCH_CHECK(c);
+    blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmax, nullptr, ngc, w->NpadK, w->eA);
+    QX_LAUNCH_CHECK(c);
+    slice_cols_kernel<<<dim3(ngc, w->NpadK / 128), 256, ND * 16384, st>>>(c->ao, c->Npad, nullptr, w->eA, w->NpadK, w->njt, w->plane_stride, w->T);
     QX_LAUNCH_CHECK(c);
     c->i8_valid = true;
     return QEXXC_OK;
 }
 
+}  // namespace
+
+void i8_release(qexxc_ctx* c) {
+    delete (I8Ws*)c->i8ws;
+    c->i8ws = nullptr;
+}
+
+bool i8_enabled(const qexxc_ctx* c) {
+    if (c->B != 1 || c->ao_shared || c->Npad > 2048) return false;
+    const char* e = getenv("QEXXC_I8");
+    if (e) return atoi(e) != 0;
+    return c->N >= 256;
+}
+
 int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_cstride, cudaStream_t st) {
-    const int nkc = (c->Npad + KC - 1) / KC, nct = (nkc * KC) / IN;
-    if (!c->i8_valid) {
-        ProfScope prof(c, QEXXC_PROF_EVAL_AO, st);
-        QX_TRY(launch_slice_ao(c, st));
-    }
+    QX_TRY(i8_prepare(c, st));
+    I8Ws* w = (I8Ws*)c->i8ws;
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
-    slice_s_kernel<<<nkc * KC, 256, 0, st>>>(c->S, c->Npad, c->Nc, nkc, nct, (signed char*)c->i8_B, c->i8_sb);
+    slice_s_kernel<<<w->NpadK, 256, 0, st>>>(c->S, c->Npad, c->Nc, w->nkc, w->njt, w->Bs, w->sb);
     QX_LAUNCH_CHECK(c);
-    I8Args a{};
-    a.A8 = (const signed char*)c->i8_A;
-    a.B8 = (const signed char*)c->i8_B;
-    a.sa = c->i8_sa;
-    a.sb = c->i8_sb;
+    RqArgs a{};
+    a.sc.A = w->A;
+    a.sc.B = w->Bs;
+    const long ntiles = c->Gpad / IM;
+    a.sc.a_plane = ntiles * w->nkc * (long)ATILE;
+    a.sc.b_plane = (long)w->njt * w->nkc * BTILE;
+    a.sc.nkc = w->nkc;
+    a.sc.nct = (c->Nc + IN - 1) / IN;  // column tiles that hold data
+    a.sc.Nc = c->Nc;
+    a.sc.tri = tri;
+    a.sc.dbg = 0;
+    a.sa = w->sa;
+    a.sb = w->sb;
     a.ao = c->ao;
     a.q = q;
     a.ao_cstride = (long)c->GpadMax * c->Npad;
     a.q_cstride = q_cstride;
     a.Npad = c->Npad;
-    a.Nc = c->Nc;
-    a.nkc = nkc;
-    a.nct = (c->Nc + IN - 1) / IN;  // column tiles that hold data
-    a.nctB = nct;
     a.ncomp = ncomp;
-    a.tri = tri;
-    a.ntiles = c->Gpad / IM;
     a.f[0] = (tri ? 2.0 : 1.0) * fac4[0];
     a.f[1] = fac4[1];
     a.f[2] = fac4[2];
     a.f[3] = fac4[3];
-    const size_t sm = rowquad_i8_smem();
-    QX_CUDA(cudaFuncSetAttribute(rowquad_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    rowquad_i8_kernel<<<(unsigned)a.ntiles, I8_THREADS, sm, st>>>(a);
+    rowquad_i8_kernel<<<(unsigned)ntiles, I8_THREADS, i8_smem(), st>>>(a);
+    QX_LAUNCH_CHECK(c);
+    return QEXXC_OK;
+}
+
+int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st) {
+    QX_TRY(i8_prepare(c, st));
+    I8Ws* w = (I8Ws*)c->i8ws;
+    ProfScope prof(c, QEXXC_PROF_WSYRK, st);
+    const bool sym = (Bsrc == nullptr);
+    const int ngc = c->Gpad / 128, nblk = (ngc + KDC - 1) / KDC;
+    // the weighted operand: exponents, then digit planes
+    if (sym) {
+        blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmax, s, ngc, w->NpadK, w->eB);
+        QX_LAUNCH_CHECK(c);
+        slice_cols_kernel<<<dim3(ngc, w->NpadK / 128), 256, ND * 16384, st>>>(c->ao, c->Npad, s, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
+    } else {
+        colmax_kernel<<<ngc, 256, 0, st>>>(Bsrc, c->Npad, w->NpadK, w->cmaxW);
+        QX_LAUNCH_CHECK(c);
+        blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmaxW, nullptr, ngc, w->NpadK, w->eB);
+        QX_LAUNCH_CHECK(c);
+        slice_cols_kernel<<<dim3(ngc, w->NpadK / 128), 256, ND * 16384, st>>>(Bsrc, c->Npad, nullptr, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
+    }
+    QX_LAUNCH_CHECK(c);
+    const int nit = (c->Nc + IM - 1) / IM, njt = (c->Nc + IN - 1) / IN;  // tiles that hold data
+    int ntile = 0;  // general: nit x njt; symmetric: the column tiles jt >= 2 it of each row tile
+    for (int it = 0; it < nit; ++it) ntile += sym ? std::max(0, njt - 2 * it) : njt;
+    // grid splits: as many CTAs as fill whole waves of the machine
+    int nsplit = 1;
+    double beff = 0.0;
+    for (int ns = 1; ns <= nblk; ++ns) {
+        const long ctas = (long)ntile * ns, waves = (ctas + c->num_sms - 1) / c->num_sms;
+        const double eff = (double)ctas / (double)(waves * c->num_sms);
+        if (eff > beff + 1e-9) beff = eff, nsplit = ns;
+        if (ctas >= 2L * c->num_sms) break;
+    }
+    if ((size_t)ntile * nsplit * IM * IN > c->part_doubles) {
+        set_error("internal: INT8 wsyrk partial tiles exceed the workspace");
+        return QEXXC_ERR_STATE;
+    }
+    WsArgs a{};
+    a.A = w->T;
+    a.B = w->W;
+    a.plane_stride = w->plane_stride;
+    a.eA = w->eA;
+    a.eB = w->eB;
+    a.part = c->part;
+    a.NpadK = w->NpadK;
+    a.njt = njt;
+    a.njtL = w->njt;
+    a.ngc = ngc;
+    a.nblk = nblk;
+    a.ntile = ntile;
+    a.nsplit = nsplit;
+    a.sym = sym ? 1 : 0;
+    a.dbg = getenv("QEXXC_I8_DBG") ? atoi(getenv("QEXXC_I8_DBG")) : 0;
+    wsyrk_i8_kernel<<<(unsigned)(ntile * nsplit), I8_THREADS, i8_smem(), st>>>(a);
+    QX_LAUNCH_CHECK(c);
+    wsyrk_i8_reduce_kernel<<<dim3((c->N + 31) / 32, (c->N + 7) / 8), 256, 0, st>>>(c->part, out, c->N, njt, ntile, nsplit, sym ? 1 : 0, scale, tadd);
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;
 }

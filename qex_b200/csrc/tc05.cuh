@@ -61,6 +61,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// true in exactly one lane of a converged warp (the pattern ptxas recognises for single-thread issue of UTC* instructions
+// from warp-uniform code: no per-lane "waterfall" loop around the uniform-register operands)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "@P mov.s32 %0, 1;\n\t"
+        "}"
+        : "+r"(pred));
+    return pred != 0;
+}
+// warp index as a provably warp-uniform value
+__device__ __forceinline__ int warp_uniform_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---- proxies / fences -------------------------------------------------------------------------------------------
 // generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -90,6 +106,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// same, 8 consecutive 32-bit columns, raw words (several loads can be in flight before one tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -192,7 +214,7 @@ __device__ __forceinline__ uint32_t pack_hi16(uint32_t a, uint32_t b) { return _
 }  // namespace tc05
 }  // namespace qexxc
 
-// ---- 8-bit integer operands (kind::i8, INT32 accumulation): used by the Ozaki-split study only --------------------
+// ---- 8-bit integer operands (kind::i8, INT32 accumulation): the exact Ozaki-split contractions (contract_i8.cu) --------------------
 namespace qexxc {
 namespace tc05 {
 __device__ __host__ constexpr uint32_t idesc_i8(int M, int N) {  // signed 8-bit A and B, K-major, S32 accumulators
@@ -206,6 +228,20 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same, the two 64-bit shared-memory descriptors given as (low word, common high word)
+__device__ __forceinline__ void mma_i8_lohi(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 }  // namespace tc05

@@ -28,11 +28,21 @@ for mode in ("0", "1"):
         rho = ctx.eval_rho(wl.dm, ncomp=wl.ncomp, hermi=1)
     e1.record()
     torch.cuda.synchronize()
-    res[mode] = (rho.cpu().numpy(), out.cpu().numpy(), bar.cpu().numpy(), e0.elapsed_time(e1) / 3)
+    e2, e3, e4 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e2.record()
+    for _ in range(3):
+        out, resid = ctx.nr_rks_fwd(wl.dm, wl.theta, wl.xctype)
+    e3.record()
+    for _ in range(3):
+        bar = ctx.nr_rks_vjp(wl.theta, resid, [wl.e_bar], wl.v_bar, wl.xctype)
+    e4.record()
+    torch.cuda.synchronize()
+    res[mode] = (rho.cpu().numpy(), out.cpu().numpy(), bar.cpu().numpy(), e0.elapsed_time(e1) / 3, e2.elapsed_time(e3) / 3, e3.elapsed_time(e4) / 3)
 rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
-r0, o0, b0, t0 = res["0"]
-r1, o1, b1, t1 = res["1"]
+r0, o0, b0, t0, f0, v0 = res["0"]
+r1, o1, b1, t1, f1, v1 = res["1"]
 print(json.dumps({"cfg": cfg, "G": G, "rho_rel": rel(r1, r0), "vmat_rel": rel(o1[0][: N * N], o0[0][: N * N]),
                   "excsum_abs": abs(o1[0][N * N] - o0[0][N * N]), "dm_bar_rel": rel(b1[: N * N], b0[: N * N]),
                   "theta_bar_rel": rel(b1[N * N:], b0[N * N:]), "eval_rho_ms_dmma": round(t0, 3), "eval_rho_ms_i8": round(t1, 3),
+                  "fwd_ms_dmma": round(f0, 3), "fwd_ms_i8": round(f1, 3), "vjp_ms_dmma": round(v0, 3), "vjp_ms_i8": round(v1, 3),
                   "finite": bool(np.isfinite(r1).all())}))
