@@ -43,7 +43,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "XC grid-integration grid-pts/s (fwd+VJP)"
 UNIT = "grid-pts/s"
-SUB_CONFIGS = ("c1", "c2", "c3", "c4", "c5gga", "c5_f32", "c3_f32", "c4_f32", "c5w512")
+SUB_CONFIGS = ("c1", "c2", "c3", "c4", "c5gga", "c5_dmma", "c5gga_dmma", "c5_f32", "c3_f32", "c4_f32", "c5w512")
 
 
 def _args():
@@ -256,6 +256,20 @@ def measure_dgemm_peak(torch, seconds=1.5):
     return best, sustained
 
 
+def measure_i8_peak(device):
+    """INT8 tensor-core rate (TOP/s, 2 ops per MAC) of this GPU, measured with the library's own tcgen05 issue loop."""
+    import ctypes as C
+    from qex_b200 import _lib
+    v = C.c_double(0)
+    lib = _lib.load()
+    best = 0.0
+    for _ in range(3):
+        if lib.qexxc_i8_peak(int(device), C.byref(v)) != 0:
+            return None
+        best = max(best, v.value / 1e12)
+    return best
+
+
 def ctx_npad(N):  # AO row pitch: a multiple of 32 columns (zeros in the pad)
     return ((N + 31) // 32) * 32
 
@@ -303,7 +317,7 @@ class Env:
 
 
 def measure(env: Env, args, cfg: str, precision: str, steps: int, warmup: int, headline: bool, peak_sus=None,
-            cpu_seconds: float = 0.0):
+            cpu_seconds: float = 0.0, peak_i8=None):
     """Times one workload on this process group.  Returns (summary dict for rank 0, extras)."""
     torch = env.torch
     from qex_b200 import workloads
@@ -492,22 +506,30 @@ def measure(env: Env, args, cfg: str, precision: str, steps: int, warmup: int, h
     if rank == 0:
         fl = 2.0 * Gl * Bc * N * N
         tri = wl.ncomp == 1
-        ex = {"rowquad": ctx.contraction_flops(0, tri), "wsyrk": ctx.contraction_flops(1, tri)}
+        mode = ctx.contraction_mode
+        if mode == "int8":  # exact digit split on the INT8 tensor cores: executed INT8 ops against the measured INT8 rate
+            ex = {"rowquad": ctx.contraction_i8_ops(0, tri), "wsyrk": ctx.contraction_i8_ops(1, tri)}
+            peak_c = peak_i8
+        else:
+            ex = {"rowquad": ctx.contraction_flops(0, tri), "wsyrk": ctx.contraction_flops(1, tri)}
+            peak_c = peak_sus
         kern = {}
-        for name in ("rowquad", "wsyrk", "xc_fwd", "xc_vjp", "eval_ao", "stage4"):
+        for name in ("rowquad", "wsyrk", "xc_fwd", "xc_vjp", "eval_ao", "stage4", "slice"):
             ms, n = prof[name]
             kern[name] = {"launches": n, "avg_ms": (ms / n) if n else None,
                           "share_of_step": ms / prof_total if prof_total else None}
             if name in ex and n:
                 kern[name]["algorithmic_tflops"] = fl / (ms / n * 1e-3) / 1e12
                 kern[name]["executed_tflops"] = ex[name] / (ms / n * 1e-3) / 1e12
-                kern[name]["executed_frac_of_peak"] = kern[name]["executed_tflops"] / peak_sus if peak_sus else None
+                kern[name]["executed_frac_of_peak"] = kern[name]["executed_tflops"] / peak_c if peak_c else None
+                kern[name]["executed_unit"] = "TOP/s (INT8)" if mode == "int8" else "TFLOP/s (FP64)"
         dom_all = max(kern, key=lambda k: prof[k][0])
         cpu = None
         if cpu_seconds > 0 and world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(wl, cpu_seconds)
         res = {
             "wl": wl, "value": value, "ms_per_step": ms_step, "kern": kern, "ex": ex, "fl": fl, "dominant": dom_all,
+            "mode": mode,
             "e2e": {"value": npts_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "note": e2e_note,
                     "bitwise_equal_to_device_path": e2e_same},
@@ -574,11 +596,12 @@ def run_ours(args):
         comm = Comm(rank, world, local)  # the data-path collectives go through the C ABI (qexxc_allreduce)
     env = Env(torch, tdist, world, rank, local, comm)
 
-    peak_burst = peak_sus = None
+    peak_burst = peak_sus = peak_i8 = None
     if rank == 0:
         peak_burst, peak_sus = measure_dgemm_peak(torch)
+        peak_i8 = measure_i8_peak(local)
     res, extras = measure(env, args, args.config, args.precision, args.steps, args.warmup, True, peak_sus,
-                          args.cpu_seconds)
+                          args.cpu_seconds, peak_i8)
     parity = parity_vs_single_rank(env, extras) if (world > 1 and not extras["wl"].extra.get("batch")) else None
     ctx_ws = res["workspace_gb"] if res else None
     extras["ctx"].close()
@@ -591,9 +614,16 @@ def run_ours(args):
         todo = SUB_CONFIGS if world == 1 else ("c4",)
         for name in todo:
             cfg, prec = (name[:-4], "f32") if name.endswith("_f32") else (name, "f64")
+            force_dmma = name.endswith("_dmma")  # the same workload with the contractions on the FP64 tensor pipe
+            if force_dmma:
+                cfg = name[:-5]
+            old_i8 = os.environ.get("QEXXC_I8")
+            if force_dmma:
+                os.environ["QEXXC_I8"] = "0"
             try:
                 r, ex2 = measure(env, args, cfg, prec, args.steps, args.warmup, False, peak_sus,
-                                 0.0 if (name.endswith("_f32") or name == "c5w512") else min(4.0, args.cpu_seconds))
+                                 0.0 if (name.endswith("_f32") or name == "c5w512" or force_dmma) else min(4.0, args.cpu_seconds),
+                                 peak_i8)
                 ex2["ctx"].close()
                 del ex2
                 torch.cuda.empty_cache()
@@ -606,14 +636,21 @@ def run_ours(args):
                         "dominant_kernel": r["dominant"], "dominant_share_of_step": k["share_of_step"],
                         "dominant_avg_ms": k["avg_ms"],
                         "kernel_shares": {n: v["share_of_step"] for n, v in r["kern"].items() if v["launches"]},
-                        "contraction_executed_frac_of_dgemm": {n: r["kern"][n].get("executed_frac_of_peak")
-                                                               for n in ("rowquad", "wsyrk")},
+                        "contraction_pipe": r["mode"],
+                        "contraction_executed_frac_of_pipe_peak": {n: r["kern"][n].get("executed_frac_of_peak")
+                                                                   for n in ("rowquad", "wsyrk")},
                         "gpu_launches": r["launches"], "cpu_baseline": r["cpu"],
                         "launch": "one CUDA graph replay per step" if r["graph"] else "stream launches",
                     }
             except Exception as e:  # a failing side config must not lose the headline line
                 if rank == 0:
                     subs[name] = {"error": f"{type(e).__name__}: {e}"}
+            finally:
+                if force_dmma:
+                    if old_i8 is None:
+                        os.environ.pop("QEXXC_I8", None)
+                    else:
+                        os.environ["QEXXC_I8"] = old_i8
 
     if rank == 0:
         wl, kern, ex, fl = res["wl"], res["kern"], res["ex"], res["fl"]
@@ -637,31 +674,58 @@ def run_ours(args):
             # vrho_bar (vgamma_bar) out -- summed over the two launches per step and divided by two below
             "stage4": 0.5 * 8.0 * ((C_ + 3 + (C_ == 4) + C_) + (2 * C_ + 3 + (C_ == 4) + C_ + 2 + (C_ == 4))) * res["Gl"] * res["Bl"],
         }
+        if res["mode"] == "int8":
+            # per step: geometry planes (read ao 3x: rows, column maxima, columns; write 2 x 6 planes) + two weighted
+            # operands (read ao, write 6 planes); per launch of the class = that total over its recorded scopes
+            npk = ((res["npad"] + 127) // 128) * 128
+            per_step = (3 * 8.0 * res["npad"] + 12.0 * npk + 2 * (8.0 * res["npad"] + 6.0 * npk)) * res["Gl"]
+            nsl = kern["slice"]["launches"] or 1
+            stream_bytes["slice"] = per_step * args.steps / nsl
         streaming = {}
         for name, nbytes in stream_bytes.items():
             k = kern[name]
             if k["launches"]:
                 gbs = nbytes / (k["avg_ms"] * 1e-3) / 1e9
-                streaming[name] = {"kernel": {"eval_ao": "eval_ao_kernel (K1)", "stage4": "stage4_fwd/vjp kernels"}[name],
+                streaming[name] = {"kernel": {"eval_ao": "eval_ao_kernel (K1)", "stage4": "stage4_fwd/vjp kernels",
+                                              "slice": "slice_rows / colmax / slice_cols (INT8 digit planes)"}[name],
                                    "bytes_per_launch": nbytes, "avg_ms": k["avg_ms"], "gbs": gbs,
                                    "frac_of_hbm_peak": gbs / hbm if hbm else None}
+        int8 = res["mode"] == "int8"
+        peak_c = peak_i8 if int8 else peak_sus
+        if int8:
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["c5_int8"].get(dom + "_i8_kernel") \
+                    if (wl.name == "c5" and world == 1 and G == 1_000_000) else None
+            except Exception:
+                traffic = None
         roofline = {
-            "bound": "tensor", "kernel": dom + "_kernel (FP64 DMMA.8x8x4)",
-            "achieved": kern[dom]["executed_tflops"], "peak": peak_sus, "unit": "TFLOP/s",
+            "bound": "tensor",
+            "kernel": dom + ("_i8_kernel (tcgen05.mma kind::i8, exact 6 x 6 digit split of the FP64 product)" if int8
+                             else "_kernel (FP64 DMMA.8x8x4)"),
+            "achieved": kern[dom]["executed_tflops"], "peak": peak_c, "unit": "TOP/s" if int8 else "TFLOP/s",
             "frac": kern[dom]["executed_frac_of_peak"], "traffic": traffic,
-            "frac_definition": "EXECUTED DMMA FLOP per launch / launch time / cuBLAS DGEMM sustained peak measured in this "
-                               "run (the pipe fraction); the algorithmic figure is under `algorithmic`",
+            "frac_definition": ("EXECUTED INT8 operations per launch (21 digit products of every scheduled 128x64x128 block, 2 per MAC) "
+                                "/ launch time / the INT8 tensor rate measured in this run with the library's own issue loop "
+                                "(qexxc_i8_peak; 2 x MEASURED_PEAKS.json's dense bf16 figure would be "
+                                f"{2 * (json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('bf16_tflops') or float('nan')):.0f}); "
+                                "the FP64-equivalent algorithmic figure is under `algorithmic`") if int8 else
+                               ("EXECUTED DMMA FLOP per launch / launch time / cuBLAS DGEMM sustained peak measured in this "
+                                "run (the pipe fraction); the algorithmic figure is under `algorithmic`"),
             "algorithmic": {"flop_per_launch": fl, "tflops": achieved_alg,
-                            "frac_of_peak": achieved_alg / peak_sus if peak_sus else None,
-                            "note": "SURVEY 8d's 2*G*N^2 per launch; exceeds the pipe fraction because symmetric operands "
-                                    "let the kernels skip the lower-triangular blocks"},
-            "executed_flop_per_launch": ex[dom],
+                            "frac_of_fp64_dgemm_peak": achieved_alg / peak_sus if peak_sus else None,
+                            "note": "SURVEY 8d's 2*G*N^2 FP64 FLOP per launch over the launch time, i.e. the FP64-equivalent rate; "
+                                    "cuBLAS DGEMM sustained peak measured in this run = %.1f TFLOP/s" % (peak_sus or float("nan"))},
+            "executed_per_launch": ex[dom],
+            "contraction_pipe": res["mode"],
             "traffic_note": "dram read+write bytes per launch of THIS kernel at this shape, from the committed ncu capture "
-                            "(profiles/ncu_traffic.json, profiles/r02/pair_mode_and_traffic.log; not measurable inside a "
-                            "timed run); algorithmic bytes = the AO tensor read once = "
-                            f"{8.0 * res['npad'] * res['Gl'] / 1e9:.2f} GB",
-            "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, sustained (MEASURED_PEAKS.json has no FP64 figure); "
-                           f"burst {peak_burst:.1f} TFLOP/s",
+                            "(profiles/ncu_traffic.json; not measurable inside a timed run); algorithmic bytes = "
+                            + ("the digit planes of both operands read once = %.2f GB" % (12.0 * res["npad"] * res["Gl"] / 1e9) if int8
+                               else "the AO tensor read once = %.2f GB" % (8.0 * res["npad"] * res["Gl"] / 1e9)),
+            "peak_source": ("qexxc_i8_peak measured in this run (best of 3)" if int8 else
+                            "cuBLAS DGEMM 8192^3 measured in this run, sustained (MEASURED_PEAKS.json has no FP64 figure); "
+                            f"burst {peak_burst:.1f} TFLOP/s"),
+            "fp64_dgemm_peak_tflops": peak_sus, "int8_peak_tops": peak_i8,
             "streaming": streaming, "hbm_peak_gbs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json (of measured)",
             "kernels": kern,
         }

@@ -230,12 +230,22 @@ long qexxc_launch_count(const qexxc_ctx* ctx);
 #define QEXXC_PROF_XC_VJP 3
 #define QEXXC_PROF_EVAL_AO 4
 #define QEXXC_PROF_STAGE4 5 /* the streaming stage-4 kernels: wv / E_xc / nelec forward, and their adjoint */
-#define QEXXC_PROF_NCLASS 6
+#define QEXXC_PROF_SLICE 6  /* INT8 path only: the digit-slicing passes (per geometry and per call) */
+#define QEXXC_PROF_NCLASS 7
 int qexxc_profile_enable(qexxc_ctx* ctx, int on);
 int qexxc_profile_read(qexxc_ctx* ctx, int cls, double* ms_total, long* count);
 /* DMMA FLOPs the contraction kernels actually execute for the current problem shape (zero-padded and
  * structurally-zero blocks excluded): which = 0 rowquad, 1 wsyrk; symmetric = triangular variant. */
 int qexxc_contraction_flops(qexxc_ctx* ctx, int which, int symmetric, double* executed_flops);
+/* Which tensor pipe the two contractions (numint_legacy.py:351-410 eval_rho, :432-456 V_xc) run on for this context:
+ * 0 = FP64 DMMA (contract.cu), 1 = exact INT8 digit split on tcgen05 (contract_i8.cu; env QEXXC_I8=0/1 overrides the
+ * default "nao >= 256, single molecule").  Results agree to ~1e-12 of the largest element either way. */
+int qexxc_contraction_mode(const qexxc_ctx* ctx);
+/* INT8 multiply-add operations (2 per MAC) one launch of rowquad (0) / wsyrk (1) executes in mode 1. */
+int qexxc_contraction_i8_ops(qexxc_ctx* ctx, int which, int symmetric, double* executed_ops);
+/* Measures the INT8 tensor-core rate of `device` with the library's own issue loop (kind::i8, M = 128, N = 256, K = 32,
+ * operands resident in shared memory, one CTA per SM): the roofline denominator of mode 1, in ops/s (2 per MAC). */
+int qexxc_i8_peak(int device, double* ops_per_second);
 /* Runs only the dominant contraction kernel once on the current AO/S buffers (roofline timing):
  * which = 0 rowquad (rho-type), 1 wsyrk (vmat-type). */
 int qexxc_debug_run_contraction(qexxc_ctx* ctx, int which, void* stream);

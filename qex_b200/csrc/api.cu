@@ -826,6 +826,19 @@ int qexxc_contraction_flops(qexxc_ctx* c, int which, int symmetric, double* exec
     return QEXXC_OK;
 }
 
+int qexxc_contraction_mode(const qexxc_ctx* c) { return (c && i8_enabled(c)) ? 1 : 0; }
+
+int qexxc_contraction_i8_ops(qexxc_ctx* c, int which, int symmetric, double* executed) {
+    QX_ARG(c != nullptr && executed != nullptr, "null pointer");
+    *executed = i8_executed_ops(c, which, symmetric != 0);
+    return QEXXC_OK;
+}
+
+int qexxc_i8_peak(int device, double* ops_per_second) {
+    QX_ARG(ops_per_second != nullptr, "null pointer");
+    return i8_peak_probe(device, ops_per_second);
+}
+
 int qexxc_debug_run_contraction(qexxc_ctx* c, int which, void* stream) {
     QX_ARG(c != nullptr, "ctx is null");
     QX_TRY(need_ao(c, 1));

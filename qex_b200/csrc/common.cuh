@@ -186,6 +186,8 @@ bool i8_enabled(const qexxc_ctx* c);
 void i8_release(qexxc_ctx* c);
 int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_cstride, cudaStream_t st);
 int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st);
+double i8_executed_ops(const qexxc_ctx* c, int which, bool sym);
+int i8_peak_probe(int device, double* ops_per_second);
 // ao.cu
 int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st);
 int launch_pack_ao(qexxc_ctx* c, const double* src, int ncomp, int G, cudaStream_t st);

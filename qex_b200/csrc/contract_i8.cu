@@ -678,7 +678,7 @@ int i8_prepare(qexxc_ctx* c, cudaStream_t st) {
     QX_TRY(i8_alloc(c));
     if (c->i8_valid) return QEXXC_OK;
     I8Ws* w = (I8Ws*)c->i8ws;
-    ProfScope prof(c, QEXXC_PROF_EVAL_AO, st);
+    ProfScope prof(c, QEXXC_PROF_SLICE, st);
     const unsigned nb = (unsigned)((c->Gpad + 7) / 8);
     switch (w->nkc) {
 #define QX_SR(K)                                                                                   \
@@ -711,6 +711,88 @@ void i8_release(qexxc_ctx* c) {
     c->i8ws = nullptr;
 }
 
+// INT8 operations (2 per MAC) of one launch: every scheduled (tile, k-chunk) pair runs the 21 digit products of a
+// 128 x 64 x 128 block
+double i8_executed_ops(const qexxc_ctx* c, int which, bool sym) {
+    const double per_pair = 2.0 * 21.0 * IM * IN * KC;
+    const int njt = (c->Nc + IN - 1) / IN, nit = (c->Nc + IM - 1) / IM;
+    if (which == 0) {
+        double pairs = 0.0;
+        for (int ct = 0; ct < njt; ++ct) pairs += sym ? (std::min(c->Nc, (ct + 1) * IN) + KC - 1) / KC : (c->Nc + KC - 1) / KC;
+        return per_pair * pairs * (c->Gpad / IM);
+    }
+    int ntile = 0;
+    for (int it = 0; it < nit; ++it) ntile += sym ? std::max(0, njt - 2 * it) : njt;
+    return per_pair * ntile * (c->Gpad / KC);
+}
+
+namespace {
+// the rate probe: the same unrolled issue pattern as the contractions, N = 256 only, operands resident in shared memory
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    for (int i = threadIdx.x; i < (int)(ATILE + 4 * BTILE) / 4; i += blockDim.x) ((uint32_t*)base)[i] = 0x01010101u * (uint32_t)(i % 3);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    const int warp = warp_uniform_idx();
+    if (warp == 0) tmem_alloc(&tslot, 512);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tslot;
+    if (warp == 1) {
+        constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t alo = ((smem_u32(base) >> 4) & 0x3FFFu) | (1u << 16), blo = ((smem_u32(base + ATILE) >> 4) & 0x3FFFu) | (1u << 16);
+        uint32_t phase = 0;
+        for (int it = 0; it < iters; ++it) {
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mma_i8_lohi(tm, alo + k * 2u, blo + k * 2u, DESC_HI, idesc_i8(IM, 256), 1u);
+                    mma_i8_lohi(tm + 256, alo + k * 2u, blo + k * 2u, DESC_HI, idesc_i8(IM, 256), 1u);
+                }
+                if ((it & 31) == 31 || it == iters - 1) mma_commit(&bar);
+            }
+            __syncwarp();
+            if ((it & 31) == 31 || it == iters - 1) {  // bound the number of MMAs in flight
+                mbar_wait(&bar, phase);
+                phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tm, 512);
+}
+}  // namespace
+
+int i8_peak_probe(int device, double* ops_per_second) {
+    QX_CUDA(cudaSetDevice(device));
+    int nsm = 0;
+    QX_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    const int smem = ATILE + 4 * BTILE + 1024, iters = 20000;
+    QX_CUDA(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaEvent_t e0, e1;
+    QX_CUDA(cudaEventCreate(&e0));
+    QX_CUDA(cudaEventCreate(&e1));
+    i8_peak_kernel<<<nsm, 128, smem>>>(2000);
+    QX_CUDA(cudaEventRecord(e0));
+    i8_peak_kernel<<<nsm, 128, smem>>>(iters);
+    QX_CUDA(cudaEventRecord(e1));
+    QX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    QX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ops_per_second = 2.0 * nsm * (double)iters * 8.0 * IM * 256.0 * 32.0 / (ms * 1e-3);
+    return QEXXC_OK;
+}
+
 bool i8_enabled(const qexxc_ctx* c) {
     if (c->B != 1 || c->ao_shared || c->Npad > 2048) return false;
     const char* e = getenv("QEXXC_I8");
@@ -721,9 +803,12 @@ bool i8_enabled(const qexxc_ctx* c) {
 int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_cstride, cudaStream_t st) {
     QX_TRY(i8_prepare(c, st));
     I8Ws* w = (I8Ws*)c->i8ws;
+    {
+        ProfScope prof(c, QEXXC_PROF_SLICE, st);
+        slice_s_kernel<<<w->NpadK, 256, 0, st>>>(c->S, c->Npad, c->Nc, w->nkc, w->njt, w->Bs, w->sb);
+        QX_LAUNCH_CHECK(c);
+    }
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
-    slice_s_kernel<<<w->NpadK, 256, 0, st>>>(c->S, c->Npad, c->Nc, w->nkc, w->njt, w->Bs, w->sb);
-    QX_LAUNCH_CHECK(c);
     RqArgs a{};
     a.sc.A = w->A;
     a.sc.B = w->Bs;
@@ -752,25 +837,32 @@ int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, doub
     return QEXXC_OK;
 }
 
-int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st) {
-    QX_TRY(i8_prepare(c, st));
-    I8Ws* w = (I8Ws*)c->i8ws;
-    ProfScope prof(c, QEXXC_PROF_WSYRK, st);
-    const bool sym = (Bsrc == nullptr);
-    const int ngc = c->Gpad / 128, nblk = (ngc + KDC - 1) / KDC;
-    // the weighted operand: exponents, then digit planes
-    if (sym) {
+// the per-call operand of wsyrk (s .* ao_0, or a general B): block exponents, then digit planes
+static int i8_slice_weighted(qexxc_ctx* c, I8Ws* w, const double* s, const double* Bsrc, int ngc, int nblk, cudaStream_t st) {
+    ProfScope prof(c, QEXXC_PROF_SLICE, st);
+    const dim3 grid(ngc, w->NpadK / 128);
+    if (Bsrc == nullptr) {
         blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmax, s, ngc, w->NpadK, w->eB);
         QX_LAUNCH_CHECK(c);
-        slice_cols_kernel<<<dim3(ngc, w->NpadK / 128), 256, ND * 16384, st>>>(c->ao, c->Npad, s, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
+        slice_cols_kernel<<<grid, 256, ND * 16384, st>>>(c->ao, c->Npad, s, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
     } else {
         colmax_kernel<<<ngc, 256, 0, st>>>(Bsrc, c->Npad, w->NpadK, w->cmaxW);
         QX_LAUNCH_CHECK(c);
         blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmaxW, nullptr, ngc, w->NpadK, w->eB);
         QX_LAUNCH_CHECK(c);
-        slice_cols_kernel<<<dim3(ngc, w->NpadK / 128), 256, ND * 16384, st>>>(Bsrc, c->Npad, nullptr, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
+        slice_cols_kernel<<<grid, 256, ND * 16384, st>>>(Bsrc, c->Npad, nullptr, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
     }
     QX_LAUNCH_CHECK(c);
+    return QEXXC_OK;
+}
+
+int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st) {
+    QX_TRY(i8_prepare(c, st));
+    I8Ws* w = (I8Ws*)c->i8ws;
+    const bool sym = (Bsrc == nullptr);
+    const int ngc = c->Gpad / 128, nblk = (ngc + KDC - 1) / KDC;
+    QX_TRY(i8_slice_weighted(c, w, s, Bsrc, ngc, nblk, st));
+    ProfScope prof(c, QEXXC_PROF_WSYRK, st);
     const int nit = (c->Nc + IM - 1) / IM, njt = (c->Nc + IN - 1) / IN;  // tiles that hold data
     int ntile = 0;  // general: nit x njt; symmetric: the column tiles jt >= 2 it of each row tile
     for (int it = 0; it < nit; ++it) ntile += sym ? std::max(0, njt - 2 * it) : njt;

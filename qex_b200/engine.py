@@ -344,7 +344,18 @@ class XCContext:
         check(self.lib.qexxc_contraction_flops(self._h, int(which), 1 if symmetric else 0, C.byref(v)))
         return v.value
 
-    PROF_CLASSES = {"rowquad": 0, "wsyrk": 1, "xc_fwd": 2, "xc_vjp": 3, "eval_ao": 4, "stage4": 5}
+    @property
+    def contraction_mode(self) -> str:
+        """"int8" (exact digit split on tcgen05, contract_i8.cu) or "dmma" (FP64 tensor pipe) for this context."""
+        return "int8" if self.lib.qexxc_contraction_mode(self._h) else "dmma"
+
+    def contraction_i8_ops(self, which: int, symmetric: bool) -> float:
+        """INT8 operations (2 per MAC) one launch of rowquad (0) / wsyrk (1) executes in "int8" mode."""
+        v = C.c_double(0)
+        check(self.lib.qexxc_contraction_i8_ops(self._h, int(which), 1 if symmetric else 0, C.byref(v)))
+        return v.value
+
+    PROF_CLASSES = {"rowquad": 0, "wsyrk": 1, "xc_fwd": 2, "xc_vjp": 3, "eval_ao": 4, "stage4": 5, "slice": 6}
 
     def profile_enable(self, on: bool = True):
         check(self.lib.qexxc_profile_enable(self._h, 1 if on else 0))
