@@ -74,54 +74,75 @@ __device__ __forceinline__ uint32_t tile_off(int r, int c) {  // byte offset of 
 
 // ---- slicing kernels ----------------------------------------------------------------------------------------------
 // Row-scaled planes of ao_0 (rowquad A operand): A8[s][row tile][k-chunk][16 KB tile]; sa[g] = exponent e, |ao[g,:]| < 2^e.
-// One warp per grid row; NKC k-chunks of the row live in registers between the maximum and the digit pass.
+// One CTA per 128-row tile, one warp per grid row (16 rows per warp, one after the other); the NKC k-chunks of a row live in
+// registers between the maximum and the digit pass.  The same pass takes the column maxima of the tile (cmax[tile][col],
+// rounded up to float), which the column-scaled planes of wsyrk need: the AO tensor is read once for both.
 template <int NKC>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ ao, int Npad, int nkc, long Gpad,
-                                                         signed char* __restrict__ A8, float* __restrict__ sa) {
+                                                         signed char* __restrict__ A8, float* __restrict__ sa, int NpadK,
+                                                         float* __restrict__ cmax) {
     __shared__ __align__(16) uint32_t stage[8][ND][32];
+    __shared__ unsigned int cm[NKC * KC];  // column maxima of the tile (non-negative floats order like their bit patterns)
+    for (int c = threadIdx.x; c < NKC * KC; c += 256) cm[c] = 0u;
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long g = (long)blockIdx.x * 8 + warp;
-    if (g >= Gpad) return;
-    const double* row = ao + g * Npad;
-    const long tile = g >> 7, nt = Gpad >> 7;
-    const int r = (int)(g & 127);
-    double x[NKC][4];
-    double mx = 0.0;
+    const long tile = blockIdx.x, nt = Gpad >> 7;
+    float cmx[NKC][4];
 #pragma unroll
-    for (int kc = 0; kc < NKC; ++kc) {
-        const int c = kc * KC + lane * 4;
-        if (c < Npad) {  // Npad is a multiple of 32: the four columns are inside or outside together
-            const double2 u = *reinterpret_cast<const double2*>(row + c), v = *reinterpret_cast<const double2*>(row + c + 2);
-            x[kc][0] = u.x, x[kc][1] = u.y, x[kc][2] = v.x, x[kc][3] = v.y;
-        } else {
-            x[kc][0] = x[kc][1] = x[kc][2] = x[kc][3] = 0.0;
+    for (int kc = 0; kc < NKC; ++kc) cmx[kc][0] = cmx[kc][1] = cmx[kc][2] = cmx[kc][3] = 0.0f;
+#pragma unroll 1
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp * 16 + rr;
+        const long g = tile * 128 + r;
+        const double* row = ao + g * Npad;
+        double x[NKC][4];
+        double mx = 0.0;
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+            const int c = kc * KC + lane * 4;
+            if (c < Npad) {  // Npad is a multiple of 32: the four columns are inside or outside together
+                const double2 u = *reinterpret_cast<const double2*>(row + c), v = *reinterpret_cast<const double2*>(row + c + 2);
+                x[kc][0] = u.x, x[kc][1] = u.y, x[kc][2] = v.x, x[kc][3] = v.y;
+            } else {
+                x[kc][0] = x[kc][1] = x[kc][2] = x[kc][3] = 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double ax = fabs(x[kc][j]);
+                mx = fmax(mx, ax);
+                cmx[kc][j] = fmaxf(cmx[kc][j], __double2float_ru(ax));
+            }
         }
-        mx = fmax(fmax(mx, fmax(fabs(x[kc][0]), fabs(x[kc][1]))), fmax(fabs(x[kc][2]), fabs(x[kc][3])));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        int e = 0;
+        if (mx > 0.0) (void)frexp(mx, &e);  // mx = m 2^e, m in [0.5, 1)
+        if (e < -900) e = -900;
+        if (lane == 0) sa[g] = (float)e;
+        const double scale = pow2(46 - e);
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) to_w48(x[kc][j], scale, lo[j], hi[j]);
+#pragma unroll
+            for (int s = 0; s < ND; ++s) stage[warp][s][(((lane >> 2) ^ (r & 7)) << 2) | (lane & 3)] = plane_word(lo, hi, s);
+            __syncwarp();
+            for (int idx = lane; idx < ND * 8; idx += 32) {
+                const int s = idx >> 3, ch = idx & 7;
+                const uint4 v = *reinterpret_cast<const uint4*>(&stage[warp][s][ch * 4]);
+                signed char* t = A8 + (((long)s * nt + tile) * nkc + kc) * ATILE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + ch * 16;
+                *reinterpret_cast<uint4*>(t) = v;
+            }
+            __syncwarp();
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    int e = 0;
-    if (mx > 0.0) (void)frexp(mx, &e);  // mx = m 2^e, m in [0.5, 1)
-    if (e < -900) e = -900;
-    if (lane == 0) sa[g] = (float)e;
-    const double scale = pow2(46 - e);
+    for (int kc = 0; kc < NKC; ++kc)
 #pragma unroll
-    for (int kc = 0; kc < NKC; ++kc) {
-        if (kc >= nkc) break;
-        uint32_t lo[4], hi[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) to_w48(x[kc][j], scale, lo[j], hi[j]);
-#pragma unroll
-        for (int s = 0; s < ND; ++s) stage[warp][s][(((lane >> 2) ^ (r & 7)) << 2) | (lane & 3)] = plane_word(lo, hi, s);
-        __syncwarp();
-        for (int idx = lane; idx < ND * 8; idx += 32) {
-            const int s = idx >> 3, ch = idx & 7;
-            const uint4 v = *reinterpret_cast<const uint4*>(&stage[warp][s][ch * 4]);
-            signed char* t = A8 + (((long)s * nt + tile) * nkc + kc) * ATILE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + ch * 16;
-            *reinterpret_cast<uint4*>(t) = v;
-        }
-        __syncwarp();
-    }
+        for (int j = 0; j < 4; ++j) atomicMax(&cm[kc * KC + lane * 4 + j], __float_as_uint(cmx[kc][j]));
+    __syncthreads();
+    for (int c = threadIdx.x; c < NKC * KC; c += 256) cmax[tile * NpadK + c] = __uint_as_float(cm[c]);
 }
 
 // Column-scaled planes of S (rowquad B operand): B8[t][column tile (64)][k-chunk][8 KB tile], B[n = j][k = i] = S[i][j];
@@ -271,21 +292,22 @@ struct Pipe {
 struct RqSched {
     const signed char *A, *B;
     long a_plane, b_plane, tile;
-    int nkc, nct, Nc, tri, dbg;
-    __device__ int nunits() const { return nct; }
+    int nkc, nct, Nc, tri, P, p;  // this CTA takes the column tiles ct = p, p + P, ... of its row tile
+    __device__ int nunits() const { return (nct - p + P - 1) / P; }
+    __device__ int ct_of(int u) const { return u * P + p; }
     __device__ int kbeg(int) const { return 0; }
-    __device__ int kend(int ct) const {
+    __device__ int kend(int u) const {
         if (!tri) return (Nc + KC - 1) / KC;
-        const int last = min(Nc, (ct + 1) * IN);  // S is upper triangular: rows i <= last column only
+        const int last = min(Nc, (ct_of(u) + 1) * IN);  // S is upper triangular: rows i <= last column only
         return (last + KC - 1) / KC;
     }
     __device__ long aoff(int, int kc) const { return (tile * nkc + kc) * (long)ATILE; }
-    __device__ long boff(int ct, int kc) const { return ((long)ct * nkc + kc) * (long)BTILE; }
+    __device__ long boff(int u, int kc) const { return ((long)ct_of(u) * nkc + kc) * (long)BTILE; }
 };
 struct WsSched {
     const signed char *A, *B;
     long a_plane, b_plane;
-    int it, jt, njt, ngc, blk0, blk1, dbg;
+    int it, jt, njt, ngc, blk0, blk1;
     __device__ int nunits() const { return blk1 - blk0; }
     __device__ int kbeg(int u) const { return (blk0 + u) * KDC; }
     __device__ int kend(int u) const { return min(ngc, (blk0 + u + 1) * KDC); }
@@ -421,7 +443,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
     const Pipe p = pipe_setup(smem_raw, &tslot);
     const int warp = warp_uniform_idx(), lane = threadIdx.x & 31;
     RqSched sc = a.sc;
-    sc.tile = blockIdx.x;
+    sc.tile = blockIdx.x / sc.P;  // the P CTAs of a row tile are neighbours: they run together and share its A planes in L2
+    sc.p = blockIdx.x % sc.P;
     if (warp == 1) tmem_alloc(tslot, 512);
     tc_fence_before();
     __syncthreads();
@@ -439,8 +462,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
         const int r = qd * 32 + lane;
         const long g = sc.tile * IM + r;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int ct = 0; ct < sc.nct; ++ct) {
-            const int col = ct * IN + CW * cq;
+        const int nu = sc.nunits();
+        for (int u = 0; u < nu; ++u) {
+            const int col = sc.ct_of(u) * IN + CW * cq;
             const bool live = col < a.Npad;  // Npad is a multiple of 32 and col of 16; digits of columns >= Nc are zero
             // the FP64 ao_0 values of this thread's row are fetched before the wait, so that after the drain the row-dot is
             // arithmetic only and the warp is back in time for the next (possibly short) column tile
@@ -450,7 +474,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
 #pragma unroll
                 for (int j = 0; j < CW / 2; ++j) a0[j] = ap[j];
             }
-            mbar_wait(p.tfull, ct & 1);
+            mbar_wait(p.tfull, u & 1);
             __syncwarp();
             tc_fence_after();
             double T[CW];
@@ -504,7 +528,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
                     double t = acc[c];
 #pragma unroll
                     for (int k = 0; k < NEW / 4 - 1; ++k) t += part[(k * 4 + c) * IM + r];
-                    a.q[(long)c * a.q_cstride + g] = a.f[c] * rs * t;
+                    // P > 1: partial sums of this CTA's column tiles, [p][c][g], added up by rowquad_i8_sum_kernel
+                    a.q[((long)sc.p * (sc.P > 1 ? 4 : 0) + c) * a.q_cstride + g] = a.f[c] * rs * t;
                 }
         }
     }
@@ -513,13 +538,25 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
     if (warp == 1) tmem_free(tm, 512);
 }
 
+// q[c][g] = sum_p part[p][c][g] (fixed order)
+__global__ void __launch_bounds__(256) rowquad_i8_sum_kernel(const double* __restrict__ part, long pstride, int P, double* __restrict__ q,
+                                                             long q_cstride, int ncomp, long n) {
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    for (int c = 0; c < ncomp; ++c) {
+        double t = 0.0;
+        for (int p = 0; p < P; ++p) t += part[((long)p * 4 + c) * pstride + g];
+        q[(long)c * q_cstride + g] = t;
+    }
+}
+
 // ---- wsyrk ------------------------------------------------------------------------------------------------------------
 struct WsArgs {
     const signed char *A, *B;   // unweighted / weighted column-scaled planes
     long plane_stride;
     const int *eA, *eB;         // block exponents [nblk][NpadK]
     double* part;               // [nsplit][ntile][128 x 64]
-    int NpadK, njt, njtL, ngc, nblk, ntile, nsplit, sym, dbg;  // njt: column tiles that hold data (tile enumeration); njtL: pitch of the plane layout
+    int NpadK, njt, njtL, ngc, nblk, ntile, nsplit, sym;  // njt: column tiles that hold data (tile enumeration); njtL: pitch of the plane layout
 };
 
 __device__ __forceinline__ void ws_tile(const WsArgs& a, int t, int& it, int& jt) {
@@ -546,7 +583,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) wsyrk_i8_kernel(const WsArgs a)
     sc.A = a.A, sc.B = a.B, sc.a_plane = sc.b_plane = a.plane_stride;
     ws_tile(a, t, sc.it, sc.jt);
     sc.njt = a.njtL, sc.ngc = a.ngc;
-    sc.dbg = a.dbg;
     sc.blk0 = (int)((long)a.nblk * sp / a.nsplit), sc.blk1 = (int)((long)a.nblk * (sp + 1) / a.nsplit);
     if (warp == 1) tmem_alloc(tslot, 512);
     tc_fence_before();
@@ -629,6 +665,7 @@ struct I8Ws {
     signed char *A = nullptr, *Bs = nullptr;  // rowquad: row-scaled ao planes, S planes
     float* sa = nullptr;
     double* sb = nullptr;
+    double* qpart = nullptr;                  // rowquad: partial sums [4 column groups][4 components][GpadMax]
     signed char *T = nullptr, *W = nullptr;   // wsyrk: column-scaled planes of ao_0 (per geometry) and of the weighted operand (per call)
     float *cmax = nullptr, *cmaxW = nullptr;  // 128-row column maxima of ao_0 / of a general B operand
     int *eA = nullptr, *eB = nullptr;
@@ -656,7 +693,7 @@ int i8_alloc(qexxc_ctx* c) {
         return true;
     };
     bool ok = A((void**)&w->A, planes) && A((void**)&w->T, planes) && A((void**)&w->W, planes) && A((void**)&w->Bs, sbytes) &&
-              A((void**)&w->sa, sizeof(float) * c->GpadMax) && A((void**)&w->sb, sizeof(double) * w->NpadK) &&
+              A((void**)&w->sa, sizeof(float) * c->GpadMax) && A((void**)&w->qpart, sizeof(double) * 16 * (size_t)c->GpadMax) && A((void**)&w->sb, sizeof(double) * w->NpadK) &&
               A((void**)&w->cmax, sizeof(float) * (size_t)w->ngcMax * w->NpadK) &&
               A((void**)&w->eA, sizeof(int) * (size_t)w->nblkMax * w->NpadK) && A((void**)&w->eB, sizeof(int) * (size_t)w->nblkMax * w->NpadK);
     if (ok && c->C == 4) ok = A((void**)&w->cmaxW, sizeof(float) * (size_t)w->ngcMax * w->NpadK);
@@ -679,11 +716,11 @@ int i8_prepare(qexxc_ctx* c, cudaStream_t st) {
     if (c->i8_valid) return QEXXC_OK;
     I8Ws* w = (I8Ws*)c->i8ws;
     ProfScope prof(c, QEXXC_PROF_SLICE, st);
-    const unsigned nb = (unsigned)((c->Gpad + 7) / 8);
+    const unsigned nb = (unsigned)(c->Gpad / 128);
     switch (w->nkc) {
-#define QX_SR(K)                                                                                   \
-    case K:                                                                                        \
-        slice_rows_kernel<K><<<nb, 256, 0, st>>>(c->ao, c->Npad, w->nkc, c->Gpad, w->A, w->sa);   \
+#define QX_SR(K)                                                                                                          \
+    case K:                                                                                                               \
+        slice_rows_kernel<K><<<nb, 256, 0, st>>>(c->ao, c->Npad, w->nkc, c->Gpad, w->A, w->sa, w->NpadK, w->cmax);      \
         break
         QX_SR(1); QX_SR(2); QX_SR(3); QX_SR(4); QX_SR(5); QX_SR(6); QX_SR(7); QX_SR(8);
         QX_SR(9); QX_SR(10); QX_SR(11); QX_SR(12); QX_SR(13); QX_SR(14); QX_SR(15); QX_SR(16);
@@ -694,8 +731,6 @@ int i8_prepare(qexxc_ctx* c, cudaStream_t st) {
     }
     QX_LAUNCH_CHECK(c);
     const int ngc = c->Gpad / 128, nblk = (ngc + KDC - 1) / KDC;
-    colmax_kernel<<<ngc, 256, 0, st>>>(c->ao, c->Npad, w->NpadK, w->cmax);
-    QX_LAUNCH_CHECK(c);
     blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmax, nullptr, ngc, w->NpadK, w->eA);
     QX_LAUNCH_CHECK(c);
     slice_cols_kernel<<<dim3(ngc, w->NpadK / 128), 256, ND * 16384, st>>>(c->ao, c->Npad, nullptr, w->eA, w->NpadK, w->njt, w->plane_stride, w->T);
@@ -819,21 +854,30 @@ int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, doub
     a.sc.nct = (c->Nc + IN - 1) / IN;  // column tiles that hold data
     a.sc.Nc = c->Nc;
     a.sc.tri = tri;
-    a.sc.dbg = 0;
     a.sa = w->sa;
     a.sb = w->sb;
     a.ao = c->ao;
-    a.q = q;
+    // column groups per row tile: the A planes of a row tile (6 nkc x 16 KB) are re-read by every column tile; with one CTA
+    // per row tile the planes of all resident CTAs (148 x 768 KB at nao = 1000) do not stay in L2
+    int P = 1;
+    while (P < 4 && (long)(c->num_sms / P) * ND * w->nkc * ATILE > (64L << 20) && a.sc.nct >= 4 * P) P *= 2;
+    if (getenv("QEXXC_I8_P")) P = std::max(1, std::min(4, atoi(getenv("QEXXC_I8_P"))));
+    a.sc.P = P;
+    a.q = P > 1 ? w->qpart : q;
     a.ao_cstride = (long)c->GpadMax * c->Npad;
-    a.q_cstride = q_cstride;
+    a.q_cstride = P > 1 ? (long)c->GpadMax : q_cstride;
     a.Npad = c->Npad;
     a.ncomp = ncomp;
     a.f[0] = (tri ? 2.0 : 1.0) * fac4[0];
     a.f[1] = fac4[1];
     a.f[2] = fac4[2];
     a.f[3] = fac4[3];
-    rowquad_i8_kernel<<<(unsigned)ntiles, I8_THREADS, i8_smem(), st>>>(a);
+    rowquad_i8_kernel<<<(unsigned)(ntiles * P), I8_THREADS, i8_smem(), st>>>(a);
     QX_LAUNCH_CHECK(c);
+    if (P > 1) {
+        rowquad_i8_sum_kernel<<<(unsigned)((c->Gpad + 255) / 256), 256, 0, st>>>(w->qpart, c->GpadMax, P, q, q_cstride, ncomp, c->Gpad);
+        QX_LAUNCH_CHECK(c);
+    }
     return QEXXC_OK;
 }
 
@@ -894,7 +938,6 @@ int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double sc
     a.ntile = ntile;
     a.nsplit = nsplit;
     a.sym = sym ? 1 : 0;
-    a.dbg = getenv("QEXXC_I8_DBG") ? atoi(getenv("QEXXC_I8_DBG")) : 0;
     wsyrk_i8_kernel<<<(unsigned)(ntile * nsplit), I8_THREADS, i8_smem(), st>>>(a);
     QX_LAUNCH_CHECK(c);
     wsyrk_i8_reduce_kernel<<<dim3((c->N + 31) / 32, (c->N + 7) / 8), 256, 0, st>>>(c->part, out, c->N, njt, ntile, nsplit, sym ? 1 : 0, scale, tadd);

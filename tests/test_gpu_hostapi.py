@@ -228,15 +228,19 @@ def test_full_size_c5_properties():
         r = ((a @ S) * a).sum(1)
         worst = max(worst, (r - rho_k[lo : lo + 65536]).abs().max().item())
         Vref += a.T @ (a * (wt[lo : lo + 65536] * vrho_k[lo : lo + 65536])[:, None])
-    assert worst <= 1e-12 * rho_k.abs().max().item()
-    assert rel_err(V, Vref.cpu().numpy()) <= 1e-11
+    # FP64 DMMA path: rounding only (1e-12 / 1e-11).  INT8 digit-split path (the default at this nao): operands are
+    # fixed point with 46 bits below the row / column maximum and digit products beyond 256^-5 are dropped, which is
+    # ~1e-12 of the largest element -- still two orders inside the 1e-10 bar of BASELINE.json
+    int8 = ctx.contraction_mode == "int8"
+    assert worst <= (2e-11 if int8 else 1e-12) * rho_k.abs().max().item()
+    assert rel_err(V, Vref.cpu().numpy()) <= (3e-11 if int8 else 1e-11)
     del ao, Vref
     # additivity: a local functional's outputs are sums over grid points
     cut = 2048
     oa, ba = run(0, cut)
     ob, bb = run(cut, G)
-    assert rel_err((oa + ob).cpu().numpy(), out.cpu().numpy()) <= 1e-11
-    assert rel_err((ba + bb).cpu().numpy(), bar.cpu().numpy()) <= 1e-11
+    assert rel_err((oa + ob).cpu().numpy(), out.cpu().numpy()) <= (3e-11 if int8 else 1e-11)
+    assert rel_err((ba + bb).cpu().numpy(), bar.cpu().numpy()) <= (3e-11 if int8 else 1e-11)
     m = wl.mol
     ref = step_ref.xc_step(m._atm, m._bas, m._env, wl.coords[:cut], wl.weights[:cut], wl.dm, wl.net, wl.theta, "NN",
                            wl.e_bar, wl.v_bar)

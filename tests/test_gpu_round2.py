@@ -324,14 +324,17 @@ def test_full_size_c5gga_properties():
     del ao
     V = out.cpu().numpy()[0][: N * N].reshape(N, N)
     Vr = (Vref + Vref.T).cpu().numpy()
-    assert worst <= 1e-12 * rho_k.abs().max().item()
-    assert rel_err(V, Vr) <= 1e-11
+    # FP64 DMMA path: rounding only.  INT8 digit-split path (default at this nao): ~1e-12 of the largest element from the
+    # 46-bit fixed point and the dropped 256^-6 products -- two orders inside the 1e-10 bar (tests/test_gpu_i8.py)
+    int8 = ctx.contraction_mode == "int8"
+    assert worst <= (2e-11 if int8 else 1e-12) * rho_k.abs().max().item()
+    assert rel_err(V, Vr) <= (3e-11 if int8 else 1e-11)
     del Vref
     cut = 2048
     oa, ba, _ = run(0, cut)
     ob, bb, _ = run(cut, G)
-    assert rel_err((oa + ob).cpu().numpy(), out.cpu().numpy()) <= 1e-11
-    assert rel_err((ba + bb).cpu().numpy(), bar.cpu().numpy()) <= 1e-11
+    assert rel_err((oa + ob).cpu().numpy(), out.cpu().numpy()) <= (3e-11 if int8 else 1e-11)
+    assert rel_err((ba + bb).cpu().numpy(), bar.cpu().numpy()) <= (3e-11 if int8 else 1e-11)
     m = wl.mol
     ref = step_ref.xc_step(m._atm, m._bas, m._env, wl.coords[:cut], wl.weights[:cut], wl.dm, wl.net, wl.theta, "GGA",
                            wl.e_bar, wl.v_bar)
