@@ -18,6 +18,11 @@ KEYS = [
     ("duration", "gpu__time_duration.sum"),
     ("DMMA sub-pipe % of peak (active)", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active"),
     ("tensor pipe active % (elapsed)", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+    ("tensor pipe active % (active cycles)", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+    ("INT8 (IMMA) sub-pipe active %", "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active"),
+    ("shared-memory wavefronts of tensor-core operand reads % of peak", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+    ("L2 -> SM read", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second"),
+    ("L2 throughput % of peak", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("FP64 (non-tensor) pipe %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
     ("issue slots busy %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
     ("DRAM read", "dram__bytes_read.sum"),
@@ -68,15 +73,18 @@ def main(d):
             if key in rec and rec[key] != "":
                 lines.append(f"- {label}: {rec[key]} {u.get(key, '')}".rstrip())
         lines.append("")
-    ll = os.path.join(d, "launches_gpu_time.csv")
-    if os.path.exists(ll):
+    for ll, bj_name, title in ((os.path.join(d, "launches_gpu_time_int8.csv"), "bench_c5_n1_int8.json", "INT8 contractions (default for nao >= 256)"),
+                               (os.path.join(d, "launches_gpu_time.csv"), "bench_c5_n1.json", "FP64 DMMA contractions (QEXXC_I8=0)")):
+        if not os.path.exists(ll):
+            continue
+        lines += [f"# {title}", ""]
         rows = [r for r in csv.reader(l for l in open(ll) if not l.startswith("=="))]
         h = rows[0]
         ki, vi = h.index("Kernel Name"), len(h) - 1
         agg = collections.OrderedDict()
         for r in rows[1:]:
             k = short(r[ki])
-            if k.startswith("cutlass") or k.startswith("at::"):
+            if k.startswith("cutlass") or k.startswith("at::") or k.startswith("i8_peak"):
                 continue  # bench.py's own cuBLAS DGEMM peak measurement and torch fills
             a = agg.setdefault(k, [0, 0.0])
             a[0] += 1
@@ -87,8 +95,9 @@ def main(d):
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             lines.append(f"{k} | {n} | {t / 1e6:.3f} | {t / tot:.4f}")
         lines.append("")
-    bj = os.path.join(d, "bench_c5_n1.json")
-    if os.path.exists(bj):
+        bj = os.path.join(d, bj_name)
+        if not os.path.exists(bj):
+            continue
         b = json.load(open(bj))
         lines += ["## bench.py c5, N=1 (CUDA events on the launching stream, in-run shares)",
                   f"- step: {b['ms_per_step']:.2f} ms -> {b['value']:.4g} {b['unit']}; e2e {b['e2e']['value']:.4g}; "

@@ -219,12 +219,19 @@ def _run_full(wl, precision="f64"):
     return ctx, out, bar, resid
 
 
-def _check_vs_oracle(out, bar, ref, N):
+def _check_vs_oracle(out, bar, ref, N, int8=False):
+    """`int8`: the contractions ran as exact INT8 digit products of FIXED-POINT operands (csrc/contract_i8.cu): the error
+    of a V_xc / dm_bar element is ~1e-12 of the LARGEST element whatever its own size, so elements below ~1e-2 of the
+    largest are not relatively accurate to 1e-10 the way the FP64 DMMA path's are (floor 1e-6); E_xc, nelec and theta_bar
+    (sums over rho, which carries a per-grid-row exponent) keep the strict bars."""
     o, b = out.cpu().numpy()[0], bar.cpu().numpy()
     V, D, tb = o[: N * N].reshape(N, N), b[: N * N].reshape(N, N), b[N * N :]
     assert abs(o[N * N] - ref["excsum"]) <= 1e-9 and abs(o[N * N + 1] - ref["nelec"]) <= 1e-9 * max(1.0, abs(ref["nelec"]))
     assert rel_err(V, ref["vmat"]) <= TOL64 and rel_err(D, ref["dm_bar"]) <= TOL64 and rel_err(tb, ref["theta_bar"]) <= TOL64
-    assert elem_err(V, ref["vmat"]) <= TOL_ELEM and elem_err(D, ref["dm_bar"]) <= TOL_ELEM
+    floor = 1e-2 if int8 else 1e-6
+    assert elem_err(V, ref["vmat"], floor) <= TOL_ELEM and elem_err(D, ref["dm_bar"], floor) <= TOL_ELEM
+    if int8:
+        assert rel_err(V, ref["vmat"]) <= 1e-11 and rel_err(D, ref["dm_bar"]) <= 1e-11
     assert elem_err(tb, ref["theta_bar"]) <= TOL_ELEM
 
 
@@ -275,7 +282,7 @@ def test_full_size_c4_64_molecules_against_the_oracle():
     ctx.close()
 
 
-def test_full_size_c5gga_properties():
+def test_full_size_c5gga_properties(monkeypatch):
     """c5 with GGA features at full size (1000 AOs x 1e6 points x 4 components = 33.6 GB of AO values):
     determinism, the four-component rho and the V_xc contraction against library GEMMs on the same AO tensor,
     additivity over grid shards, and a leading shard against the oracle."""
@@ -338,7 +345,12 @@ def test_full_size_c5gga_properties():
     m = wl.mol
     ref = step_ref.xc_step(m._atm, m._bas, m._env, wl.coords[:cut], wl.weights[:cut], wl.dm, wl.net, wl.theta, "GGA",
                            wl.e_bar, wl.v_bar)
-    _check_vs_oracle(oa, ba, ref, N)
+    _check_vs_oracle(oa, ba, ref, N, int8=int8)
+    if int8:  # the same shard with the contractions on the FP64 tensor pipe: the strict element-wise bar
+        monkeypatch.setenv("QEXXC_I8", "0")
+        oa, ba, _ = run(0, cut)
+        assert ctx.contraction_mode == "dmma"
+        _check_vs_oracle(oa, ba, ref, N, int8=False)
     ctx.close()
 
 
@@ -439,6 +451,10 @@ def test_n_rank_allreduced_result_equals_one_rank(world):
     assert np.array_equal(h_out, oa) and np.array_equal(h_bar, ba)  # host pipeline == device-resident step
     on = oa[0]
     assert abs(on[nn] - o1[nn]) <= 1e-9 and abs(on[nn + 1] - o1[nn + 1]) <= 1e-9 * max(1.0, abs(o1[nn + 1]))
-    for a, b in ((on[:nn], o1[:nn]), (ba[:nn], b1[:nn]), (ba[nn:], b1[nn:])):
-        assert rel_err(a, b) <= TOL64 and elem_err(a, b) <= TOL_ELEM
+    # INT8 contractions (default at this nao): fixed-point operands whose exponent blocks depend on the shard boundaries, so
+    # the N-rank and 1-rank V_xc / dm_bar agree to ~1e-12 of the largest element, not element by element
+    int8 = ctx.contraction_mode == "int8"
+    for k, (a, b) in enumerate(((on[:nn], o1[:nn]), (ba[:nn], b1[:nn]), (ba[nn:], b1[nn:]))):
+        assert rel_err(a, b) <= (1e-11 if int8 else TOL64)
+        assert elem_err(a, b, 1e-2 if (int8 and k < 2) else 1e-6) <= TOL_ELEM
     ctx.close()
