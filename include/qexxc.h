@@ -241,6 +241,10 @@ int qexxc_contraction_flops(qexxc_ctx* ctx, int which, int symmetric, double* ex
  * 0 = FP64 DMMA (contract.cu), 1 = exact INT8 digit split on tcgen05 (contract_i8.cu; env QEXXC_I8=0/1 overrides the
  * default "nao >= 256, single molecule").  Results agree to ~1e-12 of the largest element either way. */
 int qexxc_contraction_mode(const qexxc_ctx* ctx);
+/* Builds now, on `stream`, whatever the contractions derive from the AO tensor alone (mode 1: the digit planes of ao_0), so
+ * that it overlaps the upload of the density matrix instead of running inside the first contraction.  Optional: the
+ * contractions build it on first use.  No-op in mode 0.  Needs qexxc_eval_ao / qexxc_set_ao first. */
+int qexxc_prepare_contractions(qexxc_ctx* ctx, void* stream);
 /* INT8 multiply-add operations (2 per MAC) one launch of rowquad (0) / wsyrk (1) executes in mode 1. */
 int qexxc_contraction_i8_ops(qexxc_ctx* ctx, int which, int symmetric, double* executed_ops);
 /* Measures the INT8 tensor-core rate of `device` with the library's own issue loop (kind::i8, M = 128, N = 256, K = 32,

@@ -27,7 +27,7 @@ EXPORTS = [
     "qexxc_get_ao", "qexxc_eval_rho", "qexxc_eval_rho_vjp", "qexxc_xc_fwd", "qexxc_xc_vjp",
     "qexxc_apply_fn_fwd", "qexxc_apply_fn_vjp", "qexxc_vxc_assemble", "qexxc_vxc_assemble_vjp",
     "qexxc_resid_doubles", "qexxc_nr_rks_fwd", "qexxc_nr_rks_vjp", "qexxc_launch_count",
-    "qexxc_debug_run_contraction", "qexxc_profile_enable", "qexxc_profile_read", "qexxc_contraction_flops", "qexxc_contraction_mode", "qexxc_contraction_i8_ops", "qexxc_i8_peak", "qexxc_eval_rho_mo", "qexxc_nr_rks_fwd_mo",
+    "qexxc_debug_run_contraction", "qexxc_profile_enable", "qexxc_profile_read", "qexxc_contraction_flops", "qexxc_contraction_mode", "qexxc_prepare_contractions", "qexxc_contraction_i8_ops", "qexxc_i8_peak", "qexxc_eval_rho_mo", "qexxc_nr_rks_fwd_mo",
     "qexxc_jk_workspace_doubles", "qexxc_dot_eri_dm", "qexxc_dot_eri_dm_vjp", "qexxc_jk_launch_count",
     "qexxc_dot_eri_dm_batched", "qexxc_dot_eri_dm_vjp_batched", "qexxc_generalized_eigh_batched",
     "qexxc_becke_partition", "qexxc_grid_launch_count", "qexxc_lda_exchange", "qexxc_lda_launch_count",
@@ -105,6 +105,7 @@ def load(build_if_missing: bool = False):
         "qexxc_nr_rks_fwd_mo": (i, [vp, i, p, p, i, p, l, p, p, vp]),
         "qexxc_contraction_flops": (i, [vp, i, i, C.POINTER(C.c_double)]),
         "qexxc_contraction_mode": (i, [vp]),
+        "qexxc_prepare_contractions": (i, [vp, vp]),
         "qexxc_contraction_i8_ops": (i, [vp, i, i, C.POINTER(C.c_double)]),
         "qexxc_i8_peak": (i, [i, C.POINTER(C.c_double)]),
         "qexxc_profile_read": (i, [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_long)]),

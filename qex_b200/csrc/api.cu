@@ -826,6 +826,14 @@ int qexxc_contraction_flops(qexxc_ctx* c, int which, int symmetric, double* exec
     return QEXXC_OK;
 }
 
+int qexxc_prepare_contractions(qexxc_ctx* c, void* stream) {
+    QX_ARG(c != nullptr, "ctx is null");
+    if (!i8_enabled(c)) return QEXXC_OK;
+    QX_TRY(need_ao(c, 1));
+    QX_CUDA(cudaSetDevice(c->device));
+    return i8_prepare_geometry(c, (cudaStream_t)stream);
+}
+
 int qexxc_contraction_mode(const qexxc_ctx* c) { return (c && i8_enabled(c)) ? 1 : 0; }
 
 int qexxc_contraction_i8_ops(qexxc_ctx* c, int which, int symmetric, double* executed) {

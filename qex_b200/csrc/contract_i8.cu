@@ -741,6 +741,8 @@ int i8_prepare(qexxc_ctx* c, cudaStream_t st) {
 
 }  // namespace
 
+int i8_prepare_geometry(qexxc_ctx* c, cudaStream_t st) { return i8_prepare(c, st); }
+
 void i8_release(qexxc_ctx* c) {
     delete (I8Ws*)c->i8ws;
     c->i8ws = nullptr;

@@ -239,14 +239,17 @@ class ShardedXC:
         d_inp = io["d_inp"]
         s_in.wait_stream(main)
         side.wait_stream(main)
-        # grid shard of this rank + the replicated (dm | theta)
+        # grid shard of this rank first (the AO evaluation waits for it; H2D copies share one engine)
         d_coords.copy_(h_coords, non_blocking=True)
         d_weights.copy_(h_weights, non_blocking=True)
-        if self.rank == 0:
-            d_inp[:n1].copy_(io["h_inp"][:n1], non_blocking=True)
-        self._bcast(d_inp[:n1], main)
-        # cotangents: needed by the VJP only -> side stream, behind the first broadcast in NCCL's issue order
+        # the replicated (dm | theta), then the cotangents (needed by the VJP only), travel on a side stream: upload on rank
+        # 0, NCCL broadcast over NVLink -- under this rank's grid upload, AO evaluation and digit slicing, which need neither
         with torch.cuda.stream(s_in):
+            if self.rank == 0:
+                d_inp[:n1].copy_(io["h_inp"][:n1], non_blocking=True)
+            self._bcast(d_inp[:n1], s_in)
+            ev_dm = torch.cuda.Event()
+            ev_dm.record(s_in)
             if self.rank == 0:
                 d_inp[n1:].copy_(io["h_inp"][n1:], non_blocking=True)
             self._bcast(d_inp[n1:], s_in)
@@ -256,6 +259,8 @@ class ShardedXC:
         v_bar = d_inp[n1 + B :].view(B, N, N)
         ctx.set_grid(d_coords, d_weights)
         ctx.eval_ao(deriv)
+        ctx.prepare_contractions()
+        main.wait_event(ev_dm)
         ctx.nr_rks_fwd(dm, theta, xctype, hermi, out=io["out"], resid=io["resid"])
         side.wait_stream(main)
         side.wait_stream(s_in)  # keeps NCCL's per-communicator issue order identical to the stream order

@@ -349,6 +349,13 @@ class XCContext:
         """"int8" (exact digit split on tcgen05, contract_i8.cu) or "dmma" (FP64 tensor pipe) for this context."""
         return "int8" if self.lib.qexxc_contraction_mode(self._h) else "dmma"
 
+    def prepare_contractions(self):
+        """Build what the contractions derive from the AO tensor alone (INT8 mode: the digit planes) now, on the current
+        stream, instead of inside the first contraction -- lets it overlap an upload of the density matrix."""
+        with torch.cuda.device(self.device):
+            check(self.lib.qexxc_prepare_contractions(self._h, _stream()))
+        return self
+
     def contraction_i8_ops(self, which: int, symmetric: bool) -> float:
         """INT8 operations (2 per MAC) one launch of rowquad (0) / wsyrk (1) executes in "int8" mode."""
         v = C.c_double(0)
