@@ -677,10 +677,10 @@ def run_ours(args):
             "stage4": 0.5 * 8.0 * ((C_ + 3 + (C_ == 4) + C_) + (2 * C_ + 3 + (C_ == 4) + C_ + 2 + (C_ == 4))) * res["Gl"] * res["Bl"],
         }
         if res["mode"] == "int8":
-            # per step: geometry planes (read ao 3x: rows, column maxima, columns; write 2 x 6 planes) + two weighted
-            # operands (read ao, write 6 planes); per launch of the class = that total over its recorded scopes
+            # per step: the row-scaled planes of the geometry (read ao once, write 6 planes; the column maxima come from the same
+            # pass) + two weighted operands (read ao, write 6 planes); per launch of the class = that total over its scopes
             npk = ((res["npad"] + 127) // 128) * 128
-            per_step = (3 * 8.0 * res["npad"] + 12.0 * npk + 2 * (8.0 * res["npad"] + 6.0 * npk)) * res["Gl"]
+            per_step = 3 * (8.0 * res["npad"] + 6.0 * npk) * res["Gl"]
             nsl = kern["slice"]["launches"] or 1
             stream_bytes["slice"] = per_step * args.steps / nsl
         streaming = {}
@@ -689,7 +689,7 @@ def run_ours(args):
             if k["launches"]:
                 gbs = nbytes / (k["avg_ms"] * 1e-3) / 1e9
                 streaming[name] = {"kernel": {"eval_ao": "eval_ao_kernel (K1)", "stage4": "stage4_fwd/vjp kernels",
-                                              "slice": "slice_rows / colmax / slice_cols (INT8 digit planes)"}[name],
+                                              "slice": "slice_rows (+ column maxima) / slice_cols (INT8 digit planes)"}[name],
                                    "bytes_per_launch": nbytes, "avg_ms": k["avg_ms"], "gbs": gbs,
                                    "frac_of_hbm_peak": gbs / hbm if hbm else None}
         int8 = res["mode"] == "int8"

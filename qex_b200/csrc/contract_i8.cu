@@ -22,12 +22,14 @@
 // needed), warp 1 issues the tcgen05.mma stream, warps 2..9 drain the accumulators (tcgen05.ld).
 //   rowquad: M = 128 grid rows (row-scaled digits of ao_0), N = 64 columns of S, K = AO index; the epilogue row-dots the
 //            recombined (ao_0 S) tile with the FP64 ao_c rows.
-//   wsyrk:   M = 128 AO rows i, N = 64 AO columns j, K = grid index.  The fixed-point exponents are per COLUMN of ao and
-//            per block of 4096 grid rows (block floating point along K); the INT32 accumulators are drained into FP64
-//            registers at every block boundary, where the block's scales are applied.
+//   wsyrk:   M = 128 AO rows i, N = 64 AO columns j, K = grid index.  A = the SAME row-scaled planes as rowquad, read MN-major
+//            (a [128 grid rows x 128 AO bytes] tile is the [AO x grid] operand transposed; exact integers relative to each
+//            row's maximum); B = s[g] 2^ea[g] ao_0[g,j] sliced per call with fixed-point exponents per COLUMN and per block of
+//            4096 grid rows (block floating point along K); the INT32 accumulators are drained into FP64 registers at every
+//            block boundary, where the block's scale is applied.
 //
 // Policy: QEXXC_I8=1 forces this path, QEXXC_I8=0 the FP64 DMMA path; unset = this path when nao >= 256 (single-molecule
-// contexts).  Cost: 18 bytes of digit planes per AO value of component 0.
+// contexts).  Cost: 12 bytes of digit planes per AO value of component 0.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -179,9 +181,13 @@ __global__ void __launch_bounds__(256) slice_s_kernel(const double* __restrict__
     }
 }
 
-// cmax[sub][col] >= max over the 128 grid rows of sub-block `sub` of |x[g][col]| (rounded up to float)
-__global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ x, int ld, int NpadK, float* __restrict__ cmax) {
+// cmax[sub][col] >= max over the 128 grid rows of sub-block `sub` of |x[g][col]| 2^rexp[g] (rounded up to float)
+__global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ x, int ld, int NpadK, const float* __restrict__ rexp,
+                                                     float* __restrict__ cmax) {
     const long g0 = (long)blockIdx.x * 128;
+    __shared__ double rf[128];
+    if (threadIdx.x < 128) rf[threadIdx.x] = rexp ? pow2((int)rexp[g0 + threadIdx.x]) : 1.0;
+    __syncthreads();
     for (int c = 4 * threadIdx.x; c < NpadK; c += 1024) {
         double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
         if (c < ld) {
@@ -189,7 +195,8 @@ __global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ 
 #pragma unroll 8
             for (int r = 0; r < 128; ++r) {
                 const double2 u = *reinterpret_cast<const double2*>(p + (long)r * ld), v = *reinterpret_cast<const double2*>(p + (long)r * ld + 2);
-                m0 = fmax(m0, fabs(u.x)), m1 = fmax(m1, fabs(u.y)), m2 = fmax(m2, fabs(v.x)), m3 = fmax(m3, fabs(v.y));
+                const double f = rf[r];
+                m0 = fmax(m0, f * fabs(u.x)), m1 = fmax(m1, f * fabs(u.y)), m2 = fmax(m2, f * fabs(v.x)), m3 = fmax(m3, f * fabs(v.y));
             }
         }
         *reinterpret_cast<float4*>(cmax + (long)blockIdx.x * NpadK + c) =
@@ -197,41 +204,43 @@ __global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ 
     }
 }
 
-// Block exponents of the wsyrk operands: eexp[blk][col] = e with |s[g] x[g][col]| < 2^e for the (up to) 4096 grid rows of
-// block blk.  Exact for s == nullptr; with weights it is the bound  max_sub (max_{g in sub} |s[g]|) * cmax[sub][col]  over
-// the block's 128-row sub-blocks (tight up to the variation of s inside 128 consecutive grid points).
-__global__ void __launch_bounds__(256) blk_exp_kernel(const float* __restrict__ cmax, const double* __restrict__ s, int ngc, int NpadK,
-                                                      int* __restrict__ eexp) {
-    __shared__ float smax[KDC];
+// Block exponents of the wsyrk B operand: eexp[blk][col] = e with |s[g] 2^rexp[g] x[g][col]| < 2^e for the (up to) 4096 grid
+// rows of block blk.  Exact (up to float rounding of cmax) without weights; with weights it is the bound
+// max_sub (max_{g in sub} |s[g]| 2^rexp[g]) * cmax[sub][col] over the block's 128-row sub-blocks (tight up to the variation of the
+// row factor inside 128 consecutive grid points).
+__global__ void __launch_bounds__(256) blk_exp_kernel(const float* __restrict__ cmax, const double* __restrict__ s, const float* __restrict__ rexp,
+                                                      int ngc, int NpadK, int* __restrict__ eexp) {
+    __shared__ double smax[KDC];
     const int blk = blockIdx.x, gc0 = blk * KDC, nsub = min(KDC, ngc - gc0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int sub = warp; sub < nsub; sub += 8) {
-        float m = 1.0f;
+        double d = 1.0;
         if (s) {
-            const double* p = s + ((long)(gc0 + sub) * 128) + lane * 4;
-            double d = fmax(fmax(fabs(p[0]), fabs(p[1])), fmax(fabs(p[2]), fabs(p[3])));
+            const long g = ((long)(gc0 + sub) * 128) + lane * 4;
+            d = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d = fmax(d, fabs(s[g + k]) * (rexp ? pow2((int)rexp[g + k]) : 1.0));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
-            m = __double2float_ru(d);
         }
-        if (lane == 0) smax[sub] = m;
+        if (lane == 0) smax[sub] = d * (1.0 + 1e-6);  // slack for the roundings of the products formed later
     }
     __syncthreads();
     for (int c = threadIdx.x; c < NpadK; c += 256) {
-        float m = 0.0f;
-        for (int sub = 0; sub < nsub; ++sub) m = fmaxf(m, __fmul_ru(smax[sub], cmax[(long)(gc0 + sub) * NpadK + c]));
+        double m = 0.0;
+        for (int sub = 0; sub < nsub; ++sub) m = fmax(m, smax[sub] * (double)cmax[(long)(gc0 + sub) * NpadK + c]);
         int e = 0;
-        if (m > 0.0f) (void)frexpf(m, &e);
-        if (m > 3.0e38f) e = 129;  // overflowed bound (inf): keep the shift finite
+        if (m > 0.0) (void)frexp(m, &e);
+        e = max(-900, min(900, e));  // inf / denormal bounds: keep the shifts finite
         eexp[(long)blk * NpadK + c] = e;
     }
 }
 
-// Column-scaled planes of x[g][col] (* s[g]) for wsyrk, K = grid index:  P[plane][g-chunk][column tile (64)][8 KB tile],
+// Column-scaled planes of x[g][col] (* s[g]) (* 2^rexp[g]) for wsyrk, K = grid index:  P[plane][g-chunk][column tile (64)][8 KB tile],
 // tile row = column, tile byte = grid row inside the 128-row chunk.  One CTA per (g-chunk, 128 columns); a thread owns
 // one column and 16 consecutive grid rows = one 16-byte chunk per plane, staged in shared memory in the final layout.
 __global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restrict__ x, int ld, const double* __restrict__ s,
-                                                         const int* __restrict__ eexp, int NpadK, int njt, long plane_stride,
+                                                         const float* __restrict__ rexp, const int* __restrict__ eexp, int NpadK, int njt, long plane_stride,
                                                          signed char* __restrict__ P) {
     extern __shared__ __align__(1024) unsigned char stage[];  // [ND][128 columns][128 bytes]
     const int gc = blockIdx.x, cg = blockIdx.y, blk = gc / KDC;
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restric
     const long g0 = (long)gc * 128 + 16 * warp;
     double sv[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) sv[k] = s ? s[g0 + k] : 1.0;
+    for (int k = 0; k < 16; ++k) sv[k] = (s ? s[g0 + k] : 1.0) * (rexp ? pow2((int)rexp[g0 + k]) : 1.0);
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
         const int r = q * 32 + lane, col = cg * 128 + r;
@@ -290,6 +299,7 @@ struct Pipe {
 // A "schedule" names the output units of a CTA (column tiles of a row tile / exponent blocks of an output tile) and,
 // per unit, the k-chunk range and where its digit tiles are.
 struct RqSched {
+    static constexpr bool AMN = false;
     const signed char *A, *B;
     long a_plane, b_plane, tile;
     int nkc, nct, Nc, tri, P, p;  // this CTA takes the column tiles ct = p, p + P, ... of its row tile
@@ -304,14 +314,20 @@ struct RqSched {
     __device__ long aoff(int, int kc) const { return (tile * nkc + kc) * (long)ATILE; }
     __device__ long boff(int u, int kc) const { return ((long)ct_of(u) * nkc + kc) * (long)BTILE; }
 };
+// AROWS: the A operand is the ROW-scaled plane set of rowquad (tile [128 grid rows x 128 AO bytes] of row tile gc, k-chunk it),
+// read MN-major (M = AO index along the 128-byte rows, K = grid row); otherwise the column-scaled planes T, K-major.
+template <bool AROWS>
 struct WsSched {
+    static constexpr bool AMN = AROWS;
     const signed char *A, *B;
     long a_plane, b_plane;
-    int it, jt, njt, ngc, blk0, blk1;
+    int it, jt, njt, ngc, blk0, blk1, nkc;
     __device__ int nunits() const { return blk1 - blk0; }
     __device__ int kbeg(int u) const { return (blk0 + u) * KDC; }
     __device__ int kend(int u) const { return min(ngc, (blk0 + u + 1) * KDC); }
-    __device__ long aoff(int, int gc) const { return ((long)gc * njt + 2 * it) * (long)BTILE; }
+    __device__ long aoff(int, int gc) const {
+        return AROWS ? ((long)gc * nkc + it) * (long)ATILE : ((long)gc * njt + 2 * it) * (long)BTILE;
+    }
     __device__ long boff(int, int gc) const { return ((long)gc * njt + jt) * (long)BTILE; }
 };
 
@@ -393,11 +409,12 @@ __device__ __forceinline__ void i8_issue(const S& sc, const Pipe& p, uint32_t tm
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t acc = (s != 0 || k != 0) ? 1u : first;
-                        const uint32_t alo = alo0 + (uint32_t)s * (ATILE >> 4) + (uint32_t)k * 2u;
-                        mma_i8_lohi(tm + (uint32_t)s * IN, alo, blo + (uint32_t)k * 2u, DESC_HI, idesc_i8(IM, n0), acc);
+                        // K-major A: a k-step is 32 bytes along the 128-byte rows; MN-major A: 32 rows = four 1024-byte atoms
+                        const uint32_t alo = alo0 + (uint32_t)s * (ATILE >> 4) + (uint32_t)k * (S::AMN ? 256u : 2u);
+                        mma_i8_lohi(tm + (uint32_t)s * IN, alo, blo + (uint32_t)k * 2u, DESC_HI, idesc_i8(IM, n0, S::AMN ? 1 : 0), acc);
                         if (ntot > 256)
                             mma_i8_lohi(tm + (uint32_t)s * IN + 256, alo, blo + (4 * BTILE >> 4) + (uint32_t)k * 2u, DESC_HI,
-                                        idesc_i8(IM, ntot - 256), acc);
+                                        idesc_i8(IM, ntot - 256, S::AMN ? 1 : 0), acc);
                     }
                     mma_commit(p.emptyA + s);  // the slot is free once these MMAs have read it
                     if (s == ND - 1) mma_commit(p.emptyB + kb);
@@ -553,8 +570,9 @@ __global__ void __launch_bounds__(256) rowquad_i8_sum_kernel(const double* __res
 // ---- wsyrk ------------------------------------------------------------------------------------------------------------
 struct WsArgs {
     const signed char *A, *B;   // unweighted / weighted column-scaled planes
-    long plane_stride;
-    const int *eA, *eB;         // block exponents [nblk][NpadK]
+    long plane_stride, a_plane;
+    int nkc;
+    const int *eA, *eB;         // block exponents [nblk][NpadK]; eA == nullptr: the A digits are plain integers (row-scaled planes)
     double* part;               // [nsplit][ntile][128 x 64]
     int NpadK, njt, njtL, ngc, nblk, ntile, nsplit, sym;  // njt: column tiles that hold data (tile enumeration); njtL: pitch of the plane layout
 };
@@ -573,14 +591,15 @@ __device__ __forceinline__ void ws_tile(const WsArgs& a, int t, int& it, int& jt
     jt = 2 * it + t;
 }
 
+template <bool AROWS>
 __global__ void __launch_bounds__(I8_THREADS, 1) wsyrk_i8_kernel(const WsArgs a) {
     extern __shared__ unsigned char smem_raw[];
     uint32_t* tslot;
     const Pipe p = pipe_setup(smem_raw, &tslot);
     const int warp = warp_uniform_idx(), lane = threadIdx.x & 31;
     const int t = blockIdx.x % a.ntile, sp = blockIdx.x / a.ntile;
-    WsSched sc;
-    sc.A = a.A, sc.B = a.B, sc.a_plane = sc.b_plane = a.plane_stride;
+    WsSched<AROWS> sc;
+    sc.A = a.A, sc.B = a.B, sc.a_plane = a.a_plane, sc.b_plane = a.plane_stride, sc.nkc = a.nkc;
     ws_tile(a, t, sc.it, sc.jt);
     sc.njt = a.njtL, sc.ngc = a.ngc;
     sc.blk0 = (int)((long)a.nblk * sp / a.nsplit), sc.blk1 = (int)((long)a.nblk * (sp + 1) / a.nsplit);
@@ -604,7 +623,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) wsyrk_i8_kernel(const WsArgs a)
         for (int j = 0; j < CW; ++j) acc[j] = 0.0;
         for (int u = 0; u < sc.blk1 - sc.blk0; ++u) {
             const long eo = (long)(sc.blk0 + u) * a.NpadK;
-            const double si = pow2(a.eA[eo + i] - 26);
+            const double si = a.eA ? pow2(a.eA[eo + i] - 26) : 1.4901161193847656e-08;  // row-scaled integer A digits: 2^-26, the row's 2^ea is in B
             int eb[CW];  // fetched before the wait: the accumulators are held for as short a time as possible
             {
                 const int4* ebp = reinterpret_cast<const int4*>(a.eB + eo + j0);
@@ -692,7 +711,8 @@ int i8_alloc(qexxc_ctx* c) {
         c->bytes += bytes;
         return true;
     };
-    bool ok = A((void**)&w->A, planes) && A((void**)&w->T, planes) && A((void**)&w->W, planes) && A((void**)&w->Bs, sbytes) &&
+    const bool want_T = getenv("QEXXC_I8_T") && atoi(getenv("QEXXC_I8_T")) != 0;  // A/B runs of the column-scaled A planes
+    bool ok = A((void**)&w->A, planes) && (!want_T || A((void**)&w->T, planes)) && A((void**)&w->W, planes) && A((void**)&w->Bs, sbytes) &&
               A((void**)&w->sa, sizeof(float) * c->GpadMax) && A((void**)&w->qpart, sizeof(double) * 16 * (size_t)c->GpadMax) && A((void**)&w->sb, sizeof(double) * w->NpadK) &&
               A((void**)&w->cmax, sizeof(float) * (size_t)w->ngcMax * w->NpadK) &&
               A((void**)&w->eA, sizeof(int) * (size_t)w->nblkMax * w->NpadK) && A((void**)&w->eB, sizeof(int) * (size_t)w->nblkMax * w->NpadK);
@@ -701,11 +721,12 @@ int i8_alloc(qexxc_ctx* c) {
     if (!ok) {
         (void)cudaGetLastError();
         set_error("INT8 contraction workspace: cudaMalloc failed (%.1f GB of digit planes); set QEXXC_I8=0 for the FP64 path",
-                  3.0 * planes / 1e9);
+                  2.0 * planes / 1e9);
         return QEXXC_ERR_CUDA;
     }
     QX_CUDA(cudaFuncSetAttribute(rowquad_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem()));
-    QX_CUDA(cudaFuncSetAttribute(wsyrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem()));
+    QX_CUDA(cudaFuncSetAttribute(wsyrk_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem()));
+    QX_CUDA(cudaFuncSetAttribute(wsyrk_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem()));
     QX_CUDA(cudaFuncSetAttribute(slice_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ND * 16384));
     return QEXXC_OK;
 }
@@ -730,11 +751,14 @@ int i8_prepare(qexxc_ctx* c, cudaStream_t st) {
             return QEXXC_ERR_UNSUPPORTED;
     }
     QX_LAUNCH_CHECK(c);
-    const int ngc = c->Gpad / 128, nblk = (ngc + KDC - 1) / KDC;
-    blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmax, nullptr, ngc, w->NpadK, w->eA);
-    QX_LAUNCH_CHECK(c);
-    slice_cols_kernel<<<dim3(ngc, w->NpadK / 128), 256, ND * 16384, st>>>(c->ao, c->Npad, nullptr, w->eA, w->NpadK, w->njt, w->plane_stride, w->T);
-    QX_LAUNCH_CHECK(c);
+    if (w->T) {  // QEXXC_I8_T=1: separate column-scaled planes for the wsyrk A operand (A/B runs; the default reads A8 MN-major)
+        const int ngc = c->Gpad / 128, nblk = (ngc + KDC - 1) / KDC;
+        blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmax, nullptr, nullptr, ngc, w->NpadK, w->eA);
+        QX_LAUNCH_CHECK(c);
+        slice_cols_kernel<<<dim3(ngc, w->NpadK / 128), 256, ND * 16384, st>>>(c->ao, c->Npad, nullptr, nullptr, w->eA, w->NpadK, w->njt,
+                                                                             w->plane_stride, w->T);
+        QX_LAUNCH_CHECK(c);
+    }
     c->i8_valid = true;
     return QEXXC_OK;
 }
@@ -887,16 +911,19 @@ int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, doub
 static int i8_slice_weighted(qexxc_ctx* c, I8Ws* w, const double* s, const double* Bsrc, int ngc, int nblk, cudaStream_t st) {
     ProfScope prof(c, QEXXC_PROF_SLICE, st);
     const dim3 grid(ngc, w->NpadK / 128);
+    // default: the A operand is the row-scaled integer planes A8 (ao[g,i] = 2^(ea[g]-46) vA[g,i]), so the row's 2^ea[g] goes
+    // into the B operand here
+    const float* rexp = w->T ? nullptr : w->sa;
     if (Bsrc == nullptr) {
-        blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmax, s, ngc, w->NpadK, w->eB);
+        blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmax, s, rexp, ngc, w->NpadK, w->eB);
         QX_LAUNCH_CHECK(c);
-        slice_cols_kernel<<<grid, 256, ND * 16384, st>>>(c->ao, c->Npad, s, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
+        slice_cols_kernel<<<grid, 256, ND * 16384, st>>>(c->ao, c->Npad, s, rexp, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
     } else {
-        colmax_kernel<<<ngc, 256, 0, st>>>(Bsrc, c->Npad, w->NpadK, w->cmaxW);
+        colmax_kernel<<<ngc, 256, 0, st>>>(Bsrc, c->Npad, w->NpadK, rexp, w->cmaxW);
         QX_LAUNCH_CHECK(c);
-        blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmaxW, nullptr, ngc, w->NpadK, w->eB);
+        blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmaxW, nullptr, nullptr, ngc, w->NpadK, w->eB);
         QX_LAUNCH_CHECK(c);
-        slice_cols_kernel<<<grid, 256, ND * 16384, st>>>(Bsrc, c->Npad, nullptr, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
+        slice_cols_kernel<<<grid, 256, ND * 16384, st>>>(Bsrc, c->Npad, nullptr, rexp, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
     }
     QX_LAUNCH_CHECK(c);
     return QEXXC_OK;
@@ -926,10 +953,12 @@ int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double sc
         return QEXXC_ERR_STATE;
     }
     WsArgs a{};
-    a.A = w->T;
+    a.A = w->T ? w->T : w->A;
     a.B = w->W;
     a.plane_stride = w->plane_stride;
-    a.eA = w->eA;
+    a.a_plane = w->T ? w->plane_stride : (long)(c->Gpad / IM) * w->nkc * (long)ATILE;
+    a.nkc = w->nkc;
+    a.eA = w->T ? w->eA : nullptr;
     a.eB = w->eB;
     a.part = c->part;
     a.NpadK = w->NpadK;
@@ -940,7 +969,8 @@ int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double sc
     a.ntile = ntile;
     a.nsplit = nsplit;
     a.sym = sym ? 1 : 0;
-    wsyrk_i8_kernel<<<(unsigned)(ntile * nsplit), I8_THREADS, i8_smem(), st>>>(a);
+    if (w->T) wsyrk_i8_kernel<false><<<(unsigned)(ntile * nsplit), I8_THREADS, i8_smem(), st>>>(a);
+    else wsyrk_i8_kernel<true><<<(unsigned)(ntile * nsplit), I8_THREADS, i8_smem(), st>>>(a);
     QX_LAUNCH_CHECK(c);
     wsyrk_i8_reduce_kernel<<<dim3((c->N + 31) / 32, (c->N + 7) / 8), 256, 0, st>>>(c->part, out, c->N, njt, ntile, nsplit, sym ? 1 : 0, scale, tadd);
     QX_LAUNCH_CHECK(c);

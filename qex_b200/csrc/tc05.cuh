@@ -217,8 +217,8 @@ __device__ __forceinline__ uint32_t pack_hi16(uint32_t a, uint32_t b) { return _
 // ---- 8-bit integer operands (kind::i8, INT32 accumulation): the exact Ozaki-split contractions (contract_i8.cu) --------------------
 namespace qexxc {
 namespace tc05 {
-__device__ __host__ constexpr uint32_t idesc_i8(int M, int N) {  // signed 8-bit A and B, K-major, S32 accumulators
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __host__ constexpr uint32_t idesc_i8(int M, int N, int a_mn_major = 0) {  // signed 8-bit A and B, B K-major, S32 accumulators
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
