@@ -336,6 +336,9 @@ int qexxc_create_ex(qexxc_ctx** out, int device, int nbatch, int ncomp, int ngri
     c->red_doubles = red;
     QX_A(c->red, red);
 #undef QX_A
+    // INT8 contraction workspace (digit planes): reserved here when the policy selects that path for this shape, so that no
+    // call on the hot path allocates (CUDA-graph capture); a later QEXXC_I8=1 still allocates on first use
+    if (rc == QEXXC_OK && i8_enabled(c)) rc = i8_reserve(c);
     if (rc != QEXXC_OK) {
         qexxc_destroy(c);
         return rc;

@@ -188,6 +188,7 @@ int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, doub
 int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st);
 double i8_executed_ops(const qexxc_ctx* c, int which, bool sym);
 int i8_prepare_geometry(qexxc_ctx* c, cudaStream_t st);
+int i8_reserve(qexxc_ctx* c);  // allocate the digit-plane workspace now (qexxc_create), not on first use
 int i8_peak_probe(int device, double* ops_per_second);
 // ao.cu
 int launch_eval_ao(qexxc_ctx* c, int deriv, cudaStream_t st);

@@ -766,6 +766,7 @@ int i8_prepare(qexxc_ctx* c, cudaStream_t st) {
 }  // namespace
 
 int i8_prepare_geometry(qexxc_ctx* c, cudaStream_t st) { return i8_prepare(c, st); }
+int i8_reserve(qexxc_ctx* c) { return i8_alloc(c); }
 
 void i8_release(qexxc_ctx* c) {
     delete (I8Ws*)c->i8ws;
