@@ -311,6 +311,9 @@ struct RqSched {
         const int last = min(Nc, (ct_of(u) + 1) * IN);  // S is upper triangular: rows i <= last column only
         return (last + KC - 1) / KC;
     }
+    // 32-byte k-steps of chunk kc that can hold non-zero products: an even column tile ct = 2m ends at column 128m + 63,
+    // so with the upper-triangular S only rows i < 128m + 64 of its last k-chunk (kc = m) contribute
+    __device__ int ksteps(int u, int kc) const { return (tri && !(ct_of(u) & 1) && kc == (ct_of(u) >> 1)) ? 2 : 4; }
     __device__ long aoff(int, int kc) const { return (tile * nkc + kc) * (long)ATILE; }
     __device__ long boff(int u, int kc) const { return ((long)ct_of(u) * nkc + kc) * (long)BTILE; }
 };
@@ -325,6 +328,7 @@ struct WsSched {
     __device__ int nunits() const { return blk1 - blk0; }
     __device__ int kbeg(int u) const { return (blk0 + u) * KDC; }
     __device__ int kend(int u) const { return min(ngc, (blk0 + u + 1) * KDC); }
+    __device__ int ksteps(int, int) const { return 4; }
     __device__ long aoff(int, int gc) const {
         return AROWS ? ((long)gc * nkc + it) * (long)ATILE : ((long)gc * njt + 2 * it) * (long)BTILE;
     }
@@ -396,6 +400,7 @@ __device__ __forceinline__ void i8_issue(const S& sc, const Pipe& p, uint32_t tm
             mbar_wait(p.fullB + kb, (itB >> 1) & 1);
             const uint32_t blo = blo0 + (uint32_t)kb * (ND * BTILE >> 4);
             const uint32_t first = (uint32_t)(kc != k0);
+            const int nks = sc.ksteps(u, kc);
 #pragma unroll
             for (int s = 0; s < ND; ++s) {  // A ring slot == plane (NA == ND)
                 mbar_wait(p.fullA + s, itB & 1);
@@ -408,6 +413,7 @@ __device__ __forceinline__ void i8_issue(const S& sc, const Pipe& p, uint32_t tm
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
+                        if (k >= nks) break;
                         const uint32_t acc = (s != 0 || k != 0) ? 1u : first;
                         // K-major A: a k-step is 32 bytes along the 128-byte rows; MN-major A: 32 rows = four 1024-byte atoms
                         const uint32_t alo = alo0 + (uint32_t)s * (ATILE >> 4) + (uint32_t)k * (S::AMN ? 256u : 2u);
@@ -780,7 +786,10 @@ double i8_executed_ops(const qexxc_ctx* c, int which, bool sym) {
     const int njt = (c->Nc + IN - 1) / IN, nit = (c->Nc + IM - 1) / IM;
     if (which == 0) {
         double pairs = 0.0;
-        for (int ct = 0; ct < njt; ++ct) pairs += sym ? (std::min(c->Nc, (ct + 1) * IN) + KC - 1) / KC : (c->Nc + KC - 1) / KC;
+        for (int ct = 0; ct < njt; ++ct) {
+            pairs += sym ? (std::min(c->Nc, (ct + 1) * IN) + KC - 1) / KC : (c->Nc + KC - 1) / KC;
+            if (sym && !(ct & 1) && (ct >> 1) < (std::min(c->Nc, (ct + 1) * IN) + KC - 1) / KC) pairs -= 0.5;  // half k-chunk on the diagonal
+        }
         return per_pair * pairs * (c->Gpad / IM);
     }
     int ntile = 0;
