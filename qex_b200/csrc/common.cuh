@@ -186,6 +186,7 @@ bool i8_enabled(const qexxc_ctx* c);
 void i8_release(qexxc_ctx* c);
 int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_cstride, cudaStream_t st);
 int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st);
+int launch_rowquad_mo_i8(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, cudaStream_t st);
 double i8_executed_ops(const qexxc_ctx* c, int which, bool sym);
 int i8_prepare_geometry(qexxc_ctx* c, cudaStream_t st);
 int i8_reserve(qexxc_ctx* c);  // allocate the digit-plane workspace now (qexxc_create), not on first use

@@ -944,6 +944,7 @@ int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, int tri, cudaStrea
 // the occupation (0 for padding); q[b][g] = sum_k sgn_k ((ao L)[g,k])^2 with nk compute columns.
 int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, long q_bstride,
                       cudaStream_t st) {
+    if (i8_enabled(c)) return launch_rowquad_mo_i8(c, L, ldL, nk, sgn, q, st);
     const int Sc = round_up(nk > 0 ? nk : 1, kNBlock);
     const int BN = pick_bn(Sc);
     dim3 grid(c->Gpad / BM, c->B);

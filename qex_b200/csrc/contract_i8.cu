@@ -148,14 +148,14 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
 }
 
 // Column-scaled planes of S (rowquad B operand): B8[t][column tile (64)][k-chunk][8 KB tile], B[n = j][k = i] = S[i][j];
-// sb[j] = 2^(eb[j]-52).  One block per column j.
-__global__ void __launch_bounds__(256) slice_s_kernel(const double* __restrict__ S, int ldS, int Nc, int nkc, int nct,
+// sb[j] = 2^(eb[j]-52).  One block per column j; S is [nrow x ncol] (square for rowquad, [nao x n_occ] for the MO form).
+__global__ void __launch_bounds__(256) slice_s_kernel(const double* __restrict__ S, int ldS, int nrow, int ncol, int nkc, int nct,
                                                       signed char* __restrict__ B8, double* __restrict__ sb) {
     const int j = blockIdx.x;
     __shared__ double red[256];
     double mx = 0.0;
-    if (j < Nc)
-        for (int i = threadIdx.x; i < Nc; i += blockDim.x) mx = fmax(mx, fabs(S[(long)i * ldS + j]));
+    if (j < ncol)
+        for (int i = threadIdx.x; i < nrow; i += blockDim.x) mx = fmax(mx, fabs(S[(long)i * ldS + j]));
     red[threadIdx.x] = mx;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) slice_s_kernel(const double* __restrict__
     const double scale = pow2(46 - e);
     const int ct = j / IN, r = j % IN;
     for (int i = threadIdx.x; i < nkc * KC; i += blockDim.x) {
-        const double x = (j < Nc && i < Nc) ? S[(long)i * ldS + j] : 0.0;
+        const double x = (j < ncol && i < nrow) ? S[(long)i * ldS + j] : 0.0;
         uint32_t lo, hi;
         to_w48(x, scale, lo, hi);
         const unsigned long long w = (((unsigned long long)hi << 32) | lo) ^ 0x0000808080808080ull;
@@ -454,6 +454,7 @@ struct RqArgs {
     const float* sa;   // row exponents
     const double* sb;  // column scales 2^(eb-52)
     const double* ao;  // FP64 ao rows for the row-dot epilogue
+    const double* sgn; // MO form (non-null): q[g] = sum_k sgn[k] ((ao_0 L)[g,k])^2, no row-dot
     double* q;
     long ao_cstride, q_cstride;
     int Npad, ncomp;
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
             // the FP64 ao_0 values of this thread's row are fetched before the wait, so that after the drain the row-dot is
             // arithmetic only and the warp is back in time for the next (possibly short) column tile
             double2 a0[CW / 2];
-            if (live) {
+            if (live && !a.sgn) {
                 const double2* ap = reinterpret_cast<const double2*>(a.ao + g * a.Npad + col);
 #pragma unroll
                 for (int j = 0; j < CW / 2; ++j) a0[j] = ap[j];
@@ -511,7 +512,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p.tempty);  // the accumulators are free: the next column tile's MMAs overlap the row-dot
-            if (live) {
+            if (live && a.sgn) {  // MO form: signed sum of squares of the (ao_0 L) row
+                double s0 = 0.0;
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    const double t = T[j] * a.sb[col + j];
+                    s0 = fma(a.sgn[col + j] * t, t, s0);
+                }
+                acc[0] += s0;
+            } else if (live) {
 #pragma unroll
                 for (int j = 0; j < CW; ++j) T[j] *= a.sb[col + j];
                 double s0 = 0.0, s1 = 0.0;
@@ -544,7 +553,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
         }
         asm volatile("bar.sync 1, %0;" ::"r"(32 * NEW) : "memory");
         if (cq == 0) {
-            const double rs = pow2((int)a.sa[g]);
+            const double r1 = pow2((int)a.sa[g]), rs = a.sgn ? r1 * r1 : r1;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 if (c < a.ncomp) {
@@ -871,12 +880,15 @@ bool i8_enabled(const qexxc_ctx* c) {
     return c->N >= 256;
 }
 
-int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_cstride, cudaStream_t st) {
+// B operand = the [nrow x ncol] matrix Smat (ld ldS): the padded S of rowquad, or L = C sqrt|occ| of the MO form (sgn != nullptr)
+static int rowquad_i8_common(qexxc_ctx* c, const double* Smat, int ldS, int nrow, int ncol, int ncomp, int tri, const double* fac4,
+                             const double* sgn, int ldsgn, double* q, long q_cstride, cudaStream_t st) {
     QX_TRY(i8_prepare(c, st));
     I8Ws* w = (I8Ws*)c->i8ws;
+    const int nct = (ncol + IN - 1) / IN;  // column tiles that hold data
     {
         ProfScope prof(c, QEXXC_PROF_SLICE, st);
-        slice_s_kernel<<<w->NpadK, 256, 0, st>>>(c->S, c->Npad, c->Nc, w->nkc, w->njt, w->Bs, w->sb);
+        slice_s_kernel<<<nct * IN, 256, 0, st>>>(Smat, ldS, nrow, ncol, w->nkc, w->njt, w->Bs, w->sb);
         QX_LAUNCH_CHECK(c);
     }
     ProfScope prof(c, QEXXC_PROF_ROWQUAD, st);
@@ -887,12 +899,13 @@ int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, doub
     a.sc.a_plane = ntiles * w->nkc * (long)ATILE;
     a.sc.b_plane = (long)w->njt * w->nkc * BTILE;
     a.sc.nkc = w->nkc;
-    a.sc.nct = (c->Nc + IN - 1) / IN;  // column tiles that hold data
-    a.sc.Nc = c->Nc;
+    a.sc.nct = nct;
+    a.sc.Nc = nrow;
     a.sc.tri = tri;
     a.sa = w->sa;
     a.sb = w->sb;
     a.ao = c->ao;
+    a.sgn = sgn;
     // column groups per row tile: the A planes of a row tile (6 nkc x 16 KB) are re-read by every column tile; with one CTA
     // per row tile the planes of all resident CTAs (148 x 768 KB at nao = 1000) do not stay in L2
     int P = 1;
@@ -902,7 +915,7 @@ int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, doub
     a.q = P > 1 ? w->qpart : q;
     a.ao_cstride = (long)c->GpadMax * c->Npad;
     a.q_cstride = P > 1 ? (long)c->GpadMax : q_cstride;
-    a.Npad = c->Npad;
+    a.Npad = sgn ? ldsgn : c->Npad;  // columns beyond this hold zero digits (and lie outside sgn / the ao rows)
     a.ncomp = ncomp;
     a.f[0] = (tri ? 2.0 : 1.0) * fac4[0];
     a.f[1] = fac4[1];
@@ -915,6 +928,16 @@ int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, doub
         QX_LAUNCH_CHECK(c);
     }
     return QEXXC_OK;
+}
+
+int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_cstride, cudaStream_t st) {
+    return rowquad_i8_common(c, c->S, c->Npad, c->Nc, c->Nc, ncomp, tri, fac4, nullptr, 0, q, q_cstride, st);
+}
+
+// MO form of rho (pyscf eval_rho2, numint_legacy.py:527-545): q[g] = sum_k sgn[k] ((ao_0 L)[g,k])^2, L [Npad][ldL], nk columns
+int launch_rowquad_mo_i8(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, cudaStream_t st) {
+    static const double one4[4] = {1.0, 0.0, 0.0, 0.0};
+    return rowquad_i8_common(c, L, ldL, c->Nc, nk > 0 ? nk : 1, 1, 0, one4, sgn, ldL, q, 0, st);
 }
 
 // the per-call operand of wsyrk (s .* ao_0, or a general B): block exponents, then digit planes

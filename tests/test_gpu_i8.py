@@ -139,3 +139,22 @@ def test_i8_regrid_reuses_context(i8):
         ref = numint_ref.eval_rho(ao[0, 0], dm[0], "LDA", hermi=0).reshape(1, G)
         got = _to_np(ctx.eval_rho(dm, ncomp=1, hermi=0))[0][:, :G]
         assert rel_err(got, ref) <= TOL64
+
+
+@pytest.mark.parametrize("N,G,nmo", [(40, 1500, 7), (300, 3000, 150), (130, 2100, 65)])
+def test_i8_mo_form_of_rho(i8, N, G, nmo):
+    """rho from occupied orbitals (pyscf eval_rho2, the dms.mo_coeff branch at numint_legacy.py:527-545) on the INT8 pipe:
+    rho = sum_k occ_k (ao C_k)^2 against the dm form of the oracle, including negative and zero occupations."""
+    ao, _, w = synth_problem(N, G, 1, seed=N + nmo)
+    rng = np.random.default_rng(nmo)
+    Cm = rng.standard_normal((N, nmo)) / np.sqrt(N)
+    occ = rng.uniform(0.2, 2.0, nmo)
+    occ[::5] *= -1.0
+    occ[3] = 0.0
+    dm = (Cm * occ) @ Cm.T
+    ctx = _ctx(nao=N, ngrids_max=G, ncomp=1)
+    assert ctx.contraction_mode == "int8"
+    ctx.set_grid(None, w).set_ao(ao, 1)
+    ref = numint_ref.eval_rho(ao[0, 0], dm, "LDA", hermi=1).reshape(G)
+    got = _to_np(ctx.eval_rho_mo(Cm, occ))[0, 0]
+    assert rel_err(got, ref) <= TOL64
