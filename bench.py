@@ -722,7 +722,9 @@ def run_ours(args):
             "contraction_pipe": res["mode"],
             "traffic_note": "dram read+write bytes per launch of THIS kernel at this shape, from the committed ncu capture "
                             "(profiles/ncu_traffic.json; not measurable inside a timed run); algorithmic bytes = "
-                            + ("the digit planes of both operands read once = %.2f GB" % (12.0 * res["npad"] * res["Gl"] / 1e9) if int8
+                            + (("the A digit planes (6 B per AO value) + the FP64 ao rows of the row-dot epilogue = %.2f GB" % (14.0 * res["npad"] * res["Gl"] / 1e9)
+                                if dom == "rowquad" else
+                                "the digit planes of both operands read once = %.2f GB" % (12.0 * res["npad"] * res["Gl"] / 1e9)) if int8
                                else "the AO tensor read once = %.2f GB" % (8.0 * res["npad"] * res["Gl"] / 1e9)),
             "peak_source": ("qexxc_i8_peak measured in this run (best of 3)" if int8 else
                             "cuBLAS DGEMM 8192^3 measured in this run, sustained (MEASURED_PEAKS.json has no FP64 figure); "

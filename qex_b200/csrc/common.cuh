@@ -181,12 +181,13 @@ int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const doub
 // aow[b][g][n] = sum_c f[c] wv[b][c][g] ao[b][c][g][n]
 int launch_build_aow(qexxc_ctx* c, const double* wv, long wv_bstride, long wv_cstride, const double* fac4,
                      cudaStream_t st);
-// contract_i8.cu: exact INT8 (Ozaki) form of rowquad / wsyrk on tcgen05 (QEXXC_I8=0/1; default: nao >= 256, single molecule)
+// contract_i8.cu: exact INT8 (Ozaki) form of rowquad / wsyrk on tcgen05 (QEXXC_I8=0/1; default: nao >= 256, one AO tensor per context)
 bool i8_enabled(const qexxc_ctx* c);
 void i8_release(qexxc_ctx* c);
-int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_cstride, cudaStream_t st);
-int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st);
-int launch_rowquad_mo_i8(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, cudaStream_t st);
+int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride, long q_cstride, cudaStream_t st);
+int launch_wsyrk_i8(qexxc_ctx* c, const double* s, long s_bstride, const double* Bsrc, double scale, int tadd, double* out,
+                    long out_bstride, cudaStream_t st);
+int launch_rowquad_mo_i8(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, long q_bstride, cudaStream_t st);
 double i8_executed_ops(const qexxc_ctx* c, int which, bool sym);
 int i8_prepare_geometry(qexxc_ctx* c, cudaStream_t st);
 int i8_reserve(qexxc_ctx* c);  // allocate the digit-plane workspace now (qexxc_create), not on first use

@@ -944,7 +944,7 @@ int launch_pad_sym(qexxc_ctx* c, const double* src, int mode, int tri, cudaStrea
 // the occupation (0 for padding); q[b][g] = sum_k sgn_k ((ao L)[g,k])^2 with nk compute columns.
 int launch_rowquad_mo(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, long q_bstride,
                       cudaStream_t st) {
-    if (i8_enabled(c)) return launch_rowquad_mo_i8(c, L, ldL, nk, sgn, q, st);
+    if (i8_enabled(c)) return launch_rowquad_mo_i8(c, L, ldL, nk, sgn, q, q_bstride, st);
     const int Sc = round_up(nk > 0 ? nk : 1, kNBlock);
     const int BN = pick_bn(Sc);
     dim3 grid(c->Gpad / BM, c->B);
@@ -999,7 +999,7 @@ static bool rowquad_pair_masks(const qexxc_ctx* c, int tri, int nbulk, unsigned*
 
 int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride,
                    long q_cstride, cudaStream_t st) {
-    if (i8_enabled(c)) return launch_rowquad_i8(c, ncomp, tri, fac4, q, q_cstride, st);
+    if (i8_enabled(c)) return launch_rowquad_i8(c, ncomp, tri, fac4, q, q_bstride, q_cstride, st);
     const int BN = pick_bn(c->Nc), NT = (c->Nc + BN - 1) / BN, T = c->Gpad / BM;
     const int ntail = rowquad_tail_tiles(c, tri), nbulk = T - ntail;
     unsigned m0 = 0, m1 = 0;
@@ -1033,7 +1033,7 @@ int launch_rowquad(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double*
 
 int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bsrc, double scale, int tadd,
                  double* out, long out_bstride, cudaStream_t st) {
-    if (i8_enabled(c)) return launch_wsyrk_i8(c, s, Bsrc, scale, tadd, out, st);
+    if (i8_enabled(c)) return launch_wsyrk_i8(c, s, s_bstride, Bsrc, scale, tadd, out, out_bstride, st);
     const bool sym = (Bsrc == nullptr);
     WsPlan plan;
     QX_TRY(ws_schedule(c, sym, plan, st));

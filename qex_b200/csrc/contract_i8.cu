@@ -874,7 +874,8 @@ int i8_peak_probe(int device, double* ops_per_second) {
 }
 
 bool i8_enabled(const qexxc_ctx* c) {
-    if (c->B != 1 || c->ao_shared || c->Npad > 2048) return false;
+    // one AO tensor per context: a single molecule, or nset density matrices over a SHARED AO tensor (looped over the sets)
+    if ((c->B != 1 && !c->ao_shared) || c->Npad > 2048) return false;
     const char* e = getenv("QEXXC_I8");
     if (e) return atoi(e) != 0;
     return c->N >= 256;
@@ -930,14 +931,20 @@ static int rowquad_i8_common(qexxc_ctx* c, const double* Smat, int ldS, int nrow
     return QEXXC_OK;
 }
 
-int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_cstride, cudaStream_t st) {
-    return rowquad_i8_common(c, c->S, c->Npad, c->Nc, c->Nc, ncomp, tri, fac4, nullptr, 0, q, q_cstride, st);
+int launch_rowquad_i8(qexxc_ctx* c, int ncomp, int tri, const double* fac4, double* q, long q_bstride, long q_cstride, cudaStream_t st) {
+    for (int b = 0; b < c->B; ++b)
+        QX_TRY(rowquad_i8_common(c, c->S + (long)b * c->Npad * c->Npad, c->Npad, c->Nc, c->Nc, ncomp, tri, fac4, nullptr, 0,
+                                 q + (long)b * q_bstride, q_cstride, st));
+    return QEXXC_OK;
 }
 
 // MO form of rho (pyscf eval_rho2, numint_legacy.py:527-545): q[g] = sum_k sgn[k] ((ao_0 L)[g,k])^2, L [Npad][ldL], nk columns
-int launch_rowquad_mo_i8(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, cudaStream_t st) {
+int launch_rowquad_mo_i8(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, long q_bstride, cudaStream_t st) {
     static const double one4[4] = {1.0, 0.0, 0.0, 0.0};
-    return rowquad_i8_common(c, L, ldL, c->Nc, nk > 0 ? nk : 1, 1, 0, one4, sgn, ldL, q, 0, st);
+    for (int b = 0; b < c->B; ++b)
+        QX_TRY(rowquad_i8_common(c, L + (long)b * c->Npad * ldL, ldL, c->Nc, nk > 0 ? nk : 1, 1, 0, one4, sgn + (long)b * ldL, ldL,
+                                 q + (long)b * q_bstride, 0, st));
+    return QEXXC_OK;
 }
 
 // the per-call operand of wsyrk (s .* ao_0, or a general B): block exponents, then digit planes
@@ -962,7 +969,17 @@ static int i8_slice_weighted(qexxc_ctx* c, I8Ws* w, const double* s, const doubl
     return QEXXC_OK;
 }
 
-int launch_wsyrk_i8(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st) {
+static int wsyrk_i8_one(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st);
+
+int launch_wsyrk_i8(qexxc_ctx* c, const double* s, long s_bstride, const double* Bsrc, double scale, int tadd, double* out,
+                    long out_bstride, cudaStream_t st) {
+    for (int b = 0; b < c->B; ++b)
+        QX_TRY(wsyrk_i8_one(c, s ? s + (long)b * s_bstride : nullptr, Bsrc ? Bsrc + (long)b * c->GpadMax * c->Npad : nullptr, scale, tadd,
+                            out + (long)b * out_bstride, st));
+    return QEXXC_OK;
+}
+
+static int wsyrk_i8_one(qexxc_ctx* c, const double* s, const double* Bsrc, double scale, int tadd, double* out, cudaStream_t st) {
     QX_TRY(i8_prepare(c, st));
     I8Ws* w = (I8Ws*)c->i8ws;
     const bool sym = (Bsrc == nullptr);

@@ -158,3 +158,26 @@ def test_i8_mo_form_of_rho(i8, N, G, nmo):
     ref = numint_ref.eval_rho(ao[0, 0], dm, "LDA", hermi=1).reshape(G)
     got = _to_np(ctx.eval_rho_mo(Cm, occ))[0, 0]
     assert rel_err(got, ref) <= TOL64
+
+
+@pytest.mark.parametrize("C", [1, 4])
+def test_i8_nset_density_matrices_over_a_shared_ao_tensor(i8, C):
+    """nset density matrices of one molecule (numint_legacy.py:141-156) on the INT8 pipe: one set of digit planes of the
+    shared AO tensor, the contractions looped over the sets; every set equals its single-dm oracle result."""
+    N, G, B = 140, 2300, 3
+    ao, dm, w = synth_problem(N, G, C, seed=21)
+    rng = np.random.default_rng(22)
+    dms = np.stack([dm[0], 0.5 * dm[0] + 0.01 * rng.standard_normal((N, N)), -1.5 * dm[0].T])
+    ctx = _ctx(nao=N, ngrids_max=G, ncomp=C, nbatch=B, shared_ao=True)
+    assert ctx.contraction_mode == "int8"
+    ctx.set_grid(None, w).set_ao(ao, C)
+    xct = "GGA" if C == 4 else "LDA"
+    a = ao[0] if C == 4 else ao[0, 0]
+    got = _to_np(ctx.eval_rho(dms, ncomp=C, hermi=0))
+    rb = rng.standard_normal((B, C, G))
+    got_d = _to_np(ctx.eval_rho_vjp(rb, ncomp=C, hermi=0))
+    for b in range(B):
+        ref = numint_ref.eval_rho(a, dms[b], xct, hermi=0).reshape(C, G)
+        assert rel_err(got[b], ref) <= TOL64
+        ref_d = numint_ref.eval_rho_vjp(a, rb[b] if C == 4 else rb[b, 0], xct, hermi=0)
+        assert rel_err(got_d[b], ref_d) <= TOL64
