@@ -76,6 +76,9 @@ class _BatchProblem:
         if len(self.nelectron) != 1:
             raise NotImplementedError("one batch holds molecules with the same electron count")
         self.nelectron = self.nelectron.pop()
+        for m in mols[1:]:  # one basis table serves the whole batch (set_basis below): only the geometry (env) may differ
+            if not (np.array_equal(m._atm, mols[0]._atm) and np.array_equal(m._bas, mols[0]._bas)):
+                raise NotImplementedError("one batch holds molecules with identical _atm / _bas tables (same atoms, same basis)")
         grids = []
         for e in entries:
             g = gen_grid.Grids(e[2])
@@ -184,8 +187,20 @@ class TDKSDFTTrainer:
         return _native_apply(self.network).qex_spec
 
     def _problem(self, batch_data) -> _BatchProblem:
-        key = tuple(id(e[2]) for e in batch_data)
-        if key not in self._problems:
+        # keyed on CONTENT (geometry / basis tables and the targets), not on object identity: the same Mole objects reused
+        # with other targets, or ids recycled after garbage collection, must not hit a stale entry; bounded (LRU)
+        import hashlib
+
+        h = hashlib.sha1()
+        for e in batch_data:
+            for part in (e[0], e[1], e[2]._atm, e[2]._bas, e[2]._env):
+                h.update(np.ascontiguousarray(np.asarray(part, dtype=np.float64)).tobytes())
+        key = h.hexdigest()
+        if key in self._problems:
+            self._problems[key] = self._problems.pop(key)  # most recently used last
+        else:
+            while len(self._problems) >= 32:
+                self._problems.pop(next(iter(self._problems)))
             self._problems[key] = _BatchProblem(batch_data, self._spec(), self.device, int(self.config.get("grid_density", 0)))
         return self._problems[key]
 
