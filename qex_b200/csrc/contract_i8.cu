@@ -68,6 +68,12 @@ __device__ __forceinline__ uint32_t plane_word(const uint32_t (&lo)[4], const ui
     const uint32_t w = b < 4 ? pack_byte(lo[0], lo[1], lo[2], lo[3], b) : pack_byte(hi[0], hi[1], hi[2], hi[3], b - 4);
     return w ^ 0x80808080u;
 }
+// four consecutive doubles with one 256-bit load that does not allocate in L1: a thread of the rowquad epilogue reads 128
+// contiguous bytes of its own AO row, so narrower loads fetch every 32-byte sector twice and thrash the small L1 left
+// beside 193 KB of shared memory
+__device__ __forceinline__ void ldg256(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
 __device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
 
 __device__ __forceinline__ uint32_t tile_off(int r, int c) {  // byte offset of (row r, k c) inside a swizzled tile
@@ -492,11 +498,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
             const bool live = col < a.Npad;  // Npad is a multiple of 32 and col of 16; digits of columns >= Nc are zero
             // the FP64 ao_0 values of this thread's row are fetched before the wait, so that after the drain the row-dot is
             // arithmetic only and the warp is back in time for the next (possibly short) column tile
-            double2 a0[CW / 2];
+            double a0[CW / 4][4];
             if (live && !a.sgn) {
-                const double2* ap = reinterpret_cast<const double2*>(a.ao + g * a.Npad + col);
+                const double* ap = a.ao + g * a.Npad + col;
 #pragma unroll
-                for (int j = 0; j < CW / 2; ++j) a0[j] = ap[j];
+                for (int j = 0; j < CW / 4; ++j) ldg256(ap + 4 * j, a0[j]);
             }
             mbar_wait(p.tfull, u & 1);
             __syncwarp();
@@ -525,21 +531,27 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
                 for (int j = 0; j < CW; ++j) T[j] *= a.sb[col + j];
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                for (int j = 0; j < CW / 2; ++j) {
-                    s0 = fma(T[2 * j], a0[j].x, s0);
-                    s1 = fma(T[2 * j + 1], a0[j].y, s1);
+                for (int j = 0; j < CW / 4; ++j) {
+                    s0 = fma(T[4 * j], a0[j][0], s0);
+                    s1 = fma(T[4 * j + 1], a0[j][1], s1);
+                    s0 = fma(T[4 * j + 2], a0[j][2], s0);
+                    s1 = fma(T[4 * j + 3], a0[j][3], s1);
                 }
                 acc[0] += s0 + s1;
 #pragma unroll
                 for (int c = 1; c < 4; ++c)
                     if (c < a.ncomp) {
-                        const double2* ap = reinterpret_cast<const double2*>(a.ao + (long)c * a.ao_cstride + g * a.Npad + col);
+                        const double* ap = a.ao + (long)c * a.ao_cstride + g * a.Npad + col;
+                        double v[CW / 4][4];
+#pragma unroll
+                        for (int j = 0; j < CW / 4; ++j) ldg256(ap + 4 * j, v[j]);
                         s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                        for (int j = 0; j < CW / 2; ++j) {
-                            const double2 v = ap[j];
-                            s0 = fma(T[2 * j], v.x, s0);
-                            s1 = fma(T[2 * j + 1], v.y, s1);
+                        for (int j = 0; j < CW / 4; ++j) {
+                            s0 = fma(T[4 * j], v[j][0], s0);
+                            s1 = fma(T[4 * j + 1], v[j][1], s1);
+                            s0 = fma(T[4 * j + 2], v[j][2], s0);
+                            s1 = fma(T[4 * j + 3], v[j][3], s1);
                         }
                         acc[c] += s0 + s1;
                     }
