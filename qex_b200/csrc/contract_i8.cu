@@ -71,8 +71,13 @@ __device__ __forceinline__ uint32_t plane_word(const uint32_t (&lo)[4], const ui
 // four consecutive doubles with one 256-bit load that does not allocate in L1: a thread of the rowquad epilogue reads 128
 // contiguous bytes of its own AO row, so narrower loads fetch every 32-byte sector twice and thrash the small L1 left
 // beside 193 KB of shared memory
-__device__ __forceinline__ void ldg256(const double* p, double (&v)[4]) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+__device__ __forceinline__ void ldg256(const double* p, double (&v)[4], int wide = 1) {
+    if (wide) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    } else {
+        const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+        v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+    }
 }
 __device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
 
@@ -463,7 +468,7 @@ struct RqArgs {
     const double* sgn; // MO form (non-null): q[g] = sum_k sgn[k] ((ao_0 L)[g,k])^2, no row-dot
     double* q;
     long ao_cstride, q_cstride;
-    int Npad, ncomp;
+    int Npad, ncomp, wide;
     double f[4];
 };
 
@@ -502,7 +507,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
             if (live && !a.sgn) {
                 const double* ap = a.ao + g * a.Npad + col;
 #pragma unroll
-                for (int j = 0; j < CW / 4; ++j) ldg256(ap + 4 * j, a0[j]);
+                for (int j = 0; j < CW / 4; ++j) ldg256(ap + 4 * j, a0[j], a.wide);
             }
             mbar_wait(p.tfull, u & 1);
             __syncwarp();
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) rowquad_i8_kernel(const RqArgs 
                         const double* ap = a.ao + (long)c * a.ao_cstride + g * a.Npad + col;
                         double v[CW / 4][4];
 #pragma unroll
-                        for (int j = 0; j < CW / 4; ++j) ldg256(ap + 4 * j, v[j]);
+                        for (int j = 0; j < CW / 4; ++j) ldg256(ap + 4 * j, v[j], a.wide);
                         s0 = 0.0, s1 = 0.0;
 #pragma unroll
                         for (int j = 0; j < CW / 4; ++j) {
@@ -930,6 +935,7 @@ static int rowquad_i8_common(qexxc_ctx* c, const double* Smat, int ldS, int nrow
     a.q_cstride = P > 1 ? (long)c->GpadMax : q_cstride;
     a.Npad = sgn ? ldsgn : c->Npad;  // columns beyond this hold zero digits (and lie outside sgn / the ao rows)
     a.ncomp = ncomp;
+    a.wide = getenv("QEXXC_I8_LD128") ? 0 : 1;
     a.f[0] = (tri ? 2.0 : 1.0) * fac4[0];
     a.f[1] = fac4[1];
     a.f[2] = fac4[2];
