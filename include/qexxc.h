@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QEXXC_VERSION 200
+#define QEXXC_VERSION 210
 
 #define QEXXC_OK 0
 #define QEXXC_ERR_CUDA (-1)        /* a CUDA runtime call or kernel launch failed */

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [n for n in _declared() if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(_lib.EXPORTS) == _declared()
-    assert lib.qexxc_version() == 200
+    assert lib.qexxc_version() == 210
 
 
 def test_n_params(lib):
