@@ -114,8 +114,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
         for (int kc = 0; kc < NKC; ++kc) {
             const int c = kc * KC + lane * 4;
             if (c < Npad) {  // Npad is a multiple of 32: the four columns are inside or outside together
-                const double2 u = *reinterpret_cast<const double2*>(row + c), v = *reinterpret_cast<const double2*>(row + c + 2);
-                x[kc][0] = u.x, x[kc][1] = u.y, x[kc][2] = v.x, x[kc][3] = v.y;
+                ldg256(row + c, x[kc]);  // one 256-bit streaming load per lane: 1 KB per warp and k-chunk
             } else {
                 x[kc][0] = x[kc][1] = x[kc][2] = x[kc][3] = 0.0;
             }
