@@ -190,6 +190,7 @@ int launch_wsyrk_i8(qexxc_ctx* c, const double* s, long s_bstride, const double*
 int launch_rowquad_mo_i8(qexxc_ctx* c, const double* L, int ldL, int nk, const double* sgn, double* q, long q_bstride, cudaStream_t st);
 double i8_executed_ops(const qexxc_ctx* c, int which, bool sym);
 int i8_prepare_geometry(qexxc_ctx* c, cudaStream_t st);
+int launch_build_aow_i8(qexxc_ctx* c, const double* wv, long wv_cstride, const double* fac4, cudaStream_t st);
 int i8_reserve(qexxc_ctx* c);  // allocate the digit-plane workspace now (qexxc_create), not on first use
 int i8_peak_probe(int device, double* ops_per_second);
 // ao.cu

@@ -1065,6 +1065,10 @@ int launch_wsyrk(qexxc_ctx* c, const double* s, long s_bstride, const double* Bs
 
 int launch_build_aow(qexxc_ctx* c, const double* wv, long wv_bstride, long wv_cstride,
                      const double* fac4, cudaStream_t st) {
+    if (i8_enabled(c) && c->B == 1) {  // INT8 wsyrk follows: aow and its column maxima in one pass
+        const int rc = launch_build_aow_i8(c, wv, wv_cstride, fac4, st);
+        if (rc != QEXXC_ERR_UNSUPPORTED) return rc;
+    }
     const long total2 = (long)c->Gpad * c->Npad / 2;
     const long ao_cs = (long)c->GpadMax * c->Npad, ao_bs = c->ao_shared ? 0 : ao_cs * c->C;
     long blocks = (total2 + 255) / 256;

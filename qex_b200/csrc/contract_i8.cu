@@ -214,6 +214,50 @@ __global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ 
     }
 }
 
+// GGA: aow[g][n] = sum_c f_c wv[c][g] ao[c][g][n] (_scale_ao, numint_legacy.py:432-442) AND, in the same pass, the column
+// maxima of aow 2^rexp[g] per 128-row sub-block (what colmax_kernel would compute from a second read of aow)
+__global__ void __launch_bounds__(256) build_aow_cmax_kernel(const double* __restrict__ ao, long ao_cstride, const double* __restrict__ wv,
+                                                             long wv_cstride, double f0, double f1, double f2, double f3, int ld,
+                                                             int NpadK, const float* __restrict__ rexp, double* __restrict__ aow,
+                                                             float* __restrict__ cmax) {
+    const long g0 = (long)blockIdx.x * 128;
+    __shared__ double rf[128], w4[4][128];
+    if (threadIdx.x < 128) {
+        const long g = g0 + threadIdx.x;
+        rf[threadIdx.x] = pow2((int)rexp[g]);
+        w4[0][threadIdx.x] = f0 * wv[g];
+        w4[1][threadIdx.x] = f1 * wv[wv_cstride + g];
+        w4[2][threadIdx.x] = f2 * wv[2 * wv_cstride + g];
+        w4[3][threadIdx.x] = f3 * wv[3 * wv_cstride + g];
+    }
+    __syncthreads();
+    for (int c = 4 * threadIdx.x; c < NpadK; c += 1024) {
+        double m[4] = {0.0, 0.0, 0.0, 0.0};
+        if (c < ld) {
+#pragma unroll 4
+            for (int r = 0; r < 128; ++r) {
+                const double* p = ao + (g0 + r) * ld + c;
+                double a0[4], a1[4], a2[4], a3[4], o[4];
+                ldg256(p, a0);
+                ldg256(p + ao_cstride, a1);
+                ldg256(p + 2 * ao_cstride, a2);
+                ldg256(p + 3 * ao_cstride, a3);
+                const double w0 = w4[0][r], w1 = w4[1][r], w2 = w4[2][r], w3 = w4[3][r], f = rf[r];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    o[j] = w0 * a0[j] + w1 * a1[j] + w2 * a2[j] + w3 * a3[j];
+                    m[j] = fmax(m[j], f * fabs(o[j]));
+                }
+                double* q = aow + (g0 + r) * ld + c;
+                *reinterpret_cast<double2*>(q) = make_double2(o[0], o[1]);
+                *reinterpret_cast<double2*>(q + 2) = make_double2(o[2], o[3]);
+            }
+        }
+        *reinterpret_cast<float4*>(cmax + (long)blockIdx.x * NpadK + c) =
+            make_float4(__double2float_ru(m[0]), __double2float_ru(m[1]), __double2float_ru(m[2]), __double2float_ru(m[3]));
+    }
+}
+
 // Block exponents of the wsyrk B operand: eexp[blk][col] = e with |s[g] 2^rexp[g] x[g][col]| < 2^e for the (up to) 4096 grid
 // rows of block blk.  Exact (up to float rounding of cmax) without weights; with weights it is the bound
 // max_sub (max_{g in sub} |s[g]| 2^rexp[g]) * cmax[sub][col] over the block's 128-row sub-blocks (tight up to the variation of the
@@ -720,6 +764,7 @@ struct I8Ws {
     float *cmax = nullptr, *cmaxW = nullptr;  // 128-row column maxima of ao_0 / of a general B operand
     int *eA = nullptr, *eB = nullptr;
     int nkc = 0, NpadK = 0, njt = 0, ngcMax = 0, nblkMax = 0;
+    const double* cmaxW_of = nullptr;         // cmaxW currently holds the maxima of this matrix (set by launch_build_aow_i8)
     long plane_stride = 0;
 };
 
@@ -797,6 +842,20 @@ int i8_prepare(qexxc_ctx* c, cudaStream_t st) {
 }  // namespace
 
 int i8_prepare_geometry(qexxc_ctx* c, cudaStream_t st) { return i8_prepare(c, st); }
+
+// GGA: the weighted AO tensor of stage 4 and its 128-row column maxima in one pass (the general wsyrk that follows
+// slices aow without reading it a second time for the maxima)
+int launch_build_aow_i8(qexxc_ctx* c, const double* wv, long wv_cstride, const double* fac4, cudaStream_t st) {
+    QX_TRY(i8_prepare(c, st));
+    I8Ws* w = (I8Ws*)c->i8ws;
+    if (w->T || !w->cmaxW) return QEXXC_ERR_UNSUPPORTED;  // A/B mode with column-scaled A planes: caller uses the plain kernel
+    ProfScope prof(c, QEXXC_PROF_SLICE, st);
+    build_aow_cmax_kernel<<<c->Gpad / 128, 256, 0, st>>>(c->ao, (long)c->GpadMax * c->Npad, wv, wv_cstride, fac4[0], fac4[1], fac4[2],
+                                                        fac4[3], c->Npad, w->NpadK, w->sa, c->aow, w->cmaxW);
+    QX_LAUNCH_CHECK(c);
+    w->cmaxW_of = c->aow;
+    return QEXXC_OK;
+}
 int i8_reserve(qexxc_ctx* c) { return i8_alloc(c); }
 
 void i8_release(qexxc_ctx* c) {
@@ -976,8 +1035,11 @@ static int i8_slice_weighted(qexxc_ctx* c, I8Ws* w, const double* s, const doubl
         QX_LAUNCH_CHECK(c);
         slice_cols_kernel<<<grid, 256, ND * 16384, st>>>(c->ao, c->Npad, s, rexp, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
     } else {
-        colmax_kernel<<<ngc, 256, 0, st>>>(Bsrc, c->Npad, w->NpadK, rexp, w->cmaxW);
-        QX_LAUNCH_CHECK(c);
+        if (w->cmaxW_of != Bsrc || rexp == nullptr) {  // not already produced together with Bsrc (launch_build_aow_i8)
+            colmax_kernel<<<ngc, 256, 0, st>>>(Bsrc, c->Npad, w->NpadK, rexp, w->cmaxW);
+            QX_LAUNCH_CHECK(c);
+        }
+        w->cmaxW_of = nullptr;
         blk_exp_kernel<<<nblk, 256, 0, st>>>(w->cmaxW, nullptr, nullptr, ngc, w->NpadK, w->eB);
         QX_LAUNCH_CHECK(c);
         slice_cols_kernel<<<grid, 256, ND * 16384, st>>>(Bsrc, c->Npad, nullptr, rexp, w->eB, w->NpadK, w->njt, w->plane_stride, w->W);
